@@ -1,0 +1,136 @@
+"""Injector / extractor adapter blocks with the reference's names, signatures and state_dict keys
+(backbones/adapter_blocks.py), running on libasis_b200 kernels."""
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from . import functional as Fn
+from .layers import DropPath  # noqa: F401
+from .ms_deform_attn import MSDeformAttn
+
+
+def get_reference_points(spatial_shapes, device):
+    """Normalised cell centres ((i + .5)/W, (j + .5)/H) per level (:9-22)."""
+    pts = []
+    for H_, W_ in spatial_shapes:
+        ys = torch.linspace(0.5, H_ - 0.5, H_, dtype=torch.float32, device=device) / H_
+        xs = torch.linspace(0.5, W_ - 0.5, W_, dtype=torch.float32, device=device) / W_
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        pts.append(torch.stack((gx.reshape(-1), gy.reshape(-1)), -1)[None])
+    return torch.cat(pts, 1)[:, :, None]
+
+
+_deform_cache = {}
+
+
+def deform_inputs(x, patch_size):
+    """(:24-38).  Static per (h, w, patch, device): computed once and cached (the reference
+    recomputes it every iteration, train.py:275)."""
+    bs, c, h, w = x.shape
+    key = (h, w, patch_size, x.device)
+    hit = _deform_cache.get(key)
+    if hit is not None:
+        return hit
+    pyr = [(h // 8, w // 8), (h // 16, w // 16), (h // 32, w // 32)]
+    grid = [(h // patch_size, w // patch_size)]
+
+    def pack(ref_shapes, val_shapes):
+        ss = torch.as_tensor(val_shapes, dtype=torch.long, device=x.device)
+        lsi = torch.cat((ss.new_zeros((1,)), ss.prod(1).cumsum(0)[:-1]))
+        return [get_reference_points(ref_shapes, x.device), ss, lsi]
+
+    out = (pack(grid, pyr), pack(pyr, grid))
+    _deform_cache[key] = out
+    return out
+
+
+class DWConv(nn.Module):
+    """(:62-80) depth-wise 3x3 over the three pyramid maps stored back to back, token-major."""
+
+    def __init__(self, dim=768):
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+
+    @staticmethod
+    def maps(N, H, W):
+        n = 18 * 18                                   # hard-wired in the reference (:71)
+        maps = [(H * 2 + 1, W * 2 + 1), (H, W), (H // 2, W // 2)]
+        assert maps[0][0] * maps[0][1] == N - 5 * n and maps[1][0] * maps[1][1] == 4 * n and \
+            maps[2][0] * maps[2][1] == n, "DWConv pyramid split only matches 588x588 inputs (reference :71-75)"
+        return maps
+
+    def forward(self, x, H, W, fuse_gelu=False):
+        B, N, C = x.shape
+        return Fn.DWConvFunction.apply(x, self.dwconv.weight, self.dwconv.bias, self.maps(N, H, W), fuse_gelu)
+
+
+class ConvFFN(nn.Module):
+    """(:82-100) fc1 -> dwconv -> GELU -> fc2; GELU is fused into the dwconv kernel."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        if act_layer is not nn.GELU or drop:
+            raise NotImplementedError("ConvFFN: exact GELU and drop=0 only")
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.dwconv = DWConv(hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x, H, W, residual=None):
+        h = Fn.linear(x, self.fc1.weight, self.fc1.bias)
+        h = self.dwconv(h, H, W, fuse_gelu=True)
+        if residual is not None:
+            return Fn.linear(h, self.fc2.weight, self.fc2.bias, residual=residual)
+        return Fn.linear(h, self.fc2.weight, self.fc2.bias, out_dtype=torch.float32)
+
+
+class CACNN(nn.Module):
+    """Extractor (:102-147): c + MSDA(LN c, ref, LN x), then c + ConvFFN(LN c)."""
+
+    def __init__(self, dim, num_heads=6, n_points=4, n_levels=1, deform_ratio=1.0, with_cffn=True, cffn_ratio=0.25,
+                 drop=0.0, drop_path=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), with_cp=False):
+        super().__init__()
+        self.query_norm = norm_layer(dim)
+        self.feat_norm = norm_layer(dim)
+        self.attn = MSDeformAttn(d_model=dim, n_levels=n_levels, n_heads=num_heads, n_points=n_points,
+                                 ratio=deform_ratio)
+        self.with_cffn = with_cffn
+        self.with_cp = with_cp
+        if with_cffn:
+            self.ffn = ConvFFN(in_features=dim, hidden_features=int(dim * cffn_ratio), drop=drop)
+            self.ffn_norm = norm_layer(dim)
+            self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+
+    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index, H, W):
+        qn, fn = self.query_norm, self.feat_norm
+        query = self.attn(Fn.layer_norm(query, qn.weight, qn.bias, qn.eps), reference_points,
+                          Fn.layer_norm(feat, fn.weight, fn.bias, fn.eps), spatial_shapes, level_start_index, None,
+                          gamma=None, residual=query)
+        if self.with_cffn:
+            n = self.ffn_norm
+            query = self.ffn(Fn.layer_norm(query, n.weight, n.bias, n.eps), H, W, residual=query)
+        return query
+
+
+class CAViT(nn.Module):
+    """Injector (:149-183): q + gamma * MSDA(LN q, ref, LN feat); gamma initialised to 0."""
+
+    def __init__(self, dim, num_heads=6, n_points=4, n_levels=1, deform_ratio=1.0,
+                 norm_layer=partial(nn.LayerNorm, eps=1e-6), init_values=0.0, with_cp=False):
+        super().__init__()
+        self.with_cp = with_cp
+        self.query_norm = norm_layer(dim)
+        self.feat_norm = norm_layer(dim)
+        self.attn = MSDeformAttn(d_model=dim, n_levels=n_levels, n_heads=num_heads, n_points=n_points,
+                                 ratio=deform_ratio)
+        self.gamma = nn.Parameter(init_values * torch.ones((dim)), requires_grad=True)
+
+    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index):
+        qn, fn = self.query_norm, self.feat_norm
+        return self.attn(Fn.layer_norm(query, qn.weight, qn.bias, qn.eps), reference_points,
+                         Fn.layer_norm(feat, fn.weight, fn.bias, fn.eps), spatial_shapes, level_start_index, None,
+                         gamma=self.gamma, residual=query)

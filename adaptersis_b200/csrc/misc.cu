@@ -1,0 +1,276 @@
+// misc.cu -- patch gather for the patch-embedding GEMM and the token-major depth-wise 3x3
+// convolution of the extractor's ConvFFN (sm_100a; HBM-bound, 16-byte channel vectors).
+//   patchify <- PatchEmbed.forward (dinov2/layers/patch_embed.py:65-81): stride-p conv == GEMM
+//   dwconv   <- DWConv.forward (backbones/adapter_blocks.py:62-80): the reference transposes each
+//               pyramid level to NCHW, runs cuDNN, transposes back; here the conv runs directly
+//               on the [B, tokens, C] layout (channels are the contiguous dimension).
+#include "common.cuh"
+
+namespace asis {
+
+template <typename OT>
+__global__ void __launch_bounds__(256) patchify_kernel(const float *__restrict__ img, OT *__restrict__ cols, int B, int Cin,
+                                                       int Himg, int Wimg, int patch, int64_t ldk) {
+  const int gh = Himg / patch, gw = Wimg / patch;
+  const int K = Cin * patch * patch;
+  const int64_t total = (int64_t)B * gh * gw * ldk;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int k = (int)(i % ldk);
+  const int64_t row = i / ldk;
+  float v = 0.f;
+  if (k < K) {
+    const int dx = k % patch, dy = (k / patch) % patch, c = k / (patch * patch);
+    const int px = (int)(row % gw), py = (int)((row / gw) % gh), b = (int)(row / ((int64_t)gw * gh));
+    v = img[(((int64_t)b * Cin + c) * Himg + py * patch + dy) * Wimg + px * patch + dx];
+  }
+  cols[i] = from_f<OT>(v);
+}
+
+constexpr int kMaxMaps = 4;
+struct Maps {
+  int n;
+  int h[kMaxMaps], w[kMaxMaps], start[kMaxMaps + 1];
+};
+
+__device__ __forceinline__ int find_map(const Maps &mp, int tok) {
+  int i = 0;
+#pragma unroll
+  for (int k = 1; k < kMaxMaps; ++k)
+    if (k < mp.n && tok >= mp.start[k]) i = k;
+  return i;
+}
+
+// one thread per (b, token, 4 channels)
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T *__restrict__ x, const float *__restrict__ weight,
+                                                         const float *__restrict__ bias, T *__restrict__ pre,
+                                                         T *__restrict__ y, int B, int C, int ntok, Maps mp,
+                                                         int fuse_gelu) {
+  const int cv = C / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * ntok * cv) return;
+  const int c = (int)(i % cv) * 4;
+  const int tok = (int)((i / cv) % ntok);
+  const int b = (int)(i / ((int64_t)cv * ntok));
+  const int mi = find_map(mp, tok);
+  const int W = mp.w[mi], H = mp.h[mi], t0 = mp.start[mi];
+  const int py = (tok - t0) / W, px = (tok - t0) % W;
+  float acc[4];
+  load4(bias + c, acc);
+  const T *xb = x + ((int64_t)b * ntok + t0) * C + c;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int yy = py + dy - 1;
+    if (yy < 0 || yy >= H) continue;
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int xx = px + dx - 1;
+      if (xx < 0 || xx >= W) continue;
+      float v[4];
+      load4(xb + (int64_t)(yy * W + xx) * C, v);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] += v[k] * __ldg(weight + (c + k) * 9 + dy * 3 + dx);
+    }
+  }
+  const int64_t o = ((int64_t)b * ntok + tok) * C + c;
+  if (fuse_gelu) {
+    if (pre) store4(pre + o, acc);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = gelu_erf(acc[k]);
+  }
+  store4(y + o, acc);
+}
+
+// backward: block = 32 channel-lanes (128 channels) x 8 token-lanes; grid (C/128, token blocks).
+// dx per element; per-block partial dweight/dbias -> workspace[block_y][10][C]
+template <typename T>
+__global__ void __launch_bounds__(256) dwconv_bwd_kernel(const T *__restrict__ dy_, const T *__restrict__ pre,
+                                                         const T *__restrict__ x, const float *__restrict__ weight,
+                                                         T *__restrict__ dx_, float *__restrict__ partial, int B, int C,
+                                                         int ntok, Maps mp, int fuse_gelu) {
+  __shared__ float red[8][132];
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  const bool on = c < C;
+  float dw[10][4];
+#pragma unroll
+  for (int j = 0; j < 10; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dw[j][k] = 0.f;
+  float wv[9][4];
+#pragma unroll
+  for (int j = 0; j < 9; ++j)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wv[j][k] = on ? __ldg(weight + (c + k) * 9 + j) : 0.f;
+
+  const int64_t rows = (int64_t)B * ntok;
+  for (int64_t r = (int64_t)blockIdx.y * 8 + ty; r < rows && on; r += (int64_t)gridDim.y * 8) {
+    const int tok = (int)(r % ntok);
+    const int b = (int)(r / ntok);
+    const int mi = find_map(mp, tok);
+    const int W = mp.w[mi], H = mp.h[mi], t0 = mp.start[mi];
+    const int py = (tok - t0) / W, px = (tok - t0) % W;
+    const int64_t base = ((int64_t)b * ntok + t0) * C + c;
+    // gradient w.r.t. the conv output at this token
+    float g[4];
+    load4(dy_ + r * C + c, g);
+    if (fuse_gelu) {
+      float h[4];
+      load4(pre + r * C + c, h);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[k] *= dgelu_erf(h[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dw[9][k] += g[k];
+    float dxv[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+      for (int dxo = 0; dxo < 3; ++dxo) {
+        // weight gradient: input neighbour (py+dy-1, px+dxo-1) times g
+        const int yy = py + dy - 1, xx = px + dxo - 1;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          float v[4];
+          load4(x + base + (int64_t)(yy * W + xx) * C, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dw[dy * 3 + dxo][k] += g[k] * v[k];
+        }
+        // input gradient: output neighbour (py-dy+1, px-dxo+1) used this token with tap (dy, dxo)
+        const int oy = py - dy + 1, ox = px - dxo + 1;
+        if (oy >= 0 && oy < H && ox >= 0 && ox < W) {
+          const int64_t orow = (int64_t)b * ntok + t0 + oy * W + ox;
+          float go[4];
+          load4(dy_ + orow * C + c, go);
+          if (fuse_gelu) {
+            float h[4];
+            load4(pre + orow * C + c, h);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) go[k] *= dgelu_erf(h[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dxv[k] += go[k] * wv[dy * 3 + dxo][k];
+        }
+      }
+    }
+    store4(dx_ + r * C + c, dxv);
+  }
+  float *pp = partial + (size_t)blockIdx.y * 10 * C;
+  for (int j = 0; j < 10; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[ty][lane * 4 + k] = dw[j][k];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+      const int cc = blockIdx.x * 128 + threadIdx.x;
+      if (cc < C) pp[(size_t)j * C + cc] = t;
+    }
+  }
+}
+
+// dweight[c*9+j] / dbias[c] (+)= sum over blocks of partial[p][j][c], fixed order
+__global__ void __launch_bounds__(256) dwconv_reduce_kernel(const float *__restrict__ partial, int nparts, int C,
+                                                            float *__restrict__ dweight, float *__restrict__ dbias,
+                                                            int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 10 * C) return;
+  const int j = i / C, c = i % C;
+  float t = 0.f;
+  for (int p = 0; p < nparts; ++p) t += partial[((size_t)p * 10 + j) * C + c];
+  float *dst = j < 9 ? dweight + c * 9 + j : dbias + c;
+  if (!dst) return;
+  *dst = accumulate ? *dst + t : t;
+}
+
+static int make_maps(Maps &mp, int n_maps, const int *hs, const int *ws) {
+  ASIS_REQUIRE(n_maps >= 1 && n_maps <= kMaxMaps && hs && ws, "dwconv: 1..%d maps required", kMaxMaps);
+  mp.n = n_maps;
+  int s = 0;
+  for (int i = 0; i < kMaxMaps; ++i) {
+    mp.h[i] = i < n_maps ? hs[i] : 1;
+    mp.w[i] = i < n_maps ? ws[i] : 1;
+    mp.start[i] = s;
+    if (i < n_maps) {
+      ASIS_REQUIRE(hs[i] > 0 && ws[i] > 0, "dwconv: empty map");
+      s += hs[i] * ws[i];
+    }
+  }
+  mp.start[kMaxMaps] = s;
+  return ASIS_OK;
+}
+
+static int dwconv_row_blocks(int64_t rows) {
+  int64_t rb = (rows + 63) / 64;
+  if (rb > 256) rb = 256;
+  if (rb < 1) rb = 1;
+  return (int)rb;
+}
+
+}  // namespace asis
+
+using namespace asis;
+
+extern "C" int asis_patchify(const float *img, void *cols, int out_dtype, int B, int Cin, int Himg, int Wimg,
+                             int patch, int64_t ldk, void *stream) {
+  ASIS_REQUIRE(img && cols, "patchify: null pointer");
+  ASIS_REQUIRE(dtype_ok(out_dtype), "patchify: bad dtype");
+  ASIS_REQUIRE(B > 0 && Cin > 0 && patch > 0, "patchify: non-positive dimension");
+  ASIS_REQUIRE(Himg % patch == 0, "Input image height %d is not a multiple of patch height %d", Himg, patch);
+  ASIS_REQUIRE(Wimg % patch == 0, "Input image width %d is not a multiple of patch width: %d", Wimg, patch);
+  ASIS_REQUIRE(ldk >= (int64_t)Cin * patch * patch, "patchify: ldk too small");
+  const int64_t total = (int64_t)B * (Himg / patch) * (Wimg / patch) * ldk;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(out_dtype, OT, (patchify_kernel<OT><<<blocks, 256, 0, st>>>(img, (OT *)cols, B, Cin, Himg, Wimg, patch, ldk)));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_dwconv3x3_forward(const void *x, int dtype, const float *weight, const float *bias, void *pre,
+                                      void *y, int B, int C, int n_maps, const int *hs_host, const int *ws_host,
+                                      int fuse_gelu, void *stream) {
+  ASIS_REQUIRE(x && weight && bias && y, "dwconv_forward: null pointer");
+  ASIS_REQUIRE(dtype_ok(dtype), "dwconv_forward: bad dtype");
+  ASIS_REQUIRE(B > 0 && C > 0 && C % 4 == 0, "dwconv_forward: C=%d must be a positive multiple of 4", C);
+  ASIS_REQUIRE(aligned16(x) && aligned16(y) && aligned16(bias) && (!pre || aligned16(pre)), "dwconv_forward: pointers must be 16-byte aligned");
+  Maps mp;
+  if (int rc = make_maps(mp, n_maps, hs_host, ws_host)) return rc;
+  const int ntok = mp.start[kMaxMaps];
+  const int64_t total = (int64_t)B * ntok * (C / 4);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(dtype, T, (dwconv_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)x, weight, bias, (T *)pre, (T *)y, B, C, ntok, mp, fuse_gelu)));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" size_t asis_dwconv3x3_backward_workspace_bytes(int B, int C, int n_tok) {
+  return (size_t)dwconv_row_blocks((int64_t)B * n_tok) * 10 * C * sizeof(float);
+}
+
+extern "C" int asis_dwconv3x3_backward(const void *dy, const void *pre, const void *x, int dtype, const float *weight,
+                                       void *dx, float *dweight, float *dbias, int accumulate, int B, int C,
+                                       int n_maps, const int *hs_host, const int *ws_host, int fuse_gelu,
+                                       void *workspace, size_t workspace_bytes, void *stream) {
+  ASIS_REQUIRE(dy && x && weight && dx && dweight && dbias && workspace, "dwconv_backward: null pointer");
+  ASIS_REQUIRE(!fuse_gelu || pre, "dwconv_backward: fused GELU needs the saved pre-activation");
+  ASIS_REQUIRE(dtype_ok(dtype), "dwconv_backward: bad dtype");
+  ASIS_REQUIRE(B > 0 && C > 0 && C % 4 == 0, "dwconv_backward: C=%d must be a positive multiple of 4", C);
+  Maps mp;
+  if (int rc = make_maps(mp, n_maps, hs_host, ws_host)) return rc;
+  const int ntok = mp.start[kMaxMaps];
+  const size_t need = asis_dwconv3x3_backward_workspace_bytes(B, C, ntok);
+  if (workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "dwconv_backward: workspace %zu < %zu bytes", workspace_bytes, need);
+  const int rb = dwconv_row_blocks((int64_t)B * ntok);
+  dim3 grid((C + 127) / 128, rb);
+  cudaStream_t st = (cudaStream_t)stream;
+  float *partial = (float *)workspace;
+  ASIS_DISPATCH_DTYPE(dtype, T, (dwconv_bwd_kernel<T><<<grid, 256, 0, st>>>((const T *)dy, (const T *)pre, (const T *)x, weight, (T *)dx, partial, B, C, ntok, mp, fuse_gelu)));
+  ASIS_LAUNCHED();
+  dwconv_reduce_kernel<<<(10 * C + 255) / 256, 256, 0, st>>>(partial, rb, C, dweight, dbias, accumulate);
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}

@@ -1,0 +1,376 @@
+// norm.cu -- LayerNorm forward/backward, column sums, and small elementwise helpers (sm_100a).
+// All HBM-bound: one pass over the data, 16-byte accesses, fixed-order two-stage reductions
+// (deterministic, no float atomics).
+//
+// LayerNorm: nn.LayerNorm(eps=1e-6) of the reference (dinov2/models/vision_transformer.py:89;
+// backbones/adapter_blocks.py:114).  Column sums: bias gradients of nn.Linear and the LayerScale
+// gamma gradient (dinov2/layers/layer_scale.py:26-27).
+#include "common.cuh"
+
+namespace asis {
+
+constexpr int kLnWarps = 8;  // rows in flight per block
+
+// one warp per row; lane owns float4 vectors v = lane + 32*j, j < NV (C <= 128*NV)
+template <typename XT, typename YT, int NV>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const XT *__restrict__ x, const float *__restrict__ gamma,
+                                                                const float *__restrict__ beta, YT *__restrict__ y,
+                                                                float *__restrict__ mean, float *__restrict__ rstd,
+                                                                int R, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const XT *xr = x + (size_t)row * C;
+  float v[NV][4];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 4 * (lane + 32 * j);
+    if (c < C) {
+      load4(xr + c, v[j]);
+      s += v[j][0] + v[j][1] + v[j][2] + v[j][3];
+    } else {
+      v[j][0] = v[j][1] = v[j][2] = v[j][3] = 0.f;
+    }
+  }
+  const float mu = warp_sum(s) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 4 * (lane + 32 * j);
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d = v[j][i] - mu;
+        sq += d * d;
+      }
+    }
+  }
+  const float rs = rsqrtf(warp_sum(sq) / (float)C + eps);
+  if (lane == 0) {
+    if (mean) mean[row] = mu;
+    if (rstd) rstd[row] = rs;
+  }
+  YT *yr = y + (size_t)row * C;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 4 * (lane + 32 * j);
+    if (c < C) {
+      float g[4], b[4], o[4];
+      load4(gamma + c, g);
+      load4(beta + c, b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = (v[j][i] - mu) * rs * g[i] + b[i];
+      store4(yr + c, o);
+    }
+  }
+}
+
+// backward: warps stride over rows; per-lane partial dgamma/dbeta for the lane's columns, block
+// reduction through shared memory, one partial row per block -> workspace[block][2][C]
+template <typename DT, typename XT, int NV>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const DT *__restrict__ dy, const XT *__restrict__ x,
+                                                                const float *__restrict__ gamma,
+                                                                const float *__restrict__ mean,
+                                                                const float *__restrict__ rstd,
+                                                                const float *__restrict__ dres, float *__restrict__ dx,
+                                                                float *__restrict__ partial, int R, int C) {
+  __shared__ float red[kLnWarps][32 * 4 + 4];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float dg[NV][4], db[NV][4], g[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = 4 * (lane + 32 * j);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dg[j][i] = db[j][i] = g[j][i] = 0.f;
+    if (c < C) load4(gamma + c, g[j]);
+  }
+  for (int row = blockIdx.x * kLnWarps + wid; row < R; row += gridDim.x * kLnWarps) {
+    const float mu = mean[row], rs = rstd[row];
+    const DT *dyr = dy + (size_t)row * C;
+    const XT *xr = x + (size_t)row * C;
+    float d[NV][4], xh[NV][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 4 * (lane + 32 * j);
+      if (c < C) {
+        float xv[4];
+        load4(dyr + c, d[j]);
+        load4(xr + c, xv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xh[j][i] = (xv[i] - mu) * rs;
+          dg[j][i] += d[j][i] * xh[j][i];
+          db[j][i] += d[j][i];
+          d[j][i] *= g[j][i];  // d := dy * gamma
+          s1 += d[j][i];
+          s2 += d[j][i] * xh[j][i];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    float *dxr = dx + (size_t)row * C;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = 4 * (lane + 32 * j);
+      if (c < C) {
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = rs * (d[j][i] - s1 - xh[j][i] * s2);
+        if (dres) {
+          float r4[4];
+          load4(dres + (size_t)row * C + c, r4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] += r4[i];
+        }
+        store4(dxr + c, o);
+      }
+    }
+  }
+  // block reduction of the partials, one 128-column strip (index j) at a time
+  float *pg = partial + (size_t)blockIdx.x * 2 * C;
+  float *pb = pg + C;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    for (int pass = 0; pass < 2; ++pass) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) red[wid][lane * 4 + i] = pass == 0 ? dg[j][i] : db[j][i];
+      __syncthreads();
+      if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnWarps; ++w) t += red[w][threadIdx.x];
+        const int c = 128 * j + threadIdx.x;
+        if (c < C) (pass == 0 ? pg : pb)[c] = t;
+      }
+    }
+  }
+}
+
+// out[c] (+)= sum over nparts of partial[p][c], fixed order
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__restrict__ partial, int nparts, int stride,
+                                                              float *__restrict__ out, int n, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float t = 0.f;
+  for (int p = 0; p < nparts; ++p) t += partial[(size_t)p * stride + c];
+  out[c] = accumulate ? out[c] + t : t;
+}
+
+// column sums of X (optionally X*Y): block = 32 lanes x 8 row-lanes, lane owns 4 columns
+template <typename XT, typename YT, bool kMul>
+__global__ void __launch_bounds__(256) colsum_kernel(const XT *__restrict__ X, const YT *__restrict__ Y, int64_t ld,
+                                                     float *__restrict__ partial, int M, int N) {
+  __shared__ float red[8][132];
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  float acc[4] = {0, 0, 0, 0};
+  if (c < N) {
+    for (int r = blockIdx.y * 8 + ty; r < M; r += gridDim.y * 8) {
+      float a[4];
+      load4(X + (size_t)r * ld + c, a);
+      if (kMul) {
+        float b[4];
+        load4(Y + (size_t)r * ld + c, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += a[i] * b[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += a[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) red[ty][lane * 4 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    const int cc = blockIdx.x * 128 + threadIdx.x;
+    if (cc < N) partial[(size_t)blockIdx.y * N + cc] = t;
+  }
+}
+
+template <typename AT, typename OT>
+__global__ void __launch_bounds__(256) scale_cols_kernel(const AT *__restrict__ a, const float *__restrict__ gamma,
+                                                         OT *__restrict__ out, int64_t M, int N) {
+  const int64_t nv = (int64_t)N / 4;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * nv) return;
+  const int c = (int)(i % nv) * 4;
+  float v[4], g[4];
+  load4(a + i * 4, v);
+  load4(gamma + c, g);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) v[k] *= g[k];
+  store4(out + i * 4, v);
+}
+
+template <typename AT, typename BT, typename OT, bool kAdd>
+__global__ void __launch_bounds__(256) add_cast_kernel(const AT *__restrict__ a, const BT *__restrict__ b,
+                                                       OT *__restrict__ out, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float v[4];
+    load4(a + i, v);
+    if (kAdd) {
+      float w[4];
+      load4(b + i, w);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] += w[k];
+    }
+    store4(out + i, v);
+  } else {
+    for (int64_t k = i; k < n; ++k) out[k] = from_f<OT>(to_f(a[k]) + (kAdd ? to_f(b[k]) : 0.f));
+  }
+}
+
+static int ln_nv(int C) {
+  const int nv = (C + 127) / 128;
+  if (nv <= 1) return 1;
+  if (nv <= 2) return 2;
+  if (nv <= 3) return 3;
+  if (nv <= 4) return 4;
+  if (nv <= 6) return 6;
+  if (nv <= 8) return 8;
+  return 0;
+}
+
+static int ln_bwd_blocks(int R) {
+  const int want = (R + kLnWarps - 1) / kLnWarps;
+  return want < 296 ? want : 296;  // 2 x 148 SMs
+}
+
+}  // namespace asis
+
+using namespace asis;
+
+#define LN_NV_SWITCH(nv, ...)                    \
+  switch (nv) {                                  \
+    case 1: { constexpr int NV = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int NV = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int NV = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int NV = 4; __VA_ARGS__; } break; \
+    case 6: { constexpr int NV = 6; __VA_ARGS__; } break; \
+    default: { constexpr int NV = 8; __VA_ARGS__; } break; \
+  }
+
+extern "C" int asis_layernorm_forward(const void *x, int x_dtype, const float *gamma, const float *beta, void *y,
+                                      int y_dtype, float *mean, float *rstd, int R, int C, float eps, void *stream) {
+  ASIS_REQUIRE(x && gamma && beta && y, "layernorm_forward: null pointer");
+  ASIS_REQUIRE(dtype_ok(x_dtype) && dtype_ok(y_dtype), "layernorm_forward: bad dtype");
+  ASIS_REQUIRE(R > 0 && C > 0 && C % 4 == 0, "layernorm_forward: C=%d must be a positive multiple of 4", C);
+  const int nv = ln_nv(C);
+  if (!nv) ASIS_FAIL(ASIS_ERR_UNSUPPORTED, "layernorm_forward: C=%d > 1024 not supported", C);
+  ASIS_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta), "layernorm_forward: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (R + kLnWarps - 1) / kLnWarps;
+  ASIS_DISPATCH_DTYPE(x_dtype, XT, ASIS_DISPATCH_DTYPE(y_dtype, YT, LN_NV_SWITCH(nv, (ln_fwd_kernel<XT, YT, NV><<<blocks, kLnWarps * 32, 0, st>>>((const XT *)x, gamma, beta, (YT *)y, mean, rstd, R, C, eps)))));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" size_t asis_layernorm_backward_workspace_bytes(int R, int C) {
+  return (size_t)ln_bwd_blocks(R) * 2 * C * sizeof(float);
+}
+
+extern "C" int asis_layernorm_backward(const void *dy, int dy_dtype, const void *x, int x_dtype, const float *gamma,
+                                       const float *mean, const float *rstd, const float *dres, float *dx,
+                                       float *dgamma, float *dbeta, int accumulate, int R, int C, void *workspace,
+                                       size_t workspace_bytes, void *stream) {
+  ASIS_REQUIRE(dy && x && gamma && mean && rstd && dx && workspace, "layernorm_backward: null pointer");
+  ASIS_REQUIRE(dtype_ok(dy_dtype) && dtype_ok(x_dtype), "layernorm_backward: bad dtype");
+  ASIS_REQUIRE(R > 0 && C > 0 && C % 4 == 0, "layernorm_backward: C=%d must be a positive multiple of 4", C);
+  const int nv = ln_nv(C);
+  if (!nv) ASIS_FAIL(ASIS_ERR_UNSUPPORTED, "layernorm_backward: C=%d > 1024 not supported", C);
+  const size_t need = asis_layernorm_backward_workspace_bytes(R, C);
+  if (workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "layernorm_backward: workspace %zu < %zu bytes", workspace_bytes, need);
+  ASIS_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(gamma) && aligned16(workspace) && (!dres || aligned16(dres)), "layernorm_backward: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ln_bwd_blocks(R);
+  float *partial = (float *)workspace;
+  ASIS_DISPATCH_DTYPE(dy_dtype, DT, ASIS_DISPATCH_DTYPE(x_dtype, XT, LN_NV_SWITCH(nv, (ln_bwd_kernel<DT, XT, NV><<<blocks, kLnWarps * 32, 0, st>>>((const DT *)dy, (const XT *)x, gamma, mean, rstd, dres, dx, partial, R, C)))));
+  ASIS_LAUNCHED();
+  if (dgamma) {
+    reduce_partials_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial, blocks, 2 * C, dgamma, C, accumulate);
+    ASIS_LAUNCHED();
+  }
+  if (dbeta) {
+    reduce_partials_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial + C, blocks, 2 * C, dbeta, C, accumulate);
+    ASIS_LAUNCHED();
+  }
+  return ASIS_OK;
+}
+
+static int colsum_rb(int M) {
+  int rb = (M + 63) / 64;
+  if (rb > 128) rb = 128;
+  if (rb < 1) rb = 1;
+  return rb;
+}
+
+extern "C" size_t asis_colsum_workspace_bytes(int M, int N) { return (size_t)colsum_rb(M) * N * sizeof(float); }
+
+extern "C" int asis_colsum(const void *X, int x_dtype, const void *Y, int y_dtype, int64_t ld, float *out,
+                           int accumulate, int M, int N, void *workspace, size_t workspace_bytes, void *stream) {
+  ASIS_REQUIRE(X && out && workspace, "colsum: null pointer");
+  ASIS_REQUIRE(dtype_ok(x_dtype) && (!Y || dtype_ok(y_dtype)), "colsum: bad dtype");
+  ASIS_REQUIRE(M > 0 && N > 0 && N % 4 == 0 && ld % 4 == 0 && ld >= N, "colsum: N=%d and ld must be multiples of 4", N);
+  const size_t need = asis_colsum_workspace_bytes(M, N);
+  if (workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "colsum: workspace %zu < %zu bytes", workspace_bytes, need);
+  ASIS_REQUIRE(aligned16(X) && (!Y || aligned16(Y)), "colsum: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rb = colsum_rb(M);
+  dim3 grid((N + 127) / 128, rb);
+  float *partial = (float *)workspace;
+  if (Y) {
+    ASIS_DISPATCH_DTYPE(x_dtype, XT, ASIS_DISPATCH_DTYPE(y_dtype, YT, (colsum_kernel<XT, YT, true><<<grid, 256, 0, st>>>((const XT *)X, (const YT *)Y, ld, partial, M, N))));
+  } else {
+    ASIS_DISPATCH_DTYPE(x_dtype, XT, (colsum_kernel<XT, float, false><<<grid, 256, 0, st>>>((const XT *)X, nullptr, ld, partial, M, N)));
+  }
+  ASIS_LAUNCHED();
+  reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, rb, N, out, N, accumulate);
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_scale_cols(const void *a, int a_dtype, const float *gamma, void *out, int out_dtype, int64_t M,
+                               int N, void *stream) {
+  ASIS_REQUIRE(a && gamma && out, "scale_cols: null pointer");
+  ASIS_REQUIRE(dtype_ok(a_dtype) && dtype_ok(out_dtype), "scale_cols: bad dtype");
+  ASIS_REQUIRE(M > 0 && N > 0 && N % 4 == 0, "scale_cols: N=%d must be a multiple of 4", N);
+  ASIS_REQUIRE(aligned16(a) && aligned16(out) && aligned16(gamma), "scale_cols: pointers must be 16-byte aligned");
+  const int64_t total = M * (N / 4);
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(a_dtype, AT, ASIS_DISPATCH_DTYPE(out_dtype, OT, (scale_cols_kernel<AT, OT><<<blocks, 256, 0, st>>>((const AT *)a, gamma, (OT *)out, M, N))));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_add(const void *a, int a_dtype, const void *b, int b_dtype, void *out, int out_dtype, int64_t n,
+                        void *stream) {
+  ASIS_REQUIRE(a && b && out && n > 0, "add: null pointer or empty");
+  ASIS_REQUIRE(dtype_ok(a_dtype) && dtype_ok(b_dtype) && dtype_ok(out_dtype), "add: bad dtype");
+  ASIS_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out), "add: pointers must be 16-byte aligned");
+  const unsigned blocks = (unsigned)(((n + 3) / 4 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(a_dtype, AT, ASIS_DISPATCH_DTYPE(b_dtype, BT, ASIS_DISPATCH_DTYPE(out_dtype, OT, (add_cast_kernel<AT, BT, OT, true><<<blocks, 256, 0, st>>>((const AT *)a, (const BT *)b, (OT *)out, n)))));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_cast(const void *a, int a_dtype, void *out, int out_dtype, int64_t n, void *stream) {
+  ASIS_REQUIRE(a && out && n > 0, "cast: null pointer or empty");
+  ASIS_REQUIRE(dtype_ok(a_dtype) && dtype_ok(out_dtype), "cast: bad dtype");
+  ASIS_REQUIRE(aligned16(a) && aligned16(out), "cast: pointers must be 16-byte aligned");
+  const unsigned blocks = (unsigned)(((n + 3) / 4 + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(a_dtype, AT, ASIS_DISPATCH_DTYPE(out_dtype, OT, (add_cast_kernel<AT, AT, OT, false><<<blocks, 256, 0, st>>>((const AT *)a, nullptr, (OT *)out, n))));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}

@@ -1,0 +1,99 @@
+"""Data-parallel plumbing: one process per GPU, parameters replicated, batch sharded, gradients
+all-reduced in buckets over NCCL (NVLink 5 / NVSwitch) on a side stream while backward is still
+running -- the only collective the path has (reference: four
+DistributedDataParallel wrappers, train.py:84,96,112,116).
+
+Buckets are formed in reverse parameter-registration order (the order backward produces
+gradients); a bucket is reduced as soon as all its gradients have been accumulated
+(post-accumulate-grad hooks).  Works with any torch.distributed backend (gloo on CPU for tests)."""
+import torch
+import torch.distributed as dist
+
+
+class BucketedGradAllReduce:
+    def __init__(self, params, bucket_bytes=64 << 20, process_group=None, average=True):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.average = average
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        self.buckets = []
+        cur, cur_bytes = [], 0
+        for p in reversed(self.params):
+            nb = p.numel() * 4
+            if cur and cur_bytes + nb > bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nb
+        if cur:
+            self.buckets.append(cur)
+        self._bucket_of = {id(p): i for i, b in enumerate(self.buckets) for p in b}
+        self._pending = [0] * len(self.buckets)
+        self._flat = [None] * len(self.buckets)
+        self._works = []
+        self._comm_stream = None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self.reset()
+
+    def reset(self):
+        self._pending = [len(b) for b in self.buckets]
+        self._works = []
+
+    def _stream(self, device):
+        if device.type != "cuda":
+            return None
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device)
+        return self._comm_stream
+
+    def _on_grad(self, p):
+        i = self._bucket_of[id(p)]
+        self._pending[i] -= 1
+        if self._pending[i] == 0:
+            self._launch(i)
+
+    def _launch(self, i):
+        if self.world == 1:
+            return
+        bucket = self.buckets[i]
+        dev = bucket[0].device
+        n = sum(p.numel() for p in bucket)
+        if self._flat[i] is None:
+            self._flat[i] = torch.empty(n, dtype=torch.float32, device=dev)
+        flat = self._flat[i]
+        side = self._stream(dev)
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream(dev))
+            ctx = torch.cuda.stream(side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            torch._foreach_copy_(list(flat.split([p.numel() for p in bucket])), [p.grad.reshape(-1).float() for p in bucket])
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._works.append((i, work))
+
+    def finish(self):
+        """Wait for all buckets, write the reduced (averaged) gradients back."""
+        if self.world == 1:
+            self.reset()
+            return
+        # parameters that never received a gradient this step leave their bucket unreduced
+        for i, left in enumerate(self._pending):
+            if left != 0 and left != len(self.buckets[i]):
+                raise RuntimeError("gradient bucket partially filled: unused parameters in a bucket")
+        for i, work in self._works:
+            work.wait()
+            bucket = self.buckets[i]
+            flat = self._flat[i]
+            if self.average:
+                flat.div_(self.world)
+            for p, chunk in zip(bucket, flat.split([p.numel() for p in bucket])):
+                p.grad.copy_(chunk.view_as(p.grad))
+        if self._comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        self.reset()
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()

@@ -1,0 +1,261 @@
+"""Tensor-level wrappers over the C ABI (no autograd here).  Each function allocates its outputs
+with torch (device memory is PyTorch's job), passes raw pointers + sizes + the current CUDA stream
+to libasis_b200.so and returns.  Argument order follows include/asis_b200.h."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (BF16, EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_SCALE_RESIDUAL, F32, MAJOR_K,
+                   MAJOR_MN, check, dt, need_cuda, ptr, stream, workspace)
+
+TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------ MSDA
+def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights):
+    need_cuda(value, spatial_shapes, level_start_index, sampling_locations, attention_weights)
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    value = _c(value)
+    loc = _c(sampling_locations.float())
+    aw = _c(attention_weights.float())
+    ss = _c(spatial_shapes.to(torch.int64))
+    lsi = _c(level_start_index.to(torch.int64))
+    out = torch.empty(N, Lq, M * D, dtype=value.dtype, device=value.device)
+    check(_lib.load().asis_msda_forward(ptr(value), dt(value), ptr(ss), ptr(lsi), ptr(loc), ptr(aw), ptr(out),
+                                        dt(out), N, S, M, D, Lq, L, P, stream()))
+    return out
+
+
+def msda_backward(value, spatial_shapes, level_start_index, sampling_locations, attention_weights, grad_out):
+    need_cuda(value, grad_out)
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    lib = _lib.load()
+    value = _c(value)
+    loc = _c(sampling_locations.float())
+    aw = _c(attention_weights.float())
+    ss = _c(spatial_shapes.to(torch.int64))
+    lsi = _c(level_start_index.to(torch.int64))
+    grad_out = _c(grad_out.to(value.dtype))
+    gv = torch.empty_like(value)
+    gl = torch.empty_like(loc)
+    ga = torch.empty_like(aw)
+    nbytes = lib.asis_msda_backward_workspace_bytes(N, S, M, D, Lq, L, P)
+    ws = workspace(nbytes, value.device)
+    check(lib.asis_msda_backward(ptr(value), dt(value), ptr(ss), ptr(lsi), ptr(loc), ptr(aw), ptr(grad_out),
+                                 dt(grad_out), ptr(gv), ptr(gl), ptr(ga), N, S, M, D, Lq, L, P, ptr(ws), nbytes,
+                                 stream()))
+    return gv, gl, ga
+
+
+def _ref_layout(reference_points, R, Lq, L):
+    ref = _c(reference_points.float())
+    rows = ref.shape[0] * ref.shape[1]
+    if rows not in (R, Lq):
+        raise RuntimeError(f"reference_points rows {tuple(reference_points.shape)} do not match queries")
+    return ref, rows, ref.shape[2], ref.shape[3]
+
+
+def msda_prep_forward(offsets, logits, reference_points, spatial_shapes, N, Lq, M, L, P):
+    """offsets [N,Lq,M*L*P*2], logits [N,Lq,M*L*P] -> loc [N,Lq,M,L,P,2], attn [N,Lq,M,L,P] (f32)."""
+    need_cuda(offsets, logits, reference_points)
+    R = N * Lq
+    if reference_points.shape[-1] not in (2, 4):
+        raise ValueError(
+            "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
+    ref, rows, rl, rd = _ref_layout(reference_points, R, Lq, L)
+    offsets = _c(offsets)
+    logits = _c(logits.to(offsets.dtype))
+    ss = _c(spatial_shapes.to(torch.int64))
+    loc = torch.empty(N, Lq, M, L, P, 2, dtype=torch.float32, device=offsets.device)
+    attn = torch.empty(N, Lq, M, L, P, dtype=torch.float32, device=offsets.device)
+    check(_lib.load().asis_msda_prep_forward(ptr(offsets), ptr(logits), dt(offsets), ptr(ref), rows, rl, rd,
+                                             ptr(ss), ptr(loc), ptr(attn), R, Lq, M, L, P, stream()))
+    return loc, attn
+
+
+def msda_prep_backward(grad_loc, grad_attn, attn, reference_points, spatial_shapes, out_dtype, N, Lq, M, L, P):
+    R = N * Lq
+    ref, rows, rl, rd = _ref_layout(reference_points, R, Lq, L)
+    ss = _c(spatial_shapes.to(torch.int64))
+    goff = torch.empty(N, Lq, M * L * P * 2, dtype=out_dtype, device=attn.device)
+    glog = torch.empty(N, Lq, M * L * P, dtype=out_dtype, device=attn.device)
+    check(_lib.load().asis_msda_prep_backward(ptr(_c(grad_loc)), ptr(_c(grad_attn)), ptr(attn), ptr(ref), rows, rl,
+                                              rd, ptr(ss), ptr(goff), ptr(glog), dt(goff), R, Lq, M, L, P,
+                                              stream()))
+    return goff, glog
+
+
+# ------------------------------------------------------------------------------------- LayerNorm
+def layernorm_forward(x2d, weight, bias, eps, out_dtype):
+    need_cuda(x2d, weight, bias)
+    R, C = x2d.shape
+    x2d = _c(x2d)
+    y = torch.empty(R, C, dtype=out_dtype, device=x2d.device)
+    mean = torch.empty(R, dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty(R, dtype=torch.float32, device=x2d.device)
+    check(_lib.load().asis_layernorm_forward(ptr(x2d), dt(x2d), ptr(weight), ptr(bias), ptr(y), dt(y), ptr(mean),
+                                             ptr(rstd), R, C, float(eps), stream()))
+    return y, mean, rstd
+
+
+def layernorm_backward(dy2d, x2d, weight, mean, rstd, dres=None, want_param_grads=True):
+    """dx (f32) = dres + LN'(dy); returns dx, dweight, dbias (f32 or None)."""
+    R, C = x2d.shape
+    lib = _lib.load()
+    dy2d = _c(dy2d)
+    dx = torch.empty(R, C, dtype=torch.float32, device=x2d.device)
+    dw = torch.empty(C, dtype=torch.float32, device=x2d.device) if want_param_grads else None
+    db = torch.empty(C, dtype=torch.float32, device=x2d.device) if want_param_grads else None
+    nbytes = lib.asis_layernorm_backward_workspace_bytes(R, C)
+    ws = workspace(nbytes, x2d.device)
+    if dres is not None:
+        dres = _c(dres.float())
+    check(lib.asis_layernorm_backward(ptr(dy2d), dt(dy2d), ptr(x2d), dt(x2d), ptr(weight), ptr(mean), ptr(rstd),
+                                      ptr(dres), ptr(dx), ptr(dw), ptr(db), 0, R, C, ptr(ws), nbytes, stream()))
+    return dx, dw, db
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm(compute, A, a_major, B, b_major, M, N, K, out_dtype, epilogue=EPI_NONE, bias=None, gamma=None,
+         residual=None, aux=None, out=None, want_aux_dtype=None):
+    """C[M,N] = epi(sum_k A[m,k] B[n,k]).  A/B are 2-D row-major tensors whose contiguous dimension
+    is K (major K) or the M/N dimension (major MN).  Returns (C, aux)."""
+    need_cuda(A, B)
+    A = _c(A)
+    B = _c(B)
+    dev = A.device
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=dev)
+    if epilogue in (EPI_GELU, EPI_SCALE_RESIDUAL) and aux is None and want_aux_dtype is not None:
+        aux = torch.empty(M, N, dtype=want_aux_dtype, device=dev)
+    if residual is not None:
+        residual = _c(residual)
+        assert residual.dtype == torch.float32 and residual.shape[-1] == N
+    check(_lib.load().asis_gemm(compute, ptr(A), a_major, A.stride(0), ptr(B), b_major, B.stride(0), ptr(out),
+                                dt(out), out.stride(0), M, N, K, epilogue, ptr(bias), ptr(gamma), ptr(residual),
+                                ptr(aux), dt(aux) if aux is not None else 0, aux.stride(0) if aux is not None else 0,
+                                stream()))
+    return out, aux
+
+
+def colsum(X2d, Y2d=None, out=None, accumulate=False):
+    need_cuda(X2d)
+    M, N = X2d.shape
+    lib = _lib.load()
+    X2d = _c(X2d)
+    if Y2d is not None:
+        Y2d = _c(Y2d)
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=X2d.device)
+    nbytes = lib.asis_colsum_workspace_bytes(M, N)
+    ws = workspace(nbytes, X2d.device)
+    check(lib.asis_colsum(ptr(X2d), dt(X2d), ptr(Y2d), dt(Y2d) if Y2d is not None else 0, X2d.stride(0), ptr(out),
+                          int(accumulate), M, N, ptr(ws), nbytes, stream()))
+    return out
+
+
+def scale_cols(a2d, gamma, out_dtype):
+    M, N = a2d.shape
+    a2d = _c(a2d)
+    out = torch.empty(M, N, dtype=out_dtype, device=a2d.device)
+    check(_lib.load().asis_scale_cols(ptr(a2d), dt(a2d), ptr(gamma), ptr(out), dt(out), M, N, stream()))
+    return out
+
+
+def add(a, b, out_dtype):
+    a = _c(a)
+    b = _c(b)
+    out = torch.empty(a.shape, dtype=out_dtype, device=a.device)
+    check(_lib.load().asis_add(ptr(a), dt(a), ptr(b), dt(b), ptr(out), dt(out), a.numel(), stream()))
+    return out
+
+
+def cast(a, out_dtype):
+    if a.dtype == out_dtype:
+        return a
+    a = _c(a)
+    out = torch.empty(a.shape, dtype=out_dtype, device=a.device)
+    check(_lib.load().asis_cast(ptr(a), dt(a), ptr(out), dt(out), a.numel(), stream()))
+    return out
+
+
+# ------------------------------------------------------------------------------------- attention
+def attention_forward(compute, qkv, B, T, H, hd):
+    """qkv [B,T,3*H*hd] (packed [3,H,hd]) -> out [B,T,H*hd], lse [B,H,T]."""
+    need_cuda(qkv)
+    lib = _lib.load()
+    qkv = _c(qkv)
+    out = torch.empty(B, T, H * hd, dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
+    nbytes = lib.asis_attention_forward_workspace_bytes(compute, B, T, H, hd)
+    ws = workspace(nbytes, qkv.device)
+    check(lib.asis_attention_forward(compute, ptr(qkv), ptr(out), ptr(lse), B, T, H, hd, ptr(ws), nbytes, stream()))
+    return out, lse
+
+
+def attention_backward(compute, qkv, out, lse, dout, B, T, H, hd):
+    lib = _lib.load()
+    dout = _c(dout.to(qkv.dtype))
+    dqkv = torch.empty_like(qkv)
+    nbytes = lib.asis_attention_backward_workspace_bytes(compute, B, T, H, hd)
+    ws = workspace(nbytes, qkv.device)
+    check(lib.asis_attention_backward(compute, ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), B, T, H, hd,
+                                      ptr(ws), nbytes, stream()))
+    return dqkv
+
+
+# ---------------------------------------------------------------------------------- front / conv
+def patchify(img, patch, out_dtype, ldk):
+    need_cuda(img)
+    B, Cin, H, W = img.shape
+    if H % patch != 0:
+        raise AssertionError(f"Input image height {H} is not a multiple of patch height {patch}")
+    if W % patch != 0:
+        raise AssertionError(f"Input image width {W} is not a multiple of patch width: {patch}")
+    img = _c(img.float())
+    cols = torch.empty(B * (H // patch) * (W // patch), ldk, dtype=out_dtype, device=img.device)
+    check(_lib.load().asis_patchify(ptr(img), ptr(cols), dt(cols), B, Cin, H, W, patch, ldk, stream()))
+    return cols
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*vals)
+
+
+def dwconv3x3_forward(x, weight, bias, maps, fuse_gelu, save_pre):
+    """x [B, n_tok, C]; maps = [(h, w), ...] back to back along n_tok."""
+    need_cuda(x, weight, bias)
+    B, ntok, C = x.shape
+    assert sum(h * w for h, w in maps) == ntok
+    x = _c(x)
+    y = torch.empty_like(x)
+    pre = torch.empty_like(x) if (fuse_gelu and save_pre) else None
+    hs = _int_array([h for h, _ in maps])
+    ws_ = _int_array([w for _, w in maps])
+    check(_lib.load().asis_dwconv3x3_forward(ptr(x), dt(x), ptr(_c(weight.float())), ptr(_c(bias.float())), ptr(pre),
+                                             ptr(y), B, C, len(maps), hs, ws_, int(fuse_gelu), stream()))
+    return y, pre
+
+
+def dwconv3x3_backward(dy, pre, x, weight, maps, fuse_gelu):
+    B, ntok, C = x.shape
+    lib = _lib.load()
+    dy = _c(dy.to(x.dtype))
+    dx = torch.empty_like(x)
+    dw = torch.empty(C, 1, 3, 3, dtype=torch.float32, device=x.device)
+    db = torch.empty(C, dtype=torch.float32, device=x.device)
+    hs = _int_array([h for h, _ in maps])
+    ws_ = _int_array([w for _, w in maps])
+    nbytes = lib.asis_dwconv3x3_backward_workspace_bytes(B, C, ntok)
+    ws = workspace(nbytes, x.device)
+    check(lib.asis_dwconv3x3_backward(ptr(dy), ptr(pre), ptr(x), dt(x), ptr(_c(weight.float())), ptr(dx), ptr(dw),
+                                      ptr(db), 0, B, C, len(maps), hs, ws_, int(fuse_gelu), ptr(ws), nbytes,
+                                      stream()))
+    return dx, dw, db

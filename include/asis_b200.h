@@ -1,0 +1,198 @@
+/* asis_b200.h -- C ABI of libasis_b200.so: the B200 (sm_100a) kernels behind the AdapterSIS
+ * encoder hot path.
+ *
+ * The reference (weimengmeng1999/AdapterSIS) has no native boundary at all: its deformable
+ * attention "op" is a Python loop over F.grid_sample (backbones/ops/modules/ms_deform_attn.py:33-54)
+ * and every dense op is an nn.Module calling ATen.  The historical native boundary of this op
+ * family is MSDeformAttnFunction.apply (ms_deform_attn.py:17-30, call site :176-183); this header
+ * is what a replacement for that boundary -- and for the dense ops next to it -- exports.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named *_host;
+ *   - the caller owns every buffer, including workspaces (sized by the matching
+ *     *_workspace_bytes function); nothing here allocates or frees device memory;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point
+ *     synchronises; the library is re-entrant across streams;
+ *   - return value 0 = enqueued; negative = ASIS_ERR_*; asis_last_error() returns a
+ *     thread-local, human-readable message for the last failure on the calling thread;
+ *   - dtype arguments: ASIS_F32 = 0, ASIS_BF16 = 1.  "compute mode" ASIS_F32 uses fp32 FFMA
+ *     kernels (parity mode, 1e-4), ASIS_BF16 uses tcgen05 tensor-core kernels with bf16
+ *     operands and fp32 accumulation (performance mode, 2e-2).
+ */
+#ifndef ASIS_B200_H_
+#define ASIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASIS_ABI_VERSION 1
+
+enum { ASIS_F32 = 0, ASIS_BF16 = 1 };
+
+enum {
+  ASIS_OK = 0,
+  ASIS_ERR_INVALID = -1,   /* bad argument (shape, dtype, alignment, null pointer) */
+  ASIS_ERR_WORKSPACE = -2, /* workspace too small */
+  ASIS_ERR_CUDA = -3,      /* a CUDA runtime / driver call failed */
+  ASIS_ERR_UNSUPPORTED = -4
+};
+
+/* Operand majors for asis_gemm (which dimension is contiguous in memory). */
+enum { ASIS_MAJOR_K = 0, ASIS_MAJOR_MN = 1 };
+
+/* Epilogues for asis_gemm.  acc = sum_k A[m,k]*B[n,k] (fp32). */
+enum {
+  ASIS_EPI_NONE = 0,          /* C = acc (+ bias)                                             */
+  ASIS_EPI_GELU = 1,          /* aux = acc + bias (pre-activation, optional); C = gelu_erf(aux) */
+  ASIS_EPI_SCALE_RESIDUAL = 2,/* aux = acc + bias (optional); C = residual + gamma[n] * aux     */
+  ASIS_EPI_DGELU = 3,         /* C = acc * gelu_erf'(aux_in)      (aux is an INPUT here)        */
+  ASIS_EPI_ACCUMULATE = 4     /* C += acc   (fp32 C only; weight-gradient accumulation)       */
+};
+
+int asis_abi_version(void);
+const char *asis_last_error(void);
+/* Number of kernels this library has launched on the calling process since load (bench.py's
+ * gpu_launches claim is read from here). */
+uint64_t asis_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention  --  replaces ms_deform_attn_core_pytorch
+ * (ms_deform_attn.py:33-54) behind MSDeformAttnFunction.apply (:17-30).
+ *
+ *   value            [N, S, M, D]          value_dtype (f32 | bf16)
+ *   spatial_shapes   [L, 2] int64 (H, W)   device memory, as the reference passes it
+ *   level_start      [L]    int64          device memory (the reference ignores it, :26; here it
+ *                                          is used, so it must be the exclusive cumsum of H*W)
+ *   sampling_loc     [N, Lq, M, L, P, 2]   f32, (x, y) normalised to [0,1]
+ *   attn_weight      [N, Lq, M, L, P]      f32
+ *   out              [N, Lq, M*D]          out_dtype
+ * Pixel coordinate = loc * size - 0.5, bilinear, zero padding (grid_sample align_corners=False).
+ * D must be a multiple of 4 (f32) / 8 (bf16); L <= 8; L*P <= 64.
+ * ------------------------------------------------------------------------------------------ */
+int asis_msda_forward(const void *value, int value_dtype, const int64_t *spatial_shapes,
+                      const int64_t *level_start, const float *sampling_loc,
+                      const float *attn_weight, void *out, int out_dtype, int N, int S, int M,
+                      int D, int Lq, int L, int P, void *stream);
+
+/* Backward (the reference's Function has none; semantics = autograd through the
+ * reference core).  Atomic-free and run-to-run deterministic: contributions to grad_value are
+ * bucketed per value pixel (counting sort), ordered, then reduced by one thread group per pixel.
+ *   grad_out     [N, Lq, M*D]  gdtype      grad_value  [N, S, M, D]  gdtype (fully overwritten)
+ *   grad_loc     [N, Lq, M, L, P, 2] f32   grad_attn   [N, Lq, M, L, P] f32
+ */
+size_t asis_msda_backward_workspace_bytes(int N, int S, int M, int D, int Lq, int L, int P);
+int asis_msda_backward(const void *value, int value_dtype, const int64_t *spatial_shapes,
+                       const int64_t *level_start, const float *sampling_loc,
+                       const float *attn_weight, const void *grad_out, int gdtype,
+                       void *grad_value, float *grad_loc, float *grad_attn, int N, int S, int M,
+                       int D, int Lq, int L, int P, void *workspace, size_t workspace_bytes,
+                       void *stream);
+
+/* Fused softmax(L*P) + sampling-location arithmetic of MSDeformAttn.forward (:156-171):
+ *   logits [R, M*L*P] -> attn [R, M, L, P] = softmax over L*P;
+ *   offsets [R, M, L, P, 2] + reference points -> loc = ref + off / (W_l, H_l)     (ref_dim 2)
+ *                                                 loc = ref.xy + off / P * ref.wh * 0.5 (ref_dim 4)
+ *   ref [Rr, Lr, ref_dim] with Rr in {R, Lq} (broadcast over batch) and Lr in {L, 1}.
+ * and its backward (grad_loc, grad_attn -> grad_offsets, grad_logits). */
+int asis_msda_prep_forward(const void *offsets, const void *logits, int in_dtype, const float *ref,
+                           int ref_rows, int ref_levels, int ref_dim, const int64_t *spatial_shapes,
+                           float *loc, float *attn, int R, int Lq, int M, int L, int P, void *stream);
+int asis_msda_prep_backward(const float *grad_loc, const float *grad_attn, const float *attn,
+                            const float *ref, int ref_rows, int ref_levels, int ref_dim,
+                            const int64_t *spatial_shapes, void *grad_offsets, void *grad_logits,
+                            int out_dtype, int R, int Lq, int M, int L, int P, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LayerNorm (nn.LayerNorm(eps=1e-6): dinov2/models/vision_transformer.py:89,
+ * backbones/adapter_blocks.py:114,118-119,127,163-164).
+ *   x [R, C] x_dtype -> y [R, C] y_dtype; mean/rstd [R] f32 saved for backward.
+ * Backward: dx = (dres ? dres : 0) + LN'(dy); partial dgamma/dbeta in workspace, reduced in
+ * fixed order (deterministic) into dgamma/dbeta (accumulate != 0 adds to existing contents).
+ * ------------------------------------------------------------------------------------------ */
+int asis_layernorm_forward(const void *x, int x_dtype, const float *gamma, const float *beta,
+                           void *y, int y_dtype, float *mean, float *rstd, int R, int C, float eps,
+                           void *stream);
+size_t asis_layernorm_backward_workspace_bytes(int R, int C);
+int asis_layernorm_backward(const void *dy, int dy_dtype, const void *x, int x_dtype,
+                            const float *gamma, const float *mean, const float *rstd,
+                            const float *dres, float *dx, float *dgamma, float *dbeta,
+                            int accumulate, int R, int C, void *workspace, size_t workspace_bytes,
+                            void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense contraction  C[M,N] = epilogue( sum_k A[m,k] * B[n,k] )        (nn.Linear and its grads)
+ *   compute ASIS_BF16: A, B bf16; tcgen05.mma (kind::f16) with TMA-fed 128B-swizzled tiles,
+ *                      fp32 accumulators in TMEM.  lda/ldb/ldc in elements; pointers 16-byte
+ *                      aligned, leading dimensions multiples of 8.
+ *   compute ASIS_F32 : A, B f32; FFMA tiles (parity mode).
+ *   a_major/b_major: ASIS_MAJOR_K  -> operand stored [rows, K] (K contiguous, ld = row pitch)
+ *                    ASIS_MAJOR_MN -> operand stored [K, rows] (rows contiguous, ld = k pitch)
+ *   bias [N] f32 (nullable), gamma [N] f32, residual [M, ldc] f32, aux [M, ldaux] aux_dtype.
+ *   Forward Linear: A=x(K-major), B=W[out,in](K-major).  dgrad: A=dy(K), B=W(MN).
+ *   wgrad: A=dy(MN), B=x(MN), epilogue ACCUMULATE.
+ * ------------------------------------------------------------------------------------------ */
+int asis_gemm(int compute, const void *A, int a_major, int64_t lda, const void *B, int b_major,
+              int64_t ldb, void *C, int c_dtype, int64_t ldc, int M, int N, int K, int epilogue,
+              const float *bias, const float *gamma, const float *residual, void *aux,
+              int aux_dtype, int64_t ldaux, void *stream);
+
+/* Column sums (bias gradients): out[n] (+)= sum_m X[m, n];  optionally of X*Y elementwise
+ * (LayerScale gamma gradient, dinov2/layers/layer_scale.py:26-27).  Deterministic two-stage. */
+size_t asis_colsum_workspace_bytes(int M, int N);
+int asis_colsum(const void *X, int x_dtype, const void *Y, int y_dtype, int64_t ld, float *out,
+                int accumulate, int M, int N, void *workspace, size_t workspace_bytes,
+                void *stream);
+
+/* Elementwise helpers: out = a * gamma[n] (LayerScale backward, cast), out = a + b, casts. */
+int asis_scale_cols(const void *a, int a_dtype, const float *gamma, void *out, int out_dtype,
+                    int64_t M, int N, void *stream);
+int asis_add(const void *a, int a_dtype, const void *b, int b_dtype, void *out, int out_dtype,
+             int64_t n, void *stream);
+int asis_cast(const void *a, int a_dtype, void *out, int out_dtype, int64_t n, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Self-attention over packed qkv  (dinov2/layers/attention.py:56-69 / :73-89)
+ *   qkv [B, T, 3, H, hd] -> out [B, T, H*hd];  softmax((q*hd^-0.5) k^T) v, no mask, no dropout.
+ *   lse [B, H, T] f32 saved for backward.
+ *   compute ASIS_BF16: flash-style tcgen05 kernel, hd == 64.
+ *   compute ASIS_F32 : FFMA kernel, any hd <= 128 (parity mode).
+ * Backward: dqkv [B, T, 3, H, hd] fully overwritten.
+ * ------------------------------------------------------------------------------------------ */
+size_t asis_attention_forward_workspace_bytes(int compute, int B, int T, int H, int hd);
+int asis_attention_forward(int compute, const void *qkv, void *out, float *lse, int B, int T,
+                           int H, int hd, void *workspace, size_t workspace_bytes, void *stream);
+size_t asis_attention_backward_workspace_bytes(int compute, int B, int T, int H, int hd);
+int asis_attention_backward(int compute, const void *qkv, const void *out, const float *lse,
+                            const void *dout, void *dqkv, int B, int T, int H, int hd,
+                            void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Patch embedding front end (dinov2/layers/patch_embed.py:65-81): gather p x p patches of an
+ * NCHW f32 image into rows [B*gh*gw, ldk] (k = c*p*p + dy*p + dx, zero padded to ldk) so that
+ * the stride-p convolution becomes asis_gemm; and its transpose for the input gradient.
+ * ------------------------------------------------------------------------------------------ */
+int asis_patchify(const float *img, void *cols, int out_dtype, int B, int Cin, int Himg, int Wimg,
+                  int patch, int64_t ldk, void *stream);
+
+/* Depth-wise 3x3 convolution over token-major pyramids (backbones/adapter_blocks.py:62-80):
+ *   x [B, n_tok, C] holding `n_maps` maps back to back (map i is hs[i] x ws[i]); stride 1, pad 1,
+ *   weight [C, 3, 3] f32, bias [C] f32; optional fused exact GELU on the output.
+ *   hs_host/ws_host are HOST arrays. */
+int asis_dwconv3x3_forward(const void *x, int dtype, const float *weight, const float *bias,
+                           void *pre, void *y, int B, int C, int n_maps, const int *hs_host,
+                           const int *ws_host, int fuse_gelu, void *stream);
+size_t asis_dwconv3x3_backward_workspace_bytes(int B, int C, int n_tok);
+int asis_dwconv3x3_backward(const void *dy, const void *pre, const void *x, int dtype,
+                            const float *weight, void *dx, float *dweight, float *dbias,
+                            int accumulate, int B, int C, int n_maps, const int *hs_host,
+                            const int *ws_host, int fuse_gelu, void *workspace,
+                            size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASIS_B200_H_ */

@@ -1,0 +1,61 @@
+"""World-size-2 gloo test of the data-parallel gradient path (CPU): bucketed, hook-driven
+all-reduce must equal the mean of the per-rank gradients, with several buckets in flight."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from adaptersis_b200.dp import BucketedGradAllReduce
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 16), torch.nn.Linear(16, 4))
+        red = BucketedGradAllReduce(net.parameters(), bucket_bytes=600)     # forces several buckets
+        assert len(red.buckets) >= 3
+        for step in range(2):
+            g = torch.Generator().manual_seed(100 + step)
+            data = torch.randn(world, 5, 8, generator=g)
+            net.zero_grad(set_to_none=True)
+            net(data[rank]).square().sum().backward()
+            red.finish()
+            got = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+            ref_net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 16), torch.nn.Linear(16, 4))
+            ref_net.load_state_dict(net.state_dict())
+            tot = 0
+            for r in range(world):
+                tot = tot + ref_net(data[r]).square().sum()
+            (tot / world).backward()
+            want = torch.cat([p.grad.reshape(-1) for p in ref_net.parameters()])
+            assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (rank, step, float((got - want).abs().max()))
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(30)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res

@@ -1,0 +1,137 @@
+"""GPU parity of the dense / normalisation kernels in fp32 parity mode (FFMA kernels) vs plain
+torch fp32 on the same inputs (tolerance 1e-4 max-relative), through the C ABI."""
+import pytest
+import torch
+
+from conftest import relerr
+import adaptersis_b200 as asis
+from adaptersis_b200 import kernels as K
+from adaptersis_b200._lib import (EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_SCALE_RESIDUAL, F32, MAJOR_K,
+                                  MAJOR_MN)
+from oracle import layers as o_layers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("R,C", [(37, 64), (1765, 1024), (100, 384), (64, 768), (9, 32)])
+def test_layernorm(R, C):
+    torch.manual_seed(0)
+    x = torch.randn(R, C, device=DEV) * 2 + 0.5
+    w = torch.randn(C, device=DEV)
+    b = torch.randn(C, device=DEV)
+    dy = torch.randn(R, C, device=DEV)
+    dres = torch.randn(R, C, device=DEV)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (C,), wr, br, 1e-6)
+    gx, gw, gb = torch.autograd.grad(yr, (xr, wr, br), dy)
+    y, mean, rstd = K.layernorm_forward(x, w, b, 1e-6, torch.float32)
+    assert relerr(y, yr) < TOL
+    dx, dw, db = K.layernorm_backward(dy, x, w, mean, rstd, dres)
+    assert relerr(dx, gx + dres) < TOL and relerr(dw, gw) < TOL and relerr(db, gb) < TOL
+    yb, _, _ = K.layernorm_forward(x.bfloat16(), w, b, 1e-6, torch.bfloat16)
+    assert relerr(yb.float(), torch.nn.functional.layer_norm(x.bfloat16().float(), (C,), w, b, 1e-6)) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K_", [(70, 96, 40), (257, 192, 64), (128, 64, 1024), (5, 8, 3)])
+def test_gemm_f32_majors_and_epilogues(M, N, K_):
+    torch.manual_seed(1)
+    A = torch.randn(M, K_, device=DEV)
+    B = torch.randn(N, K_, device=DEV)
+    ref = A @ B.t()
+    for am in (MAJOR_K, MAJOR_MN):
+        for bm in (MAJOR_K, MAJOR_MN):
+            a = A if am == MAJOR_K else A.t().contiguous()
+            b = B if bm == MAJOR_K else B.t().contiguous()
+            c, _ = K.gemm(F32, a, am, b, bm, M, N, K_, torch.float32)
+            assert relerr(c, ref) < TOL
+    bias = torch.randn(N, device=DEV)
+    gamma = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    c, _ = K.gemm(F32, A, MAJOR_K, B, MAJOR_K, M, N, K_, torch.float32, bias=bias)
+    assert relerr(c, ref + bias) < TOL
+    c, aux = K.gemm(F32, A, MAJOR_K, B, MAJOR_K, M, N, K_, torch.float32, epilogue=EPI_GELU, bias=bias,
+                    want_aux_dtype=torch.float32)
+    assert relerr(aux, ref + bias) < TOL and relerr(c, torch.nn.functional.gelu(ref + bias)) < TOL
+    c, aux = K.gemm(F32, A, MAJOR_K, B, MAJOR_K, M, N, K_, torch.float32, epilogue=EPI_SCALE_RESIDUAL, bias=bias,
+                    gamma=gamma, residual=res, want_aux_dtype=torch.float32)
+    assert relerr(c, res + gamma * (ref + bias)) < TOL and relerr(aux, ref + bias) < TOL
+    h = torch.randn(M, N, device=DEV, requires_grad=True)
+    (dg,) = torch.autograd.grad(torch.nn.functional.gelu(h), h, torch.ones_like(h))
+    c, _ = K.gemm(F32, A, MAJOR_K, B, MAJOR_K, M, N, K_, torch.float32, epilogue=EPI_DGELU, aux=h.detach())
+    assert relerr(c, ref * dg) < TOL
+    acc = torch.randn(M, N, device=DEV)
+    want = acc + ref
+    c, _ = K.gemm(F32, A, MAJOR_K, B, MAJOR_K, M, N, K_, torch.float32, epilogue=EPI_ACCUMULATE, out=acc)
+    assert relerr(c, want) < TOL
+
+
+def test_colsum_scale_add_cast():
+    torch.manual_seed(2)
+    X = torch.randn(1000, 192, device=DEV)
+    Y = torch.randn(1000, 192, device=DEV)
+    assert relerr(K.colsum(X), X.sum(0)) < TOL
+    assert relerr(K.colsum(X, Y), (X * Y).sum(0)) < TOL
+    assert relerr(K.colsum(X.bfloat16()), X.bfloat16().float().sum(0)) < TOL
+    g = torch.randn(192, device=DEV)
+    assert relerr(K.scale_cols(X, g, torch.float32), X * g) < 1e-6
+    assert relerr(K.add(X, Y.bfloat16(), torch.float32), X + Y.bfloat16().float()) < 1e-6
+    assert torch.equal(K.cast(X, torch.bfloat16), X.bfloat16())
+    v = torch.randn(1003, device=DEV)
+    assert torch.equal(K.cast(v[:1001].clone(), torch.bfloat16), v[:1001].bfloat16())
+
+
+@pytest.mark.parametrize("B,T,H,hd", [(2, 19, 4, 16), (1, 300, 3, 64), (2, 77, 2, 32)])
+def test_attention_f32(B, T, H, hd):
+    torch.manual_seed(3)
+    C = H * hd
+    qkv = torch.randn(B, T, 3 * C, device=DEV, requires_grad=True)
+    q, k, v = qkv.view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    p = torch.softmax((q * hd ** -0.5) @ k.transpose(-1, -2), -1)
+    ref = (p @ v).transpose(1, 2).reshape(B, T, C)
+    dout = torch.randn(B, T, C, device=DEV)
+    (gref,) = torch.autograd.grad(ref, qkv, dout)
+    with asis.precision("fp32"):
+        x = qkv.detach().clone().requires_grad_(True)
+        out = asis.functional.attention(x, H)
+        assert relerr(out, ref) < TOL
+        (g,) = torch.autograd.grad(out, x, dout)
+        assert relerr(g, gref) < TOL
+
+
+def test_patchify_and_dwconv():
+    torch.manual_seed(4)
+    img = torch.rand(2, 3, 42, 28, device=DEV)
+    cols = K.patchify(img, 14, torch.float32, 592)
+    ref = img.view(2, 3, 3, 14, 2, 14).permute(0, 2, 4, 1, 3, 5).reshape(12, 588)
+    assert torch.equal(cols[:, :588], ref) and float(cols[:, 588:].abs().max()) == 0.0
+    with pytest.raises(AssertionError, match="multiple of patch"):
+        K.patchify(torch.rand(1, 3, 40, 28, device=DEV), 14, torch.float32, 592)
+    C = 64
+    maps = [(7, 5), (4, 3)]
+    ntok = sum(h * w for h, w in maps)
+    for fuse in (False, True):
+        x = torch.randn(2, ntok, C, device=DEV, requires_grad=True)
+        w = torch.randn(C, 1, 3, 3, device=DEV, requires_grad=True)
+        b = torch.randn(C, device=DEV, requires_grad=True)
+        outs, s = [], 0
+        for hh, ww in maps:
+            t = x[:, s:s + hh * ww].transpose(1, 2).reshape(2, C, hh, ww)
+            t = torch.nn.functional.conv2d(t, w, b, padding=1, groups=C)
+            outs.append(t.flatten(2).transpose(1, 2))
+            s += hh * ww
+        ref = torch.cat(outs, 1)
+        if fuse:
+            ref = torch.nn.functional.gelu(ref)
+        dy = torch.randn_like(ref)
+        gx, gw, gb = torch.autograd.grad(ref, (x, w, b), dy)
+        x2 = x.detach().clone().requires_grad_(True)
+        w2 = w.detach().clone().requires_grad_(True)
+        b2 = b.detach().clone().requires_grad_(True)
+        y = asis.functional.DWConvFunction.apply(x2, w2, b2, maps, fuse)
+        assert relerr(y, ref) < TOL
+        hx, hw, hb = torch.autograd.grad(y, (x2, w2, b2), dy)
+        assert relerr(hx, gx) < TOL and relerr(hw, gw) < TOL and relerr(hb, gb) < TOL
