@@ -1,0 +1,94 @@
+"""MSDeformAttn microbench (BASELINE.json config 5 + the two real shapes): achieved GB/s on
+algorithmic bytes for the forward gather and the atomic-free backward.
+CUDA-event timing on the launching stream, L2 flushed between timed iterations."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from adaptersis_b200 import kernels as K  # noqa: E402
+
+
+def alg_bytes(N, S, M, D, Lq, L, P, ev, eo):
+    C = M * D
+    pts = N * Lq * M * L * P
+    fwd = ev * N * S * C + 4 * pts * 2 + 4 * pts + eo * N * Lq * C
+    bwd = eo * N * Lq * C + ev * N * S * C + 12 * pts + ev * N * S * C + 12 * pts
+    return fwd, bwd
+
+
+def make(N, Lq, M, D, shapes, P, dtype, dev, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(N, S, M, D, generator=g).to(dev, dtype)
+    side = int(Lq ** 0.5)
+    qi = torch.arange(Lq)
+    ref = torch.stack([((qi % side).float() + 0.5) / side, ((qi // side).float().clamp(max=side - 1) + 0.5) / side], -1)
+    loc = ref.view(1, Lq, 1, 1, 1, 2).expand(N, Lq, M, L, P, 2).clone()
+    for l, (H, W) in enumerate(shapes):
+        loc[:, :, :, l] += (torch.rand(N, Lq, M, P, 2, generator=g) * 8 - 4) / torch.tensor([W, H], dtype=torch.float32)
+    far = torch.rand(N, Lq, M, L, P, generator=g) < 0.05
+    loc[far] = torch.rand(int(far.sum()), 2, generator=g) * 1.2 - 0.1
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    gout = torch.randn(N, Lq, M * D, generator=g).to(dev, dtype)
+    ss = torch.as_tensor(shapes, dtype=torch.long, device=dev)
+    lsi = torch.cat([ss.new_zeros(1), ss.prod(1).cumsum(0)[:-1]])
+    return value, ss, lsi, loc.to(dev), aw.to(dev), gout
+
+
+def timeit(fn, iters, flush):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    dev = torch.device("cuda:0")
+    peak = 6504.1
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    cases = [("injector_real", 12, 1764, 8, 128, [(73, 73), (36, 36), (18, 18)], 4),
+             ("extractor_real", 12, 6949, 8, 128, [(42, 42)], 4)]
+    for Lq in (1024, 1764, 4096, 6949, 16384, 30000):
+        cases.append((f"sweep_g36_Lq{Lq}", 12, Lq, 16, 64, [(72, 72), (36, 36), (18, 18)], 4))
+    for Lq in (1764, 6949, 30000):
+        cases.append((f"sweep_g92_Lq{Lq}", 12, Lq, 16, 64, [(184, 184), (92, 92), (46, 46)], 4))
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    rows = []
+    for name, N, Lq, M, D, shapes, P in cases:
+        if only and only not in name:
+            continue
+        for dtype in (torch.float32, torch.bfloat16):
+            v, ss, lsi, loc, aw, gout = make(N, Lq, M, D, shapes, P, dtype, dev)
+            S = v.shape[1]
+            e = 4 if dtype == torch.float32 else 2
+            fb, bb = alg_bytes(N, S, M, D, Lq, len(shapes), P, e, e)
+            tf = timeit(lambda: K.msda_forward(v, ss, lsi, loc, aw), 10, flush)
+            tb = timeit(lambda: K.msda_backward(v, ss, lsi, loc, aw, gout), 10, flush)
+            row = dict(case=name, dtype=str(dtype).split(".")[-1], N=N, Lq=Lq, S=S, M=M, D=D,
+                       fwd_ms=round(tf, 4), fwd_GBs=round(fb / tf / 1e6, 1), fwd_frac=round(fb / tf / 1e6 / peak, 3),
+                       bwd_ms=round(tb, 4), bwd_GBs=round(bb / tb / 1e6, 1), bwd_frac=round(bb / tb / 1e6 / peak, 3))
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    return rows
+
+
+if __name__ == "__main__":
+    main()
