@@ -19,7 +19,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v"]
-SOURCES = ["api.cu", "msda.cu", "norm.cu", "gemm_f32.cu", "attention_f32.cu", "misc.cu", "gemm_tc.cu"]
+SOURCES = ["api.cu", "msda.cu", "norm.cu", "gemm_f32.cu", "attention_f32.cu", "misc.cu", "gemm_tc.cu", "attention_tc.cu"]
 
 
 def _deps_mtime():

@@ -1,14 +1,405 @@
-// temporary: tcgen05 paths not built yet
+// gemm_tc.cu -- bf16 tensor-core GEMM for sm_100a: C[M,N] = epilogue(sum_k A[m,k] * B[n,k]).
+//
+// One persistent, warp-specialised kernel per (A-major, B-major) pair:
+//   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring (4 stages x 48 KB)
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, 128 x 256 x 16 per instruction,
+//                              fp32 accumulators in TMEM (2 x 256 columns, double buffered)
+//   warps 2..9  epilogue       tcgen05.ld -> registers -> fused epilogue (bias / exact GELU /
+//                              LayerScale + residual / GELU' / accumulate) -> 16-byte global stores
+// Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+// Tails in M, N and K come for free from TMA zero fill; stores are masked.
+//
+// Both operands may be K-major (nn.Linear forward: x[R,K], W[N,K]) or MN-major (input gradient:
+// W as [K=N_out rows, K_in]; weight gradient: dy[R,N_out] and x[R,K_in], reduction over the rows),
+// so no operand is ever transposed in memory.  Weight gradients (few output tiles, very long K)
+// are split along K across CTAs and combined with fp32 red.global.add.
+#include <mutex>
+
 #include "epilogue.cuh"
+#include "tc_common.cuh"
+
 namespace asis {
-int gemm_tc_launch(const void *, int, int64_t, const void *, int, int64_t, int, int, int, const EpiArgs &, cudaStream_t) {
-  ASIS_FAIL(ASIS_ERR_UNSUPPORTED, "gemm: tcgen05 path not built");
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int A_BYTES = BM * BK * 2;           // 16 KB
+constexpr int B_BYTES = BN * BK * 2;           // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
+constexpr int BOX_BYTES = 64 * BK * 2;         // one 64 x 64 MN-major TMA box: 8 KB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct GemmTcParams {
+  int M, N, K;
+  int m_tiles, n_tiles, splits, kb_per_split, kb_total;
+  int atomic_out;  // split-K: combine with red.global.add.f32
+  EpiArgs epi;
+};
+
+__device__ __forceinline__ void load8f(const float *p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4 *>(p);
+  const float4 b = *reinterpret_cast<const float4 *>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
-int attention_tc_forward(const void *, void *, float *, int, int, int, int, cudaStream_t) {
-  ASIS_FAIL(ASIS_ERR_UNSUPPORTED, "attention: tcgen05 path not built");
+__device__ __forceinline__ void load8(const void *base, int dtype, size_t idx, float (&v)[8]) {
+  if (dtype == ASIS_F32) {
+    load8f(reinterpret_cast<const float *>(base) + idx, v);
+  } else {
+    const uint4 t = *reinterpret_cast<const uint4 *>(reinterpret_cast<const bf16 *>(base) + idx);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
+      v[2 * i] = __low2float(h);
+      v[2 * i + 1] = __high2float(h);
+    }
+  }
 }
-size_t attention_tc_bwd_ws(int, int, int, int) { return 0; }
-int attention_tc_backward(const void *, const void *, const float *, const void *, void *, int, int, int, int, void *, cudaStream_t) {
-  ASIS_FAIL(ASIS_ERR_UNSUPPORTED, "attention: tcgen05 path not built");
+__device__ __forceinline__ void store8(void *base, int dtype, size_t idx, const float (&v)[8]) {
+  if (dtype == ASIS_F32) {
+    float *p = reinterpret_cast<float *>(base) + idx;
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(base) + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
+
+// epilogue for 32 consecutive columns of one row
+__device__ __forceinline__ void epi_row32(const GemmTcParams &p, int row, int col0, const float (&acc)[32], bool vec_ok) {
+  const EpiArgs &e = p.epi;
+  if (row >= p.M || col0 >= p.N) return;
+  if (!vec_ok || col0 + 32 > p.N) {
+    for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
+      if (p.atomic_out)
+        atomicAdd(reinterpret_cast<float *>(e.C) + (size_t)row * e.ldc + col0 + j, acc[j]);
+      else
+        epi_scalar(e, row, col0 + j, acc[j]);
+    }
+    return;
+  }
+  const size_t ci = (size_t)row * e.ldc + col0;
+  const size_t ai = (size_t)row * e.ldaux + col0;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = acc[8 * g + i];
+    if (p.atomic_out) {
+      float *c = reinterpret_cast<float *>(e.C) + ci + 8 * g;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(c + i, v[i]);
+      continue;
+    }
+    if (e.bias && e.kind != ASIS_EPI_DGELU && e.kind != ASIS_EPI_ACCUMULATE) {
+      float b[8];
+      load8f(e.bias + col0 + 8 * g, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += b[i];
+    }
+    switch (e.kind) {
+      case ASIS_EPI_GELU:
+        if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        break;
+      case ASIS_EPI_SCALE_RESIDUAL: {
+        if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
+        float r[8], gm[8];
+        load8f(e.residual + ci + 8 * g, r);
+        load8f(e.gamma + col0 + 8 * g, gm);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = r[i] + gm[i] * v[i];
+      } break;
+      case ASIS_EPI_DGELU: {
+        float h[8];
+        load8(e.aux, e.aux_dtype, ai + 8 * g, h);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= dgelu_erf(h[i]);
+      } break;
+      case ASIS_EPI_ACCUMULATE: {
+        float c[8];
+        load8f(reinterpret_cast<const float *>(e.C) + ci + 8 * g, c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += c[i];
+      } break;
+      default:
+        break;
+    }
+    store8(e.C, e.c_dtype, ci + 8 * g, v);
+  }
+}
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES;
+  uint64_t *tfull_bar = empty_bar + STAGES;
+  uint64_t *tempty_bar = tfull_bar + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + a, 1);
+      mbar_init(tempty_bar + a, NUM_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile % p.m_tiles;
+        const int rest = tile / p.m_tiles;
+        const int n_blk = rest % p.n_tiles;
+        const int split = rest / p.n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t *sa = smem + stage * STAGE_BYTES;
+          uint8_t *sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(full_bar + stage, STAGE_BYTES);
+          if (A_MN == 0) {
+            tma_load_2d(&tmA, full_bar + stage, sa, kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(&tmA, full_bar + stage, sa + j * BOX_BYTES, m_blk * BM + j * 64, kb * BK);
+          }
+          if (B_MN == 0) {
+            tma_load_2d(&tmB, full_bar + stage, sb, kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(&tmB, full_bar + stage, sb + j * BOX_BYTES, n_blk * BN + j * 64, kb * BK);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = (tile / p.m_tiles) / p.n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: +32 B per 16 k inside the 128 B swizzle row.  MN-major: +2 groups of 8 k-rows.
+            const uint64_t da = A_MN == 0 ? smem_desc(sa + k * 32, 16, 1024) : smem_desc(sa + k * 2048, BOX_BYTES, 1024);
+            const uint64_t db = B_MN == 0 ? smem_desc(sb + k * 32, 16, 1024) : smem_desc(sb + k * 2048, BOX_BYTES, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);  // frees the smem stage when the MMAs above have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull_bar + acc);  // accumulator complete
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int ew = warp - 2;           // 0..7
+    const int quarter = warp & 3;      // TMEM lane quarter this warp may access
+    const int half = ew >> 2;          // column half: [half*128, half*128+128)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (p.epi.ldc % 8 == 0) && (!p.epi.aux || p.epi.ldaux % 8 == 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile % p.m_tiles;
+      const int n_blk = (tile / p.m_tiles) % p.n_tiles;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int col_in_tile = half * 128 + c * 32;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + col_in_tile, v);
+        epi_row32(p, row, n_blk * BN + col_in_tile, v, vec_ok);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap *map, const void *base, uint64_t inner, uint64_t outer, uint64_t pitch_elems,
+                 uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) ASIS_FAIL(ASIS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ASIS_FAIL(ASIS_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (inner=%llu outer=%llu pitch=%llu)", (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)pitch_elems);
+  return ASIS_OK;
+}
+
+int make_tmap_3d(CUtensorMap *map, const void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_elems,
+                 uint64_t pitch2_elems, uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) ASIS_FAIL(ASIS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_elems * 2, pitch2_elems * 2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void *>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ASIS_FAIL(ASIS_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed with %d", (int)r);
+  return ASIS_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int A_MN, int B_MN>
+static int launch_variant(const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    ASIS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    configured = true;
+  }
+  gemm_tc_kernel<A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b_major, int64_t ldb, int M, int N,
+                   int K, const EpiArgs &epi, cudaStream_t st) {
+  ASIS_REQUIRE(aligned16(A) && aligned16(B) && aligned16(epi.C), "gemm(bf16): A, B, C must be 16-byte aligned");
+  ASIS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%lld, ldb=%lld must be multiples of 8 elements (TMA 16-byte pitch)", (long long)lda, (long long)ldb);
+  GemmTcParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + BN - 1) / BN;
+  p.kb_total = (K + BK - 1) / BK;
+  p.epi = epi;
+  const int sms = sm_count();
+  const int tiles = p.m_tiles * p.n_tiles;
+  int splits = 1;
+  const bool can_split = epi.c_dtype == ASIS_F32 && (epi.kind == ASIS_EPI_ACCUMULATE || (epi.kind == ASIS_EPI_NONE && !epi.bias));
+  if (can_split && tiles * 2 <= sms && p.kb_total >= 16) {
+    splits = sms / tiles;
+    if (splits > p.kb_total / 8) splits = p.kb_total / 8;
+    if (splits > 16) splits = 16;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  p.splits = splits;
+  p.atomic_out = splits > 1;
+  if (p.atomic_out && epi.kind == ASIS_EPI_NONE) {
+    if (epi.ldc == N)
+      ASIS_CUDA(cudaMemsetAsync(epi.C, 0, (size_t)M * N * sizeof(float), st));
+    else
+      ASIS_CUDA(cudaMemset2DAsync(epi.C, epi.ldc * sizeof(float), 0, (size_t)N * sizeof(float), M, st));
+  }
+  CUtensorMap ta, tb;
+  int rc;
+  if (a_major == ASIS_MAJOR_K) rc = make_tmap_2d(&ta, A, K, M, lda, BK, BM);
+  else rc = make_tmap_2d(&ta, A, M, K, lda, 64, BK);
+  if (rc) return rc;
+  if (b_major == ASIS_MAJOR_K) rc = make_tmap_2d(&tb, B, K, N, ldb, BK, BN);
+  else rc = make_tmap_2d(&tb, B, N, K, ldb, 64, BK);
+  if (rc) return rc;
+  const int total = tiles * splits;
+  const int grid = total < sms ? total : sms;
+  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_K) return launch_variant<0, 0>(ta, tb, p, grid, st);
+  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_MN) return launch_variant<0, 1>(ta, tb, p, grid, st);
+  if (a_major == ASIS_MAJOR_MN && b_major == ASIS_MAJOR_MN) return launch_variant<1, 1>(ta, tb, p, grid, st);
+  return launch_variant<1, 0>(ta, tb, p, grid, st);
+}
+
 }  // namespace asis

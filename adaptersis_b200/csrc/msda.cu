@@ -44,8 +44,10 @@ struct Footprint {
 };
 __device__ __forceinline__ Footprint footprint(float lx, float ly, int H, int W) {
   Footprint f;
-  const float x = ((2.0f * lx - 1.0f + 1.0f) * (float)W - 1.0f) * 0.5f;
-  const float y = ((2.0f * ly - 1.0f + 1.0f) * (float)H - 1.0f) * 0.5f;
+  // explicit round-to-nearest steps (no FMA contraction): floor() of this value decides the
+  // bilinear cell, so it is kept bit-identical to the plain IEEE evaluation of the formula
+  const float x = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(2.0f, lx), -1.0f), 1.0f), (float)W), -1.0f), 0.5f);
+  const float y = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fadd_rn(__fmul_rn(2.0f, ly), -1.0f), 1.0f), (float)H), -1.0f), 0.5f);
   f.any = (x > -1.0f) && (x < (float)W) && (y > -1.0f) && (y < (float)H);
   const float xf = floorf(x), yf = floorf(y);
   f.x0 = f.any ? (int)xf : 0;

@@ -1,6 +1,9 @@
 """FeatureDecoder (backbones/decoders.py:92-164) -- same layer layout and state_dict keys.
 SURVEY.md section 8(f) rank 2: *next*, runs on PyTorch library convolutions for now."""
+import torch
 import torch.nn as nn
+
+from .functional import get_precision
 
 
 class FeatureDecoder(nn.Module):
@@ -19,6 +22,10 @@ class FeatureDecoder(nn.Module):
         self.final_out = nn.Conv2d(features[4], num_classes, 3, padding=1)
 
     def forward(self, x):
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=get_precision() != "fp32"):
+            return self._forward(x)
+
+    def _forward(self, x):
         for k in range(1, 5):
             x = getattr(self, f"decoder_{k}")(x)
         return self.final_out(x)

@@ -2,7 +2,10 @@
 state_dict keys.  SURVEY.md section 8(f) rank 1: this component is *next*, not yet on the
 hand-written path; it runs on PyTorch library convolutions (cuDNN) + SyncBatchNorm for now and is
 excluded from every "our kernels" claim."""
+import torch
 import torch.nn as nn
+
+from .functional import get_precision
 
 
 def _cbr(cin, cout, stride, padding):
@@ -26,6 +29,11 @@ class FeatureEncoder(nn.Module):
         self.fc4 = nn.Conv2d(8 * p, embed_dim, kernel_size=1, bias=True)
 
     def forward(self, x, need_c1=True):
+        # fp32 parity mode: keep the library convolutions out of TF32
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=get_precision() != "fp32"):
+            return self._forward(x, need_c1)
+
+    def _forward(self, x, need_c1):
         c1 = self.stem(x)
         c2 = self.conv2(c1)
         c3 = self.conv3(c2)

@@ -27,6 +27,9 @@ def set_precision(mode):
     if mode not in ("fp32", "bf16"):
         raise ValueError("precision must be 'fp32' or 'bf16'")
     _MODE[0] = mode
+    # the not-yet-native parts (spatial prior module / decoder convolutions) run on
+    # cuDNN: keep them out of TF32 in parity mode, forward and backward
+    torch.backends.cudnn.allow_tf32 = mode != "fp32"
 
 
 @contextlib.contextmanager
@@ -36,7 +39,10 @@ def precision(mode):
     try:
         yield
     finally:
-        _MODE[0] = old
+        set_precision(old)
+
+
+set_precision(_MODE[0])
 
 
 def _cfg(mode=None):

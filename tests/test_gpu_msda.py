@@ -29,6 +29,14 @@ def _rand_case(seed, N, Lq, M, D, shapes, P, spread=4.0, oob=0.05):
         loc[:, :, :, l] += (torch.rand(N, Lq, M, P, 2, generator=g) * 2 - 1) * spread / torch.tensor([W, H], dtype=torch.float32)
     far = torch.rand(N, Lq, M, L, P, generator=g) < oob
     loc[far] = torch.rand(int(far.sum()), 2, generator=g) * 1.2 - 0.1
+    # d(out)/d(loc) is discontinuous where a pixel coordinate is an integer; two correct fp32
+    # evaluations may floor() differently there, so keep samples 1e-3 px away from cell borders
+    for l, (H, W) in enumerate(shapes):
+        size = torch.tensor([W, H], dtype=torch.float32)
+        pix = loc[:, :, :, l] * size - 0.5
+        frac = pix - pix.floor()
+        near = (frac < 1e-3) | (frac > 1 - 1e-3)
+        loc[:, :, :, l] = torch.where(near, loc[:, :, :, l] + 3e-3 / size, loc[:, :, :, l])
     aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
     gout = torch.randn(N, Lq, M * D, generator=g)
     return value, torch.as_tensor(shapes, dtype=torch.long), loc, aw, gout
