@@ -11,6 +11,30 @@ from ._lib import (BF16, EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_SCAL
 
 TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
 
+# optional per-launch profiler (bench.py): an object with .begin(name, work, unit) -> token and
+# .end(token); records CUDA events on the launching stream around the kernel(s) of one op
+_PROF = [None]
+
+
+def set_profiler(p):
+    _PROF[0] = p
+
+
+class _Span:
+    __slots__ = ("tok",)
+
+    def __init__(self, name, work, unit):
+        p = _PROF[0]
+        self.tok = p.begin(name, work, unit) if p is not None else None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        if self.tok is not None:
+            _PROF[0].end(self.tok)
+        return False
+
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
@@ -27,8 +51,11 @@ def msda_forward(value, spatial_shapes, level_start_index, sampling_locations, a
     ss = _c(spatial_shapes.to(torch.int64))
     lsi = _c(level_start_index.to(torch.int64))
     out = torch.empty(N, Lq, M * D, dtype=value.dtype, device=value.device)
-    check(_lib.load().asis_msda_forward(ptr(value), dt(value), ptr(ss), ptr(lsi), ptr(loc), ptr(aw), ptr(out),
-                                        dt(out), N, S, M, D, Lq, L, P, stream()))
+    e = value.element_size()
+    pts = N * Lq * M * L * P
+    with _Span("msda_fwd", e * N * S * M * D + 12 * pts + e * N * Lq * M * D, "B"):
+        check(_lib.load().asis_msda_forward(ptr(value), dt(value), ptr(ss), ptr(lsi), ptr(loc), ptr(aw), ptr(out),
+                                            dt(out), N, S, M, D, Lq, L, P, stream()))
     return out
 
 
@@ -48,9 +75,12 @@ def msda_backward(value, spatial_shapes, level_start_index, sampling_locations, 
     ga = torch.empty_like(aw)
     nbytes = lib.asis_msda_backward_workspace_bytes(N, S, M, D, Lq, L, P)
     ws = workspace(nbytes, value.device)
-    check(lib.asis_msda_backward(ptr(value), dt(value), ptr(ss), ptr(lsi), ptr(loc), ptr(aw), ptr(grad_out),
-                                 dt(grad_out), ptr(gv), ptr(gl), ptr(ga), N, S, M, D, Lq, L, P, ptr(ws), nbytes,
-                                 stream()))
+    e = value.element_size()
+    pts = N * Lq * M * L * P
+    with _Span("msda_bwd", e * N * Lq * M * D + 2 * e * N * S * M * D + 24 * pts, "B"):
+        check(lib.asis_msda_backward(ptr(value), dt(value), ptr(ss), ptr(lsi), ptr(loc), ptr(aw), ptr(grad_out),
+                                     dt(grad_out), ptr(gv), ptr(gl), ptr(ga), N, S, M, D, Lq, L, P, ptr(ws), nbytes,
+                                     stream()))
     return gv, gl, ga
 
 
@@ -100,8 +130,9 @@ def layernorm_forward(x2d, weight, bias, eps, out_dtype):
     y = torch.empty(R, C, dtype=out_dtype, device=x2d.device)
     mean = torch.empty(R, dtype=torch.float32, device=x2d.device)
     rstd = torch.empty(R, dtype=torch.float32, device=x2d.device)
-    check(_lib.load().asis_layernorm_forward(ptr(x2d), dt(x2d), ptr(weight), ptr(bias), ptr(y), dt(y), ptr(mean),
-                                             ptr(rstd), R, C, float(eps), stream()))
+    with _Span("ln_fwd", R * C * (x2d.element_size() + y.element_size()), "B"):
+        check(_lib.load().asis_layernorm_forward(ptr(x2d), dt(x2d), ptr(weight), ptr(bias), ptr(y), dt(y),
+                                                 ptr(mean), ptr(rstd), R, C, float(eps), stream()))
     return y, mean, rstd
 
 
@@ -117,8 +148,10 @@ def layernorm_backward(dy2d, x2d, weight, mean, rstd, dres=None, want_param_grad
     ws = workspace(nbytes, x2d.device)
     if dres is not None:
         dres = _c(dres.float())
-    check(lib.asis_layernorm_backward(ptr(dy2d), dt(dy2d), ptr(x2d), dt(x2d), ptr(weight), ptr(mean), ptr(rstd),
-                                      ptr(dres), ptr(dx), ptr(dw), ptr(db), 0, R, C, ptr(ws), nbytes, stream()))
+    nb = R * C * (dy2d.element_size() + x2d.element_size() + 4 + (4 if dres is not None else 0))
+    with _Span("ln_bwd", nb, "B"):
+        check(lib.asis_layernorm_backward(ptr(dy2d), dt(dy2d), ptr(x2d), dt(x2d), ptr(weight), ptr(mean), ptr(rstd),
+                                          ptr(dres), ptr(dx), ptr(dw), ptr(db), 0, R, C, ptr(ws), nbytes, stream()))
     return dx, dw, db
 
 
@@ -138,10 +171,11 @@ def gemm(compute, A, a_major, B, b_major, M, N, K, out_dtype, epilogue=EPI_NONE,
     if residual is not None:
         residual = _c(residual)
         assert residual.dtype == torch.float32 and residual.shape[-1] == N
-    check(_lib.load().asis_gemm(compute, ptr(A), a_major, A.stride(0), ptr(B), b_major, B.stride(0), ptr(out),
-                                dt(out), out.stride(0), M, N, K, epilogue, ptr(bias), ptr(gamma), ptr(residual),
-                                ptr(aux), dt(aux) if aux is not None else 0, aux.stride(0) if aux is not None else 0,
-                                stream()))
+    with _Span("gemm_bf16" if compute == BF16 else "gemm_f32", 2.0 * M * N * K, "FLOP"):
+        check(_lib.load().asis_gemm(compute, ptr(A), a_major, A.stride(0), ptr(B), b_major, B.stride(0), ptr(out),
+                                    dt(out), out.stride(0), M, N, K, epilogue, ptr(bias), ptr(gamma), ptr(residual),
+                                    ptr(aux), dt(aux) if aux is not None else 0,
+                                    aux.stride(0) if aux is not None else 0, stream()))
     return out, aux
 
 
@@ -156,8 +190,10 @@ def colsum(X2d, Y2d=None, out=None, accumulate=False):
         out = torch.empty(N, dtype=torch.float32, device=X2d.device)
     nbytes = lib.asis_colsum_workspace_bytes(M, N)
     ws = workspace(nbytes, X2d.device)
-    check(lib.asis_colsum(ptr(X2d), dt(X2d), ptr(Y2d), dt(Y2d) if Y2d is not None else 0, X2d.stride(0), ptr(out),
-                          int(accumulate), M, N, ptr(ws), nbytes, stream()))
+    nb = M * N * (X2d.element_size() + (Y2d.element_size() if Y2d is not None else 0))
+    with _Span("colsum", nb, "B"):
+        check(lib.asis_colsum(ptr(X2d), dt(X2d), ptr(Y2d), dt(Y2d) if Y2d is not None else 0, X2d.stride(0),
+                              ptr(out), int(accumulate), M, N, ptr(ws), nbytes, stream()))
     return out
 
 
@@ -165,7 +201,8 @@ def scale_cols(a2d, gamma, out_dtype):
     M, N = a2d.shape
     a2d = _c(a2d)
     out = torch.empty(M, N, dtype=out_dtype, device=a2d.device)
-    check(_lib.load().asis_scale_cols(ptr(a2d), dt(a2d), ptr(gamma), ptr(out), dt(out), M, N, stream()))
+    with _Span("scale_cols", M * N * (a2d.element_size() + out.element_size()), "B"):
+        check(_lib.load().asis_scale_cols(ptr(a2d), dt(a2d), ptr(gamma), ptr(out), dt(out), M, N, stream()))
     return out
 
 
@@ -196,7 +233,9 @@ def attention_forward(compute, qkv, B, T, H, hd):
     lse = torch.empty(B, H, T, dtype=torch.float32, device=qkv.device)
     nbytes = lib.asis_attention_forward_workspace_bytes(compute, B, T, H, hd)
     ws = workspace(nbytes, qkv.device)
-    check(lib.asis_attention_forward(compute, ptr(qkv), ptr(out), ptr(lse), B, T, H, hd, ptr(ws), nbytes, stream()))
+    with _Span("attn_fwd", 4.0 * B * H * T * T * hd, "FLOP"):
+        check(lib.asis_attention_forward(compute, ptr(qkv), ptr(out), ptr(lse), B, T, H, hd, ptr(ws), nbytes,
+                                         stream()))
     return out, lse
 
 
@@ -206,8 +245,9 @@ def attention_backward(compute, qkv, out, lse, dout, B, T, H, hd):
     dqkv = torch.empty_like(qkv)
     nbytes = lib.asis_attention_backward_workspace_bytes(compute, B, T, H, hd)
     ws = workspace(nbytes, qkv.device)
-    check(lib.asis_attention_backward(compute, ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), B, T, H, hd,
-                                      ptr(ws), nbytes, stream()))
+    with _Span("attn_bwd", 10.0 * B * H * T * T * hd, "FLOP"):   # algorithmic: 5 GEMMs (7 are executed)
+        check(lib.asis_attention_backward(compute, ptr(qkv), ptr(out), ptr(lse), ptr(dout), ptr(dqkv), B, T, H, hd,
+                                          ptr(ws), nbytes, stream()))
     return dqkv
 
 

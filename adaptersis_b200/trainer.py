@@ -1,0 +1,76 @@
+"""One training iteration of the reference's train() loop (train.py:268-441) as a callable:
+H2D copy -> adapter encoder -> FeatureDecoder -> bilinear resize -> Softmax -> dice loss ->
+backward -> (bucketed gradient all-reduce) -> SGD step -> loss.item().
+
+Differences from the script as shipped, all deliberate and documented in DESIGN.md:
+  * the graph is left connected (no torch.no_grad around the backbone blocks / the final concat),
+    so the backbone runs forward AND backward as BASELINE.json asks;
+  * deform_inputs and the interpolated position embedding are cached instead of recomputed."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as Fn
+from .decoders import FeatureDecoder
+from .dp import BucketedGradAllReduce
+from .encoder import AdapterEncoder
+
+
+def dice_loss_after_softmax(prob, target, n_classes):
+    """DC(n).forward on the output of nn.Softmax(1) (train.py:424-428; segloss/dice.py:5-36): the
+    reference applies softmax a second time inside the loss; kept as is."""
+    p = torch.softmax(prob, 1)
+    onehot = F.one_hot(target.long(), n_classes).permute(0, 3, 1, 2).to(p.dtype)
+    inter = (p * onehot).sum((2, 3))
+    dice = (2 * inter) / (p.sum((2, 3)) + onehot.sum((2, 3)) + 10e-20)
+    return 1.0 - dice.mean()
+
+
+class TrainStep(nn.Module):
+    def __init__(self, arch="vit_large", num_classes=2, adapter_heads=8, inplanes=64, lr=0.01, momentum=0.99,
+                 weight_decay=3e-5, train_backbone=True, dec_features=None, device="cuda", precision="bf16",
+                 bucket_bytes=64 << 20):
+        super().__init__()
+        self.precision = precision
+        self.encoder = AdapterEncoder(arch=arch, adapter_heads=adapter_heads, inplanes=inplanes,
+                                      frozen_backbone=not train_backbone, injector_init=0.0)
+        C = self.encoder.model.embed_dim
+        feats = dec_features or [C, 512, 256, 128, 64]
+        self.seg_decoder = FeatureDecoder(embed_dim=C, num_classes=num_classes, features=feats)
+        self.num_classes = num_classes
+        self.to(device)
+        self.encoder.model.eval()
+        if not train_backbone:
+            for p in self.encoder.model.parameters():
+                p.requires_grad_(False)
+        params = [p for p in self.parameters() if p.requires_grad]
+        # reference: SGD(momentum=0.99, weight_decay=3e-5), train.py:178-189
+        self.optimizer = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay, foreach=True)
+        self.reducer = BucketedGradAllReduce(params, bucket_bytes=bucket_bytes)
+        self.device = torch.device(device)
+
+    def forward_loss(self, inp, target):
+        with Fn.precision(self.precision):
+            feat = self.encoder(inp)["feat"]
+            out = self.seg_decoder(feat.float())
+            H, W = target.shape[1], target.shape[2]
+            out = F.interpolate(out, size=(H, W), mode="bilinear")
+            out = torch.softmax(out, 1)
+            return dice_loss_after_softmax(out, target, self.num_classes)
+
+    def step_device(self, inp, target):
+        """inputs already on the device; returns the loss tensor (no host sync)."""
+        self.optimizer.zero_grad(set_to_none=True)
+        with Fn.precision(self.precision):
+            loss = self.forward_loss(inp, target)
+            loss.backward()
+        self.reducer.finish()
+        self.optimizer.step()
+        return loss
+
+    def step(self, inp_host, target_host):
+        """The call a user makes (train.py:270-271, :432-440): pinned host batch in, python float out."""
+        inp = inp_host.to(self.device, non_blocking=True)
+        target = target_host.to(self.device, non_blocking=True)
+        loss = self.step_device(inp, target)
+        return float(loss.item())
