@@ -4,14 +4,17 @@
 // dropout); T = 1765 is not a multiple of the 128-row tiles: TMA zero-fills rows >= T and the
 // softmax masks key columns >= T.
 //
-// Forward  (grid: q-blocks x H x B):  warp 0 TMA, warp 1 MMA issuer, warps 2-5 softmax (1 thread =
-//   1 query row).  S = Q K^T into TMEM (double buffered) -> registers -> online softmax -> P (bf16)
-//   written to 128B-swizzled smem -> O_j = P V (V consumed MN-major straight from the TMA tile) ->
-//   registers, rescaled and accumulated in fp32.
-// Backward (two atomic-free kernels, both recompute P from the saved log-sum-exp):
-//   dK/dV kernel, one CTA per key block:   S^T = K Q^T, dP^T = V dO^T  -> P^T, dS^T -> smem ->
+// All three kernels: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = softmax (1 thread =
+// 1 TMEM lane = 1 row).  Each CTA is a *serial* chain  MMA -> softmax -> MMA  with single-buffered
+// TMEM / smem, sized (<= 96 KB smem, 256 TMEM columns) so that TWO CTAs are resident per SM and
+// overlap one CTA's softmax (MUFU/FMA bound) with the other's tensor-core work.
+// Forward  (grid: 128-query blocks x H x B), 128-key tiles:  S = Q K^T (TMEM) -> online softmax in
+//   registers -> P (bf16) into 128B-swizzled smem -> O_j = P V (V consumed MN-major straight from
+//   its TMA tile) -> accumulated in registers with the usual max-rescaling.
+// Backward (two atomic-free kernels, both recompute P from the saved log-sum-exp), 64-wide tiles:
+//   dK/dV kernel, one CTA per 128 keys:    S^T = K Q^T, dP^T = V dO^T  -> P^T, dS^T -> smem ->
 //                                          dV += P^T dO, dK += dS^T Q   (accumulated in TMEM)
-//   dQ kernel,    one CTA per query block: S = Q K^T, dP = dO V^T -> dS -> smem -> dQ += dS K
+//   dQ kernel,    one CTA per 128 queries: S = Q K^T, dP = dO V^T -> dS -> smem -> dQ += dS K
 // Every gradient element is produced by exactly one CTA: deterministic, no atomics.
 #include "tc_common.cuh"
 
@@ -68,11 +71,30 @@ __device__ __forceinline__ void store_out64(bf16 *dst, const float (&o)[64], flo
 }
 
 // descriptors for the tile shapes used here
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kstep) {       // [rows x 64] sub-tiles, K = columns
-  return smem_desc(tile + (kstep >> 2) * T16K + (kstep & 3) * 32, 16, 1024);
+// K-major operand [rows x 64*n]: 64-column sub-tiles `sub_bytes` apart, K = columns, 16 per k-step
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kstep, uint32_t sub_bytes = T16K) {
+  return smem_desc(tile + (kstep >> 2) * sub_bytes + (kstep & 3) * 32, 16, 1024);
 }
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kstep) {      // [K rows x 64], N = columns
+// MN-major operand [K rows x 64]: N = the 64 columns, 16 K-rows (2 KB) per k-step
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kstep) {
   return smem_desc(tile + kstep * 2048, T16K, 1024);
+}
+
+// pack 32 floats to bf16 and write them as row `row`, columns [col0, col0+32) of a K-major 128B-swizzled
+// tile whose 64-column sub-tiles hold `rows` rows each
+__device__ __forceinline__ void store_row32(uint8_t *tile, int rows, int row, int col0, const float (&v)[32]) {
+  uint8_t *sub = tile + (col0 >> 6) * (rows * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+  const int ch0 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(sub + (((ch0 + c) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 struct AttnParams {
@@ -85,23 +107,27 @@ struct AttnParams {
   bf16 *dqkv;        // bwd: [B, T, 3, H, 64]
 };
 
+constexpr int HALF = 64;                     // key / query tile width of the backward kernels
+constexpr int T8K = HALF * HD * 2;           // one 64 x 64 bf16 tile
+constexpr uint32_t TMEM_COLS = 256;
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = T16K /*Q*/ + 2 * T16K /*K*/ + 2 * T16K /*V*/ + 2 * T32K /*P*/ + 1024 + 256;
+constexpr int FWD_SMEM = T16K /*Q*/ + T16K /*K*/ + T16K /*V*/ + T32K /*P*/ + 1024 + 128;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sQ = smem;
   uint8_t *sK = sQ + T16K;
-  uint8_t *sV = sK + 2 * T16K;
-  uint8_t *sP = sV + 2 * T16K;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * T32K);
-  uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 7,
-           *p_full = bars + 9, *o_full = bars + 11, *o_empty = bars + 13;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 15);
+  uint8_t *sV = sK + T16K;
+  uint8_t *sP = sV + T16K;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + T32K);
+  uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *s_full = bars + 3, *s_empty = bars + 4,
+           *p_full = bars + 5, *o_full = bars + 6, *o_empty = bars + 7;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
@@ -111,34 +137,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(kv_full + i, 1);
-      mbar_init(kv_empty + i, 1);
-      mbar_init(s_full + i, 1);
-      mbar_init(s_empty + i, 4);
-      mbar_init(p_full + i, 4);
-      mbar_init(o_full + i, 1);
-      mbar_init(o_empty + i, 4);
-    }
+    mbar_init(k_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 256;
+  const uint32_t tS = tmem, tO = tmem + 128;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, T16K);
       tma_load_3d(&tmQKV, q_full, sQ, h * HD, q0, b);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        if (j >= 2) mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full + s, 2 * T16K);
-        tma_load_3d(&tmQKV, kv_full + s, sK + s * T16K, C + h * HD, j * TILE, b);
-        tma_load_3d(&tmQKV, kv_full + s, sV + s * T16K, 2 * C + h * HD, j * TILE, b);
+        if (j > 0) mbar_wait(s_full, (j - 1) & 1);    // S_{j-1} = Q K_{j-1}^T finished: K buffer is free
+        mbar_arrive_expect_tx(k_full, T16K);
+        tma_load_3d(&tmQKV, k_full, sK, C + h * HD, j * TILE, b);
+        if (j > 0) mbar_wait(o_full, (j - 1) & 1);    // P_{j-1} V_{j-1} finished: V buffer is free
+        mbar_arrive_expect_tx(v_full, T16K);
+        tma_load_3d(&tmQKV, v_full, sV, 2 * C + h * HD, j * TILE, b);
       }
     }
   } else if (warp == 1) {
@@ -147,28 +172,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       constexpr uint32_t idesc_o = make_idesc(TILE, HD, 0, 1);     // O = P V   : V is MN-major
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       mbar_wait(q_full, 0);
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(kv_full + s, (j >> 1) & 1);
-        if (j >= 2) mbar_wait(s_empty + s, ((j >> 1) & 1) ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tS + s * TILE, desc_kmajor(aQ, k), desc_kmajor(aK + s * T16K, k), idesc_s, k > 0);
-        umma_commit(s_full + s);
-      };
-      issue_s(0);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        if (j + 1 < nkv) issue_s(j + 1);
-        mbar_wait(p_full + s, (j >> 1) & 1);
-        if (j >= 2) mbar_wait(o_empty + s, ((j >> 1) & 1) ^ 1);
+        mbar_wait(k_full, j & 1);
+        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tO + s * HD, desc_kmajor(aP + s * T32K, k), desc_mnmajor(aV + s * T16K, k), idesc_o, k > 0);
-        umma_commit(o_full + s);
-        umma_commit(kv_empty + s);
+        for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_s, k > 0);
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
+        mbar_wait(v_full, j & 1);
+        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_bf16(tO, desc_kmajor(aP, k), desc_mnmajor(aV, k), idesc_o, k > 0);
+        umma_commit(o_full);
       }
     }
   } else {
@@ -180,76 +197,81 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     for (int i = 0; i < 64; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      const int s = j & 1;
-      mbar_wait(s_full + s, (j >> 1) & 1);
-      tc_fence_after();
       const int kv0 = j * TILE;
-      // pass 1: row maximum of the scaled scores
-      float m_new = m_run;
+      const bool tail = kv0 + TILE > p.T;            // only the last key block has invalid columns
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row maximum of the raw scores (scale > 0, applied once to the maximum)
+      float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float v[32];
-        tmem_ld32(tS + lane_addr + s * TILE + c * 32, v);
+        tmem_ld32(tS + lane_addr + c * 32, v);
+        if (tail) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float t = (kv0 + c * 32 + i < p.T) ? v[i] * p.scale_log2 : -INFINITY;
-          m_new = fmaxf(m_new, t);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (kv0 + c * 32 + i < p.T) ? v[i] : -INFINITY);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
         }
       }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float alpha = fast_exp2(m_run - m_new);
-      // pass 2: probabilities -> smem (bf16), row sum
-      float l_add = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(tS + lane_addr + s * TILE + c * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float t = (kv0 + c * 32 + i < p.T) ? fast_exp2(v[i] * p.scale_log2 - m_new) : 0.f;
-          v[i] = t;
-          l_add += t;
-        }
-        store_row32_sw128(sP + s * T32K, row, c * 32, v);
-      }
-      tc_fence_before();
-      fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty + s);
-        mbar_arrive(p_full + s);
-      }
-      // fold in the previous block's P V, then rescale to the new maximum
+      // fold in the previous block's P V (its completion also frees the P buffer), rescale
       if (j > 0) {
-        const int sp = (j - 1) & 1;
-        mbar_wait(o_full + sp, ((j - 1) >> 1) & 1);
+        mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float v[32];
-          tmem_ld32(tO + lane_addr + sp * HD + c * 32, v);
+          tmem_ld32(tO + lane_addr + c * 32, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[c * 32 + i] += v[i];
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty + sp);
-      }
+        if (lane == 0) mbar_arrive(o_empty);
+        if (alpha != 1.f) {
 #pragma unroll
-      for (int i = 0; i < 64; ++i) o[i] *= alpha;
+          for (int i = 0; i < 64; ++i) o[i] *= alpha;
+        }
+      }
+      // pass 2: probabilities -> smem (bf16), row sum
+      float l_add = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float v[32];
+        tmem_ld32(tS + lane_addr + c * 32, v);
+        if (tail) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            v[i] = (kv0 + c * 32 + i < p.T) ? fast_exp2(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fast_exp2(fmaf(v[i], p.scale_log2, -m_new));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) l_add += v[i];
+        store_row32(sP, TILE, row, c * 32, v);
+      }
+      tc_fence_before();
+      fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty);
+        mbar_arrive(p_full);
+      }
       l_run = l_run * alpha + l_add;
       m_run = m_new;
     }
-    {
-      const int sp = (nkv - 1) & 1;
-      mbar_wait(o_full + sp, ((nkv - 1) >> 1) & 1);
-      tc_fence_after();
+    mbar_wait(o_full, (nkv - 1) & 1);
+    tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(tO + lane_addr + sp * HD + c * 32, v);
+    for (int c = 0; c < 2; ++c) {
+      float v[32];
+      tmem_ld32(tO + lane_addr + c * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += v[i];
-      }
+      for (int i = 0; i < 32; ++i) o[c * 32 + i] += v[i];
     }
     const int t = q0 + row;
     if (t < p.T) {
@@ -261,7 +283,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, TMEM_COLS);
   }
 }
 
@@ -299,24 +321,24 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16 *__restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, dK / dV: one CTA per (key block, head, image); loops over query blocks
+// backward, dK / dV: one CTA per (128-key block, head, image); loops over 64-query tiles
 // ------------------------------------------------------------------------------------------------
-constexpr int BWD_SMEM = 2 * T16K /*resident pair*/ + 2 * 2 * T16K /*streamed pair x 2 stages*/ + 2 * T32K + 2 * TILE * 4 + 1024 + 256;
+constexpr int DKDV_SMEM = 2 * T16K /*K, V*/ + 2 * 2 * T8K /*Q, dO x 2 stages*/ + 2 * T16K /*P^T, dS^T*/ + 2 * HALF * 4 + 1024 + 128;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                     const AttnParams p) {
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ,
+                     const __grid_constant__ CUtensorMap tmDO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sK = smem;
   uint8_t *sV = sK + T16K;
-  uint8_t *sQ = sV + T16K;            // 2 stages
-  uint8_t *sDO = sQ + 2 * T16K;       // 2 stages
-  uint8_t *sPT = sDO + 2 * T16K;      // P^T   [keys x queries]
-  uint8_t *sDST = sPT + T32K;         // dS^T
-  float *sLse = reinterpret_cast<float *>(sDST + T32K);
-  float *sD = sLse + TILE;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sD + TILE);
+  uint8_t *sQ = sV + T16K;            // 2 stages x 8 KB
+  uint8_t *sDO = sQ + 2 * T8K;        // 2 stages x 8 KB
+  uint8_t *sPT = sDO + 2 * T8K;       // P^T   [128 keys x 64 queries]
+  uint8_t *sDST = sPT + T16K;         // dS^T
+  float *sLse = reinterpret_cast<float *>(sDST + T16K);
+  float *sD = sLse + HALF;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sD + HALF);
   uint64_t *kv_full = bars, *q_full = bars + 1, *q_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 6,
            *p_full = bars + 7, *acc_full = bars + 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
@@ -324,10 +346,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
   const int C = p.H * HD;
-  const int nq = (p.T + TILE - 1) / TILE;
+  const int nq = (p.T + HALF - 1) / HALF;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -340,54 +363,54 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
+  const uint32_t tST = tmem, tDPT = tmem + 64, tDV = tmem + 128, tDK = tmem + 192;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, 2 * T16K);
-      tma_load_3d(&tmQKV, kv_full, sK, C + h * HD, k0, b);
-      tma_load_3d(&tmQKV, kv_full, sV, 2 * C + h * HD, k0, b);
+      tma_load_3d(&tmKV, kv_full, sK, C + h * HD, k0, b);
+      tma_load_3d(&tmKV, kv_full, sV, 2 * C + h * HD, k0, b);
       for (int i = 0; i < nq; ++i) {
         const int s = i & 1;
         if (i >= 2) mbar_wait(q_empty + s, ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full + s, 2 * T16K);
-        tma_load_3d(&tmQKV, q_full + s, sQ + s * T16K, h * HD, i * TILE, b);
-        tma_load_3d(&tmDO, q_full + s, sDO + s * T16K, h * HD, i * TILE, b);
+        mbar_arrive_expect_tx(q_full + s, 2 * T8K);
+        tma_load_3d(&tmQ, q_full + s, sQ + s * T8K, h * HD, i * HALF, b);
+        tma_load_3d(&tmDO, q_full + s, sDO + s * T8K, h * HD, i * HALF, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(TILE, TILE, 0, 0);
-      constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);
+      constexpr uint32_t idesc_s = make_idesc(TILE, HALF, 0, 0);   // [128 keys] x [64 queries]
+      constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);     // [128 keys] x [64 hd], B MN-major
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO),
                      aPT = smem_u32(sPT), aDST = smem_u32(sDST);
       mbar_wait(kv_full, 0);
       for (int i = 0; i < nq; ++i) {
         const int s = i & 1;
         mbar_wait(q_full + s, (i >> 1) & 1);
-        if (i >= 1) mbar_wait(s_empty, (i - 1) & 1);   // softmax finished reading S^T / dP^T of block i-1
+        if (i >= 1) mbar_wait(s_empty, (i - 1) & 1);   // softmax finished reading S^T / dP^T of tile i-1
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // S^T = K Q^T
-          umma_bf16(tST, desc_kmajor(aK, k), desc_kmajor(aQ + s * T16K, k), idesc_s, k > 0);
+          umma_bf16(tST, desc_kmajor(aK, k), desc_kmajor(aQ + s * T8K, k), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dP^T = V dO^T
-          umma_bf16(tDPT, desc_kmajor(aV, k), desc_kmajor(aDO + s * T16K, k), idesc_s, k > 0);
+          umma_bf16(tDPT, desc_kmajor(aV, k), desc_kmajor(aDO + s * T8K, k), idesc_s, k > 0);
         umma_commit(s_full);
         mbar_wait(p_full, i & 1);     // P^T and dS^T are in smem
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dV += P^T dO
-          umma_bf16(tDV, desc_kmajor(aPT, k), desc_mnmajor(aDO + s * T16K, k), idesc_g, (i > 0 || k > 0));
+        for (int k = 0; k < 4; ++k)   // dV += P^T dO      (K = 64 queries)
+          umma_bf16(tDV, desc_kmajor(aPT, k), desc_mnmajor(aDO + s * T8K, k), idesc_g, (i > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dK += dS^T Q
-          umma_bf16(tDK, desc_kmajor(aDST, k), desc_mnmajor(aQ + s * T16K, k), idesc_g, (i > 0 || k > 0));
-        umma_commit(q_empty + s);     // Q/dO stage and the P^T/dS^T buffers are free once these finish
+        for (int k = 0; k < 4; ++k)   // dK += dS^T Q
+          umma_bf16(tDK, desc_kmajor(aDST, k), desc_mnmajor(aQ + s * T8K, k), idesc_g, (i > 0 || k > 0));
+        umma_commit(q_empty + s);     // Q/dO stage (and the P^T/dS^T buffers) free once these finish
       }
       umma_commit(acc_full);
     }
@@ -400,32 +423,33 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     const float *lse_b = p.lse + ((size_t)b * p.H + h) * p.T;
     const float *d_b = p.dvec + ((size_t)b * p.H + h) * p.T;
     for (int i = 0; i < nq; ++i) {
-      const int qi = i * TILE + tid;
-      // previous iteration's readers of sLse/sD are done (they passed the barrier below and the
-      // MMA of this iteration cannot complete before p_full of the previous one)
+      named_bar_sync(1, 128);                // everyone is done reading sLse/sD of the previous tile
+      if (tid < HALF) {
+        const int qi = i * HALF + tid;
+        sLse[tid] = qi < p.T ? lse_b[qi] * LOG2E : 0.f;
+        sD[tid] = qi < p.T ? d_b[qi] : 0.f;
+      }
       named_bar_sync(1, 128);
-      sLse[tid] = qi < p.T ? lse_b[qi] * LOG2E : 0.f;
-      sD[tid] = qi < p.T ? d_b[qi] : 0.f;
-      named_bar_sync(1, 128);
+      // s_full(i) is committed after the dV/dK MMAs of tile i-1 (in-order tensor pipe), so once it
+      // fires the P^T / dS^T buffers are free as well
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      // the P^T / dS^T buffers were last read by the MMAs of block i-1; they are complete because
-      // s_full(i) was committed after them (in-order tensor pipe)
+      const bool tail = i * HALF + HALF > p.T;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float st[32], dp[32];
         tmem_ld32(tST + lane_addr + c * 32, st);
         tmem_ld32(tDPT + lane_addr + c * 32, dp);
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
           const int col = c * 32 + q;
-          const bool ok = key_ok && (i * TILE + col < p.T);
-          const float pr = ok ? fast_exp2(st[q] * p.scale_log2 - sLse[col]) : 0.f;
+          const bool ok = key_ok && (!tail || i * HALF + col < p.T);
+          const float pr = ok ? fast_exp2(fmaf(st[q], p.scale_log2, -sLse[col])) : 0.f;
           st[q] = pr;
-          dp[q] = ok ? pr * (dp[q] - sD[col]) : 0.f;
+          dp[q] = pr * (dp[q] - sD[col]);
         }
-        store_row32_sw128(sPT, row, c * 32, st);
-        store_row32_sw128(sDST, row, c * 32, dp);
+        store_row32(sPT, TILE, row, c * 32, st);
+        store_row32(sDST, TILE, row, c * 32, dp);
       }
       tc_fence_before();
       fence_proxy_async();
@@ -460,24 +484,26 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, dQ: one CTA per (query block, head, image); loops over key blocks
+// backward, dQ: one CTA per (128-query block, head, image); loops over 64-key tiles
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const AttnParams p) {
+constexpr int DQ_SMEM = 2 * T16K /*Q, dO*/ + 2 * 2 * T8K /*K, V x 2 stages*/ + T16K /*dS*/ + 1024 + 128;
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
+                   const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sQ = smem;
   uint8_t *sDO = sQ + T16K;
-  uint8_t *sK = sDO + T16K;           // 2 stages
-  uint8_t *sV = sK + 2 * T16K;        // 2 stages
-  uint8_t *sDS = sV + 2 * T16K;       // dS [queries x keys]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sDS + 2 * T32K + 2 * TILE * 4);
+  uint8_t *sK = sDO + T16K;           // 2 stages x 8 KB
+  uint8_t *sV = sK + 2 * T8K;         // 2 stages x 8 KB
+  uint8_t *sDS = sV + 2 * T8K;        // dS [128 queries x 64 keys]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sDS + T16K);
   uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 6,
            *p_full = bars + 7, *acc_full = bars + 8;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
@@ -485,11 +511,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
   const int C = p.H * HD;
-  const int nkv = (p.T + TILE - 1) / TILE;
+  const int nkv = (p.T + HALF - 1) / HALF;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmDO);
+    tma_prefetch_desc(&tmKV);
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(kv_full + i, 1);
@@ -501,29 +528,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;
+  const uint32_t tS = tmem, tDP = tmem + 64, tDQ = tmem + 128;
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, 2 * T16K);
-      tma_load_3d(&tmQKV, q_full, sQ, h * HD, q0, b);
+      tma_load_3d(&tmQ, q_full, sQ, h * HD, q0, b);
       tma_load_3d(&tmDO, q_full, sDO, h * HD, q0, b);
       for (int j = 0; j < nkv; ++j) {
         const int s = j & 1;
         if (j >= 2) mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full + s, 2 * T16K);
-        tma_load_3d(&tmQKV, kv_full + s, sK + s * T16K, C + h * HD, j * TILE, b);
-        tma_load_3d(&tmQKV, kv_full + s, sV + s * T16K, 2 * C + h * HD, j * TILE, b);
+        mbar_arrive_expect_tx(kv_full + s, 2 * T8K);
+        tma_load_3d(&tmKV, kv_full + s, sK + s * T8K, C + h * HD, j * HALF, b);
+        tma_load_3d(&tmKV, kv_full + s, sV + s * T8K, 2 * C + h * HD, j * HALF, b);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc(TILE, TILE, 0, 0);
+      constexpr uint32_t idesc_s = make_idesc(TILE, HALF, 0, 0);
       constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);
       const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sDS);
       mbar_wait(q_full, 0);
@@ -534,16 +561,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // S = Q K^T
-          umma_bf16(tS, desc_kmajor(aQ, k), desc_kmajor(aK + s * T16K, k), idesc_s, k > 0);
+          umma_bf16(tS, desc_kmajor(aQ, k), desc_kmajor(aK + s * T8K, k), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // dP = dO V^T
-          umma_bf16(tDP, desc_kmajor(aDO, k), desc_kmajor(aV + s * T16K, k), idesc_s, k > 0);
+          umma_bf16(tDP, desc_kmajor(aDO, k), desc_kmajor(aV + s * T8K, k), idesc_s, k > 0);
         umma_commit(s_full);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dQ += dS K
-          umma_bf16(tDQ, desc_kmajor(aDS, k), desc_mnmajor(aK + s * T16K, k), idesc_g, (j > 0 || k > 0));
+        for (int k = 0; k < 4; ++k)   // dQ += dS K      (K = 64 keys)
+          umma_bf16(tDQ, desc_kmajor(aDS, k), desc_mnmajor(aK + s * T8K, k), idesc_g, (j > 0 || k > 0));
         umma_commit(kv_empty + s);
       }
       umma_commit(acc_full);
@@ -559,18 +586,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      const bool tail = j * HALF + HALF > p.T;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float sv[32], dp[32];
         tmem_ld32(tS + lane_addr + c * 32, sv);
         tmem_ld32(tDP + lane_addr + c * 32, dp);
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-          const bool ok = row_ok && (j * TILE + c * 32 + q < p.T);
-          const float pr = ok ? fast_exp2(sv[q] * p.scale_log2 - lse2) : 0.f;
+          const bool ok = row_ok && (!tail || j * HALF + c * 32 + q < p.T);
+          const float pr = ok ? fast_exp2(fmaf(sv[q], p.scale_log2, -lse2)) : 0.f;
           dp[q] = pr * (dp[q] - dsum);
         }
-        store_row32_sw128(sDS, row, c * 32, dp);
+        store_row32(sDS, TILE, row, c * 32, dp);
       }
       tc_fence_before();
       fence_proxy_async();
@@ -596,7 +624,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, TMEM_COLS);
   }
 }
 
@@ -605,6 +633,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 // ------------------------------------------------------------------------------------------------
 static int set_smem(const void *fn, int bytes) {
   ASIS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  ASIS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   return ASIS_OK;
 }
 
@@ -641,13 +670,15 @@ int attention_tc_backward(const void *qkv, const void *out, const float *lse, co
   ASIS_REQUIRE(hd == HD, "attention(bf16): head_dim must be 64");
   ASIS_REQUIRE(aligned16(qkv) && aligned16(out) && aligned16(dout) && aligned16(dqkv) && ws, "attention(bf16): pointers must be 16-byte aligned");
   const int C = H * HD;
-  CUtensorMap tq, tdo;
-  if (int rc = make_tmap_3d(&tq, qkv, 3 * C, T, B, 3 * C, (uint64_t)T * 3 * C, HD, TILE, 1)) return rc;
-  if (int rc = make_tmap_3d(&tdo, dout, C, T, B, C, (uint64_t)T * C, HD, TILE, 1)) return rc;
+  CUtensorMap tq128, tq64, tdo128, tdo64;
+  if (int rc = make_tmap_3d(&tq128, qkv, 3 * C, T, B, 3 * C, (uint64_t)T * 3 * C, HD, TILE, 1)) return rc;
+  if (int rc = make_tmap_3d(&tq64, qkv, 3 * C, T, B, 3 * C, (uint64_t)T * 3 * C, HD, HALF, 1)) return rc;
+  if (int rc = make_tmap_3d(&tdo128, dout, C, T, B, C, (uint64_t)T * C, HD, TILE, 1)) return rc;
+  if (int rc = make_tmap_3d(&tdo64, dout, C, T, B, C, (uint64_t)T * C, HD, HALF, 1)) return rc;
   static bool configured = false;
   if (!configured) {
-    if (int rc = set_smem((const void *)attn_bwd_dkdv_kernel, BWD_SMEM)) return rc;
-    if (int rc = set_smem((const void *)attn_bwd_dq_kernel, BWD_SMEM)) return rc;
+    if (int rc = set_smem((const void *)attn_bwd_dkdv_kernel, DKDV_SMEM)) return rc;
+    if (int rc = set_smem((const void *)attn_bwd_dq_kernel, DQ_SMEM)) return rc;
     configured = true;
   }
   float *dvec = (float *)ws;
@@ -665,9 +696,9 @@ int attention_tc_backward(const void *qkv, const void *out, const float *lse, co
   p.dvec = dvec;
   p.dqkv = (bf16 *)dqkv;
   dim3 grid((T + TILE - 1) / TILE, H, B);
-  attn_bwd_dkdv_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(tq, tdo, p);
+  attn_bwd_dkdv_kernel<<<grid, ATT_THREADS, DKDV_SMEM, st>>>(tq128, tq64, tdo64, p);
   ASIS_LAUNCHED();
-  attn_bwd_dq_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(tq, tdo, p);
+  attn_bwd_dq_kernel<<<grid, ATT_THREADS, DQ_SMEM, st>>>(tq128, tdo128, tq64, p);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }

@@ -7,6 +7,9 @@
 //   warps 2..9  epilogue       tcgen05.ld -> registers -> fused epilogue (bias / exact GELU /
 //                              LayerScale + residual / GELU' / accumulate) -> 16-byte global stores
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
+// Thread-block clusters of CL CTAs along M share the B tile: each CTA fetches 1/CL of it and TMA
+// multicasts the slice into every CTA of the cluster (a 128x256 tile per CTA alone needs
+// ~14 KB/clk chip-wide from L2 at full tensor rate, more than L2 delivers; CL = 2 cuts it by 1.5x).
 // Tails in M, N and K come for free from TMA zero fill; stores are masked.
 //
 // Both operands may be K-major (nn.Linear forward: x[R,K], W[N,K]) or MN-major (input gradient:
@@ -33,7 +36,7 @@ constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers
 
 struct GemmTcParams {
   int M, N, K;
-  int m_tiles, n_tiles, splits, kb_per_split, kb_total;
+  int m_tiles, m_groups, n_tiles, splits, kb_per_split, kb_total;
   int atomic_out;  // split-K: combine with red.global.add.f32
   EpiArgs epi;
 };
@@ -138,7 +141,7 @@ __device__ __forceinline__ void epi_row32(const GemmTcParams &p, int row, int co
   }
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -150,13 +153,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CL, num_clusters = gridDim.x / CL;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + s, 1);
-      mbar_init(empty_bar + s, 1);
+      mbar_init(empty_bar + s, CL);   // every CTA of the cluster releases the stage (they all write into it)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + a, 1);
@@ -167,18 +173,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();     // peers' barriers are initialised before anything remote touches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+  const int total_tiles = p.m_groups * p.n_tiles * p.splits;   // per cluster: CL adjacent m-tiles at once
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile % p.m_tiles;
-        const int rest = tile / p.m_tiles;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int m_blk = (tile % p.m_groups) * CL + crank;
+        const int rest = tile / p.m_groups;
         const int n_blk = rest % p.n_tiles;
         const int split = rest / p.n_tiles;
         const int kb0 = split * p.kb_per_split;
@@ -187,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t *sa = smem + stage * STAGE_BYTES;
           uint8_t *sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(full_bar + stage, STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar + stage, STAGE_BYTES);   // own A + the CL slices of B
           if (A_MN == 0) {
             tma_load_2d(&tmA, full_bar + stage, sa, kb * BK, m_blk * BM);
           } else {
@@ -195,12 +202,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < BM / 64; ++j)
               tma_load_2d(&tmA, full_bar + stage, sa + j * BOX_BYTES, m_blk * BM + j * 64, kb * BK);
           }
-          if (B_MN == 0) {
-            tma_load_2d(&tmB, full_bar + stage, sb, kb * BK, n_blk * BN);
-          } else {
+          if (CL == 1) {
+            if (B_MN == 0) {
+              tma_load_2d(&tmB, full_bar + stage, sb, kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(&tmB, full_bar + stage, sb + j * BOX_BYTES, n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(&tmB, full_bar + stage, sb + j * BOX_BYTES, n_blk * BN + j * 64, kb * BK);
+            }
+          } else {
+            // this CTA's 1/CL slice of B, multicast to the whole cluster
+            constexpr int ROWS = BN / CL;
+            if (B_MN == 0) {
+              tma_load_2d_mc(&tmB, full_bar + stage, sb + crank * ROWS * 128, kb * BK, n_blk * BN + crank * ROWS, kMask);
+            } else {
+#pragma unroll
+              for (int j = 0; j < ROWS / 64; ++j)
+                tma_load_2d_mc(&tmB, full_bar + stage, sb + (crank * (ROWS / 64) + j) * BOX_BYTES,
+                               n_blk * BN + crank * ROWS + j * 64, kb * BK, kMask);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -216,8 +236,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = (tile / p.m_tiles) / p.n_tiles;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int split = (tile / p.m_groups) / p.n_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         mbar_wait(tempty_bar + acc, acc_phase ^ 1);
@@ -235,7 +255,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint64_t db = B_MN == 0 ? smem_desc(sb + k * 32, 16, 1024) : smem_desc(sb + k * 2048, BOX_BYTES, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(empty_bar + stage);  // frees the smem stage when the MMAs above have read it
+          // frees the smem stage (in every CTA of the cluster) when the MMAs above have read it
+          if (CL == 1) umma_commit(empty_bar + stage);
+          else umma_commit_mc(empty_bar + stage, kMask);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -255,9 +277,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.epi.ldc % 8 == 0) && (!p.epi.aux || p.epi.ldaux % 8 == 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile % p.m_tiles;
-      const int n_blk = (tile / p.m_tiles) % p.n_tiles;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m_blk = (tile % p.m_groups) * CL + crank;
+      const int n_blk = (tile / p.m_groups) % p.n_tiles;
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
@@ -279,6 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();     // nobody leaves while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -344,16 +367,47 @@ int sm_count() {
   return n;
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int CL>
 static int launch_variant(const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ASIS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    ASIS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<A_MN, B_MN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
     configured = true;
   }
-  gemm_tc_kernel<A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(ta, tb, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ASIS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<A_MN, B_MN, CL>, ta, tb, p));
   ASIS_LAUNCHED();
   return ASIS_OK;
+}
+
+template <int CL>
+static int launch_majors(int a_major, int b_major, const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p,
+                         int grid, cudaStream_t st) {
+  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_K) return launch_variant<0, 0, CL>(ta, tb, p, grid, st);
+  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_MN) return launch_variant<0, 1, CL>(ta, tb, p, grid, st);
+  if (a_major == ASIS_MAJOR_MN && b_major == ASIS_MAJOR_MN) return launch_variant<1, 1, CL>(ta, tb, p, grid, st);
+  return launch_variant<1, 0, CL>(ta, tb, p, grid, st);
+}
+
+static int cluster_pref() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("ASIS_GEMM_CLUSTER");
+    v = e ? atoi(e) : 2;
+    if (v != 1 && v != 2 && v != 4) v = 2;
+  }
+  return v;
 }
 
 int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b_major, int64_t ldb, int M, int N,
@@ -366,8 +420,11 @@ int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b
   p.n_tiles = (N + BN - 1) / BN;
   p.kb_total = (K + BK - 1) / BK;
   p.epi = epi;
+  int CL = cluster_pref();
+  while (CL > 1 && p.m_tiles < CL) CL >>= 1;     // nothing to share the B tile with
+  p.m_groups = (p.m_tiles + CL - 1) / CL;
   const int sms = sm_count();
-  const int tiles = p.m_tiles * p.n_tiles;
+  const int tiles = p.m_groups * CL * p.n_tiles;
   int splits = 1;
   const bool can_split = epi.c_dtype == ASIS_F32 && (epi.kind == ASIS_EPI_ACCUMULATE || (epi.kind == ASIS_EPI_NONE && !epi.bias));
   if (can_split && tiles * 2 <= sms && p.kb_total >= 16) {
@@ -391,15 +448,16 @@ int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b
   if (a_major == ASIS_MAJOR_K) rc = make_tmap_2d(&ta, A, K, M, lda, BK, BM);
   else rc = make_tmap_2d(&ta, A, M, K, lda, 64, BK);
   if (rc) return rc;
-  if (b_major == ASIS_MAJOR_K) rc = make_tmap_2d(&tb, B, K, N, ldb, BK, BN);
+  if (b_major == ASIS_MAJOR_K) rc = make_tmap_2d(&tb, B, K, N, ldb, BK, BN / CL);   // one slice per CTA of the cluster
   else rc = make_tmap_2d(&tb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
-  const int total = tiles * splits;
-  const int grid = total < sms ? total : sms;
-  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_K) return launch_variant<0, 0>(ta, tb, p, grid, st);
-  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_MN) return launch_variant<0, 1>(ta, tb, p, grid, st);
-  if (a_major == ASIS_MAJOR_MN && b_major == ASIS_MAJOR_MN) return launch_variant<1, 1>(ta, tb, p, grid, st);
-  return launch_variant<1, 0>(ta, tb, p, grid, st);
+  const int cluster_tiles = p.m_groups * p.n_tiles * splits;
+  int clusters = sms / CL;
+  if (cluster_tiles < clusters) clusters = cluster_tiles;
+  const int grid = clusters * CL;
+  if (CL == 4) return launch_majors<4>(a_major, b_major, ta, tb, p, grid, st);
+  if (CL == 2) return launch_majors<2>(a_major, b_major, ta, tb, p, grid, st);
+  return launch_majors<1>(a_major, b_major, ta, tb, p, grid, st);
 }
 
 }  // namespace asis

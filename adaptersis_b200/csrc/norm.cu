@@ -67,45 +67,42 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const XT *__restr
 }
 
 // backward: warps stride over rows; per-lane partial dgamma/dbeta for the lane's columns, block
-// reduction through shared memory, one partial row per block -> workspace[block][2][C]
+// reduction through shared memory, one partial row per block -> workspace[block][2][C].
+// Each row is read twice (second read hits L1): pass 1 the two row sums, pass 2 dx and the column
+// partials -- keeping the row in registers instead costs ~200 registers/thread and one resident
+// block per SM, which measured 5x off the HBM roofline.
 template <typename DT, typename XT, int NV>
-__global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const DT *__restrict__ dy, const XT *__restrict__ x,
-                                                                const float *__restrict__ gamma,
-                                                                const float *__restrict__ mean,
-                                                                const float *__restrict__ rstd,
-                                                                const float *__restrict__ dres, float *__restrict__ dx,
-                                                                float *__restrict__ partial, int R, int C) {
+__global__ void __launch_bounds__(kLnWarps * 32, 2) ln_bwd_kernel(const DT *__restrict__ dy, const XT *__restrict__ x,
+                                                                   const float *__restrict__ gamma,
+                                                                   const float *__restrict__ mean,
+                                                                   const float *__restrict__ rstd,
+                                                                   const float *__restrict__ dres, float *__restrict__ dx,
+                                                                   float *__restrict__ partial, int R, int C) {
   __shared__ float red[kLnWarps][32 * 4 + 4];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  float dg[NV][4], db[NV][4], g[NV][4];
+  float dg[NV][4], db[NV][4];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int c = 4 * (lane + 32 * j);
+  for (int j = 0; j < NV; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) dg[j][i] = db[j][i] = g[j][i] = 0.f;
-    if (c < C) load4(gamma + c, g[j]);
-  }
+    for (int i = 0; i < 4; ++i) dg[j][i] = db[j][i] = 0.f;
   for (int row = blockIdx.x * kLnWarps + wid; row < R; row += gridDim.x * kLnWarps) {
     const float mu = mean[row], rs = rstd[row];
     const DT *dyr = dy + (size_t)row * C;
     const XT *xr = x + (size_t)row * C;
-    float d[NV][4], xh[NV][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = 4 * (lane + 32 * j);
       if (c < C) {
-        float xv[4];
-        load4(dyr + c, d[j]);
+        float d[4], xv[4], g[4];
+        load4(dyr + c, d);
         load4(xr + c, xv);
+        load4(gamma + c, g);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          xh[j][i] = (xv[i] - mu) * rs;
-          dg[j][i] += d[j][i] * xh[j][i];
-          db[j][i] += d[j][i];
-          d[j][i] *= g[j][i];  // d := dy * gamma
-          s1 += d[j][i];
-          s2 += d[j][i] * xh[j][i];
+          const float t = d[i] * g[i];
+          s1 += t;
+          s2 += t * ((xv[i] - mu) * rs);
         }
       }
     }
@@ -116,9 +113,17 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const DT *__restr
     for (int j = 0; j < NV; ++j) {
       const int c = 4 * (lane + 32 * j);
       if (c < C) {
-        float o[4];
+        float d[4], xv[4], g[4], o[4];
+        load4(dyr + c, d);
+        load4(xr + c, xv);
+        load4(gamma + c, g);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = rs * (d[j][i] - s1 - xh[j][i] * s2);
+        for (int i = 0; i < 4; ++i) {
+          const float xh = (xv[i] - mu) * rs;
+          dg[j][i] += d[i] * xh;
+          db[j][i] += d[i];
+          o[i] = rs * (d[i] * g[i] - s1 - xh * s2);
+        }
         if (dres) {
           float r4[4];
           load4(dres + (size_t)row * C + c, r4);
@@ -151,13 +156,24 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const DT *__restr
 }
 
 // out[c] (+)= sum over nparts of partial[p][c], fixed order
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__restrict__ partial, int nparts, int stride,
-                                                              float *__restrict__ out, int n, int accumulate) {
+// (columns [n, 2n) go to out2 when it is given: dgamma and dbeta of LayerNorm in one launch)
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const float *__restrict__ partial, int nparts, int stride,
+                                                              float *__restrict__ out, float *__restrict__ out2, int n,
+                                                              int accumulate) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n) return;
-  float t = 0.f;
-  for (int p = 0; p < nparts; ++p) t += partial[(size_t)p * stride + c];
-  out[c] = accumulate ? out[c] + t : t;
+  if (c >= (out2 ? 2 * n : n)) return;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  int p = 0;
+  for (; p + 3 < nparts; p += 4) {
+    t0 += partial[(size_t)p * stride + c];
+    t1 += partial[(size_t)(p + 1) * stride + c];
+    t2 += partial[(size_t)(p + 2) * stride + c];
+    t3 += partial[(size_t)(p + 3) * stride + c];
+  }
+  for (; p < nparts; ++p) t0 += partial[(size_t)p * stride + c];
+  const float t = (t0 + t1) + (t2 + t3);
+  float *dst = c < n ? out + c : out2 + (c - n);
+  *dst = accumulate ? *dst + t : t;
 }
 
 // column sums of X (optionally X*Y): block = 32 lanes x 8 row-lanes, lane owns 4 columns
@@ -242,7 +258,7 @@ static int ln_nv(int C) {
 
 static int ln_bwd_blocks(int R) {
   const int want = (R + kLnWarps - 1) / kLnWarps;
-  return want < 296 ? want : 296;  // 2 x 148 SMs
+  return want < 592 ? want : 592;  // 4 x 148 SMs
 }
 
 }  // namespace asis
@@ -295,12 +311,14 @@ extern "C" int asis_layernorm_backward(const void *dy, int dy_dtype, const void 
   float *partial = (float *)workspace;
   ASIS_DISPATCH_DTYPE(dy_dtype, DT, ASIS_DISPATCH_DTYPE(x_dtype, XT, LN_NV_SWITCH(nv, (ln_bwd_kernel<DT, XT, NV><<<blocks, kLnWarps * 32, 0, st>>>((const DT *)dy, (const XT *)x, gamma, mean, rstd, dres, dx, partial, R, C)))));
   ASIS_LAUNCHED();
-  if (dgamma) {
-    reduce_partials_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial, blocks, 2 * C, dgamma, C, accumulate);
+  if (dgamma && dbeta) {
+    reduce_partials_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(partial, blocks, 2 * C, dgamma, dbeta, C, accumulate);
     ASIS_LAUNCHED();
-  }
-  if (dbeta) {
-    reduce_partials_kernel<<<(C + 255) / 256, 256, 0, st>>>(partial + C, blocks, 2 * C, dbeta, C, accumulate);
+  } else if (dgamma) {
+    reduce_partials_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, blocks, 2 * C, dgamma, nullptr, C, accumulate);
+    ASIS_LAUNCHED();
+  } else if (dbeta) {
+    reduce_partials_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial + C, blocks, 2 * C, dbeta, nullptr, C, accumulate);
     ASIS_LAUNCHED();
   }
   return ASIS_OK;
@@ -333,7 +351,7 @@ extern "C" int asis_colsum(const void *X, int x_dtype, const void *Y, int y_dtyp
     ASIS_DISPATCH_DTYPE(x_dtype, XT, (colsum_kernel<XT, float, false><<<grid, 256, 0, st>>>((const XT *)X, nullptr, ld, partial, M, N)));
   }
   ASIS_LAUNCHED();
-  reduce_partials_kernel<<<(N + 255) / 256, 256, 0, st>>>(partial, rb, N, out, N, accumulate);
+  reduce_partials_kernel<<<(N + 127) / 128, 128, 0, st>>>(partial, rb, N, out, nullptr, N, accumulate);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }

@@ -87,5 +87,77 @@ def main(group):
                 print(f"attn bwd B={B} T={T} H={H}: dq {rel(dq, gq):.3e} dk {rel(dk, gk):.3e} dv {rel(dv, gv):.3e}", flush=True)
 
 
+def timeit(fn, iters=10):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def perf():
+    R = 21180
+    print("cluster =", os.environ.get("ASIS_GEMM_CLUSTER", "default(2)"))
+    for tag, M, N, Kd, am, bm, odt in [
+            ("qkv fwd K/K", R, 3072, 1024, MAJOR_K, MAJOR_K, torch.bfloat16),
+            ("proj fwd K/K", R, 1024, 1024, MAJOR_K, MAJOR_K, torch.bfloat16),
+            ("fc1 fwd K/K", R, 4096, 1024, MAJOR_K, MAJOR_K, torch.bfloat16),
+            ("fc2 fwd K/K", R, 1024, 4096, MAJOR_K, MAJOR_K, torch.bfloat16),
+            ("fc1 dgrad K/MN", R, 1024, 4096, MAJOR_K, MAJOR_MN, torch.bfloat16),
+            ("fc2 dgrad K/MN", R, 4096, 1024, MAJOR_K, MAJOR_MN, torch.bfloat16),
+            ("fc1 wgrad MN/MN", 4096, 1024, R, MAJOR_MN, MAJOR_MN, torch.float32),
+            ("proj wgrad MN/MN", 1024, 1024, R, MAJOR_MN, MAJOR_MN, torch.float32),
+            ("value_proj inj K/K", 12 * 6949, 1024, 1024, MAJOR_K, MAJOR_K, torch.bfloat16)]:
+        a = torch.randn((M, Kd) if am == MAJOR_K else (Kd, M), device=dev).bfloat16()
+        b = torch.randn((N, Kd) if bm == MAJOR_K else (Kd, N), device=dev).bfloat16()
+        ms = timeit(lambda: K.gemm(BF16, a, am, b, bm, M, N, Kd, odt))
+        print(f"gemm {tag:22s} M={M} N={N} K={Kd}: {ms * 1e3:8.1f} us  {2.0 * M * N * Kd / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    # fused epilogues on the fc1 / fc2 shapes
+    A = torch.randn(R, 1024, device=dev).bfloat16()
+    W1 = torch.randn(4096, 1024, device=dev).bfloat16()
+    bias = torch.randn(4096, device=dev)
+    ms = timeit(lambda: K.gemm(BF16, A, MAJOR_K, W1, MAJOR_K, R, 4096, 1024, torch.bfloat16, epilogue=EPI_GELU, bias=bias, want_aux_dtype=torch.bfloat16))
+    print(f"gemm fc1+bias+GELU(+aux): {ms * 1e3:8.1f} us  {2.0 * R * 4096 * 1024 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    G = torch.randn(R, 4096, device=dev).bfloat16()
+    W2 = torch.randn(1024, 4096, device=dev).bfloat16()
+    res = torch.randn(R, 1024, device=dev)
+    gam = torch.randn(1024, device=dev)
+    b2 = torch.randn(1024, device=dev)
+    ms = timeit(lambda: K.gemm(BF16, G, MAJOR_K, W2, MAJOR_K, R, 1024, 4096, torch.float32, epilogue=EPI_SCALE_RESIDUAL, bias=b2, gamma=gam, residual=res, want_aux_dtype=torch.bfloat16))
+    print(f"gemm fc2+bias+ls+residual(+aux): {ms * 1e3:8.1f} us  {2.0 * R * 4096 * 1024 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    B, T, H = 12, 1765, 16
+    qkv = torch.randn(B, T, 3 * H * 64, device=dev).bfloat16()
+    ms = timeit(lambda: K.attention_forward(BF16, qkv, B, T, H, 64))
+    print(f"attn fwd B={B} T={T} H={H}: {ms * 1e3:8.1f} us  {4.0 * B * H * T * T * 64 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    out, lse = K.attention_forward(BF16, qkv, B, T, H, 64)
+    dout = torch.randn_like(out)
+    ms = timeit(lambda: K.attention_backward(BF16, qkv, out, lse, dout, B, T, H, 64))
+    print(f"attn bwd: {ms * 1e3:8.1f} us  {10.0 * B * H * T * T * 64 / ms / 1e9:7.1f} TFLOP/s (algorithmic 5 GEMMs)", flush=True)
+    x = torch.randn(R, 1024, device=dev)
+    dy = torch.randn(R, 1024, device=dev).bfloat16()
+    w = torch.randn(1024, device=dev)
+    y, mean, rstd = K.layernorm_forward(x, w, w, 1e-6, torch.bfloat16)
+    ms = timeit(lambda: K.layernorm_backward(dy, x, w, mean, rstd, x))
+    print(f"ln_bwd R={R} C=1024: {ms * 1e3:8.1f} us  {R * 1024 * 14 / ms / 1e6:7.1f} GB/s", flush=True)
+    ms = timeit(lambda: K.layernorm_forward(x, w, w, 1e-6, torch.bfloat16))
+    print(f"ln_fwd: {ms * 1e3:8.1f} us  {R * 1024 * 6 / ms / 1e6:7.1f} GB/s", flush=True)
+    big = torch.randn(R, 4096, device=dev).bfloat16()
+    ms = timeit(lambda: K.colsum(big))
+    print(f"colsum [R,4096] bf16: {ms * 1e3:8.1f} us  {R * 4096 * 2 / ms / 1e6:7.1f} GB/s", flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "perf":
+        perf()
+        sys.exit(0)
     main(sys.argv[1])
