@@ -4,13 +4,17 @@
 // dropout); T = 1765 is not a multiple of the 128-row tiles: TMA zero-fills rows >= T and the
 // softmax masks key columns >= T.
 //
-// All three kernels: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = softmax (1 thread =
-// 1 TMEM lane = 1 row).  Each CTA is a *serial* chain  MMA -> softmax -> MMA  with single-buffered
-// TMEM / smem, sized (<= 96 KB smem, 256 TMEM columns) so that TWO CTAs are resident per SM and
-// overlap one CTA's softmax (MUFU/FMA bound) with the other's tensor-core work.
+// All three kernels: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 and 6-9 = two softmax
+// warpgroups (1 thread = 1 TMEM lane = 1 row).  Consecutive tiles alternate between the two
+// warpgroups, each with its own TMEM score buffers and smem P buffer, so the tensor core works on
+// tile i+1 / the GEMMs that consume tile i-1 while a warpgroup is in the MUFU/FMA-bound softmax of
+// tile i, and every SM sub-partition has two softmax warps to hide latency.  (A first version with
+// one warpgroup per CTA measured 16 % of the tensor peak; two resident single-buffered CTAs per SM
+// were slower still in the backward: the per-tile barrier round trips dominate.)
 // Forward  (grid: 128-query blocks x H x B), 128-key tiles:  S = Q K^T (TMEM) -> online softmax in
 //   registers -> P (bf16) into 128B-swizzled smem -> O_j = P V (V consumed MN-major straight from
-//   its TMA tile) -> accumulated in registers with the usual max-rescaling.
+//   its TMA tile) -> accumulated in registers with the usual max-rescaling.  The two warpgroups keep
+//   separate (max, sum, O) states over the even / odd key tiles and merge them at the end.
 // Backward (two atomic-free kernels, both recompute P from the saved log-sum-exp), 64-wide tiles:
 //   dK/dV kernel, one CTA per 128 keys:    S^T = K Q^T, dP^T = V dO^T  -> P^T, dS^T -> smem ->
 //                                          dV += P^T dO, dK += dS^T Q   (accumulated in TMEM)
@@ -22,7 +26,7 @@ namespace asis {
 
 using namespace tc;
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 320;      // TMA warp, MMA warp, 2 x 4 softmax warps
 constexpr int TILE = 128;      // query / key rows per tile
 constexpr int HD = 64;
 constexpr int T16K = TILE * HD * 2;           // one 128 x 64 bf16 tile
@@ -109,25 +113,26 @@ struct AttnParams {
 
 constexpr int HALF = 64;                     // key / query tile width of the backward kernels
 constexpr int T8K = HALF * HD * 2;           // one 64 x 64 bf16 tile
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;
 
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-constexpr int FWD_SMEM = T16K /*Q*/ + T16K /*K*/ + T16K /*V*/ + T32K /*P*/ + 1024 + 128;
+constexpr int FWD_STAGES = 3;
+constexpr int FWD_SMEM = T16K /*Q*/ + FWD_STAGES * 2 * T16K /*K,V*/ + 2 * T32K /*P per warpgroup*/ + 1024 + 256;
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sQ = smem;
-  uint8_t *sK = sQ + T16K;
-  uint8_t *sV = sK + T16K;
-  uint8_t *sP = sV + T16K;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + T32K);
-  uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *s_full = bars + 3, *s_empty = bars + 4,
-           *p_full = bars + 5, *o_full = bars + 6, *o_empty = bars + 7;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8);
+  uint8_t *sK = sQ + T16K;                       // FWD_STAGES tiles
+  uint8_t *sV = sK + FWD_STAGES * T16K;          // FWD_STAGES tiles
+  uint8_t *sP = sV + FWD_STAGES * T16K;          // one 32 KB buffer per warpgroup
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * T32K);
+  uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = kv_full + FWD_STAGES, *s_full = kv_empty + FWD_STAGES,
+           *s_empty = s_full + 2, *p_full = s_empty + 2, *o_full = p_full + 2, *o_empty = o_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
@@ -137,13 +142,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
-    mbar_init(k_full, 1);
-    mbar_init(v_full, 1);
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    for (int i = 0; i < FWD_STAGES; ++i) {
+      mbar_init(kv_full + i, 1);
+      mbar_init(kv_empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full + i, 1);
+      mbar_init(s_empty + i, 4);
+      mbar_init(p_full + i, 4);
+      mbar_init(o_full + i, 1);
+      mbar_init(o_empty + i, 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -151,19 +160,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 128;
+  const uint32_t tS = tmem, tO = tmem + 256;     // S[w] at w*128, O[w] at 256 + w*64
 
   if (warp == 0) {
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, T16K);
       tma_load_3d(&tmQKV, q_full, sQ, h * HD, q0, b);
       for (int j = 0; j < nkv; ++j) {
-        if (j > 0) mbar_wait(s_full, (j - 1) & 1);    // S_{j-1} = Q K_{j-1}^T finished: K buffer is free
-        mbar_arrive_expect_tx(k_full, T16K);
-        tma_load_3d(&tmQKV, k_full, sK, C + h * HD, j * TILE, b);
-        if (j > 0) mbar_wait(o_full, (j - 1) & 1);    // P_{j-1} V_{j-1} finished: V buffer is free
-        mbar_arrive_expect_tx(v_full, T16K);
-        tma_load_3d(&tmQKV, v_full, sV, 2 * C + h * HD, j * TILE, b);
+        const int st = j % FWD_STAGES, use = j / FWD_STAGES;
+        if (use > 0) mbar_wait(kv_empty + st, (use - 1) & 1);
+        mbar_arrive_expect_tx(kv_full + st, 2 * T16K);
+        tma_load_3d(&tmQKV, kv_full + st, sK + st * T16K, C + h * HD, j * TILE, b);
+        tma_load_3d(&tmQKV, kv_full + st, sV + st * T16K, 2 * C + h * HD, j * TILE, b);
       }
     }
   } else if (warp == 1) {
@@ -172,41 +180,53 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       constexpr uint32_t idesc_o = make_idesc(TILE, HD, 0, 1);     // O = P V   : V is MN-major
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       mbar_wait(q_full, 0);
+      auto issue_s = [&](int j) {
+        const int w = j & 1, u = j >> 1, st = j % FWD_STAGES;
+        mbar_wait(kv_full + st, (j / FWD_STAGES) & 1);
+        if (u > 0) mbar_wait(s_empty + w, (u - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tS + w * TILE, desc_kmajor(aQ, k), desc_kmajor(aK + st * T16K, k), idesc_s, k > 0);
+        umma_commit(s_full + w);
+      };
+      issue_s(0);
+      if (nkv > 1) issue_s(1);
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(k_full, j & 1);
-        if (j > 0) mbar_wait(s_empty, (j - 1) & 1);
+        const int w = j & 1, u = j >> 1, st = j % FWD_STAGES;
+        mbar_wait(p_full + w, u & 1);
+        if (u > 0) mbar_wait(o_empty + w, (u - 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(aQ, k), desc_kmajor(aK, k), idesc_s, k > 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        mbar_wait(v_full, j & 1);
-        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k) umma_bf16(tO, desc_kmajor(aP, k), desc_mnmajor(aV, k), idesc_o, k > 0);
-        umma_commit(o_full);
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tO + w * HD, desc_kmajor(aP + w * T32K, k), desc_mnmajor(aV + st * T16K, k), idesc_o, k > 0);
+        umma_commit(o_full + w);
+        umma_commit(kv_empty + st);
+        if (j + 2 < nkv) issue_s(j + 2);
       }
     }
   } else {
+    const int w = (warp - 2) >> 2;                  // warpgroup: key tiles j == w (mod 2)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;            // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint8_t *myP = sP + w * T32K;
     float o[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    for (int j = 0; j < nkv; ++j) {
+    int u = 0;
+    for (int j = w; j < nkv; j += 2, ++u) {
       const int kv0 = j * TILE;
       const bool tail = kv0 + TILE > p.T;            // only the last key block has invalid columns
-      mbar_wait(s_full, j & 1);
+      mbar_wait(s_full + w, u & 1);
       tc_fence_after();
       // pass 1: row maximum of the raw scores (scale > 0, applied once to the maximum)
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float v[32];
-        tmem_ld32(tS + lane_addr + c * 32, v);
+        tmem_ld32(tS + lane_addr + w * TILE + c * 32, v);
         if (tail) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (kv0 + c * 32 + i < p.T) ? v[i] : -INFINITY);
@@ -217,20 +237,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float alpha = fast_exp2(m_run - m_new);
-      // fold in the previous block's P V (its completion also frees the P buffer), rescale
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+      // fold in this warpgroup's previous P V (its completion also frees the P buffer), rescale
+      if (u > 0) {
+        mbar_wait(o_full + w, (u - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
           float v[32];
-          tmem_ld32(tO + lane_addr + c * 32, v);
+          tmem_ld32(tO + lane_addr + w * HD + c * 32, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[c * 32 + i] += v[i];
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty);
+        if (lane == 0) mbar_arrive(o_empty + w);
         if (alpha != 1.f) {
 #pragma unroll
           for (int i = 0; i < 64; ++i) o[i] *= alpha;
@@ -241,7 +261,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         float v[32];
-        tmem_ld32(tS + lane_addr + c * 32, v);
+        tmem_ld32(tS + lane_addr + w * TILE + c * 32, v);
         if (tail) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -252,31 +272,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         }
 #pragma unroll
         for (int i = 0; i < 32; ++i) l_add += v[i];
-        store_row32(sP, TILE, row, c * 32, v);
+        store_row32(myP, TILE, row, c * 32, v);
       }
       tc_fence_before();
       fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty);
-        mbar_arrive(p_full);
+        mbar_arrive(s_empty + w);
+        mbar_arrive(p_full + w);
       }
       l_run = l_run * alpha + l_add;
       m_run = m_new;
     }
-    mbar_wait(o_full, (nkv - 1) & 1);
-    tc_fence_after();
+    if (u > 0) {
+      mbar_wait(o_full + w, (u - 1) & 1);
+      tc_fence_after();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(tO + lane_addr + c * 32, v);
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(tO + lane_addr + w * HD + c * 32, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[c * 32 + i] += v[i];
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] += v[i];
+      }
     }
-    const int t = q0 + row;
-    if (t < p.T) {
-      store_out64(p.out + ((size_t)b * p.T + t) * C + h * HD, o, 1.f / l_run);
-      p.lse[((size_t)b * p.H + h) * p.T + t] = (m_run + log2f(l_run)) * LN2;
+    // merge the two warpgroups' partial softmax states (all P V reads of smem are complete: every
+    // o_full has fired).  Warpgroup 1 publishes (m, l, O) through the P buffers.
+    float *xch = reinterpret_cast<float *>(sP);     // [128 rows][66 floats] = 33 KB of the 64 KB
+    if (w == 1) {
+      // the exchange area overlaps warpgroup 0's P buffer: wait for its last P V as well
+      mbar_wait(o_full + 0, (((nkv + 1) >> 1) - 1) & 1);
+      float *r = xch + row * 66;
+      r[0] = m_run;
+      r[1] = l_run;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) r[2 + i] = o[i];
+    }
+    named_bar_sync(1, 256);
+    if (w == 0) {
+      const float *r = xch + row * 66;
+      const float m1 = r[0], l1 = r[1];
+      const float m = fmaxf(m_run, m1);
+      const float a0 = fast_exp2(m_run - m), a1 = fast_exp2(m1 - m);
+      const float l = l_run * a0 + l1 * a1;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) o[i] = o[i] * a0 + r[2 + i] * a1;
+      const int t = q0 + row;
+      if (t < p.T) {
+        store_out64(p.out + ((size_t)b * p.T + t) * C + h * HD, o, 1.f / l);
+        p.lse[((size_t)b * p.H + h) * p.T + t] = (m + log2f(l)) * LN2;
+      }
     }
   }
   tc_fence_before();
@@ -323,25 +367,27 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16 *__restri
 // ------------------------------------------------------------------------------------------------
 // backward, dK / dV: one CTA per (128-key block, head, image); loops over 64-query tiles
 // ------------------------------------------------------------------------------------------------
-constexpr int DKDV_SMEM = 2 * T16K /*K, V*/ + 2 * 2 * T8K /*Q, dO x 2 stages*/ + 2 * T16K /*P^T, dS^T*/ + 2 * HALF * 4 + 1024 + 128;
+constexpr int BWD_STAGES = 4;
+constexpr int BWD_SMEM = 2 * T16K /*resident pair*/ + BWD_STAGES * 2 * T8K /*streamed pair*/ + 2 * 2 * T16K /*2 bufs x 2 WGs*/ +
+                         2 * 2 * HALF * 4 + 1024 + 256;
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ,
                      const __grid_constant__ CUtensorMap tmDO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sK = smem;
   uint8_t *sV = sK + T16K;
-  uint8_t *sQ = sV + T16K;            // 2 stages x 8 KB
-  uint8_t *sDO = sQ + 2 * T8K;        // 2 stages x 8 KB
-  uint8_t *sPT = sDO + 2 * T8K;       // P^T   [128 keys x 64 queries]
-  uint8_t *sDST = sPT + T16K;         // dS^T
-  float *sLse = reinterpret_cast<float *>(sDST + T16K);
-  float *sD = sLse + HALF;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sD + HALF);
-  uint64_t *kv_full = bars, *q_full = bars + 1, *q_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 6,
-           *p_full = bars + 7, *acc_full = bars + 8;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+  uint8_t *sQ = sV + T16K;                 // BWD_STAGES x 8 KB
+  uint8_t *sDO = sQ + BWD_STAGES * T8K;    // BWD_STAGES x 8 KB
+  uint8_t *sPT = sDO + BWD_STAGES * T8K;   // P^T   [128 keys x 64 queries], one per warpgroup
+  uint8_t *sDST = sPT + 2 * T16K;          // dS^T, one per warpgroup
+  float *sLse = reinterpret_cast<float *>(sDST + 2 * T16K);   // [2][64]
+  float *sD = sLse + 2 * HALF;                                // [2][64]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sD + 2 * HALF);
+  uint64_t *kv_full = bars, *q_full = bars + 1, *q_empty = q_full + BWD_STAGES, *s_full = q_empty + BWD_STAGES,
+           *s_empty = s_full + 2, *p_full = s_empty + 2, *acc_full = p_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
@@ -353,13 +399,15 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmDO);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < BWD_STAGES; ++i) {
       mbar_init(q_full + i, 1);
       mbar_init(q_empty + i, 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
-    mbar_init(p_full, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full + i, 1);
+      mbar_init(s_empty + i, 4);
+      mbar_init(p_full + i, 4);
+    }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -368,7 +416,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tST = tmem, tDPT = tmem + 64, tDV = tmem + 128, tDK = tmem + 192;
+  // S^T[w] at w*64, dP^T[w] at 128 + w*64, dV at 256, dK at 320
+  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -376,11 +425,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
       tma_load_3d(&tmKV, kv_full, sK, C + h * HD, k0, b);
       tma_load_3d(&tmKV, kv_full, sV, 2 * C + h * HD, k0, b);
       for (int i = 0; i < nq; ++i) {
-        const int s = i & 1;
-        if (i >= 2) mbar_wait(q_empty + s, ((i >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(q_full + s, 2 * T8K);
-        tma_load_3d(&tmQ, q_full + s, sQ + s * T8K, h * HD, i * HALF, b);
-        tma_load_3d(&tmDO, q_full + s, sDO + s * T8K, h * HD, i * HALF, b);
+        const int st = i % BWD_STAGES, use = i / BWD_STAGES;
+        if (use > 0) mbar_wait(q_empty + st, (use - 1) & 1);
+        mbar_arrive_expect_tx(q_full + st, 2 * T8K);
+        tma_load_3d(&tmQ, q_full + st, sQ + st * T8K, h * HD, i * HALF, b);
+        tma_load_3d(&tmDO, q_full + st, sDO + st * T8K, h * HD, i * HALF, b);
       }
     }
   } else if (warp == 1) {
@@ -390,95 +439,99 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO),
                      aPT = smem_u32(sPT), aDST = smem_u32(sDST);
       mbar_wait(kv_full, 0);
+      auto issue_scores = [&](int i) {      // S^T = K Q_i^T, dP^T = V dO_i^T into warpgroup (i & 1)'s buffers
+        const int w = i & 1, u = i >> 1, st = i % BWD_STAGES;
+        mbar_wait(q_full + st, (i / BWD_STAGES) & 1);
+        if (u > 0) mbar_wait(s_empty + w, (u - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tST + w * HALF, desc_kmajor(aK, k), desc_kmajor(aQ + st * T8K, k), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tDPT + w * HALF, desc_kmajor(aV, k), desc_kmajor(aDO + st * T8K, k), idesc_s, k > 0);
+        umma_commit(s_full + w);
+      };
+      issue_scores(0);
+      if (nq > 1) issue_scores(1);
       for (int i = 0; i < nq; ++i) {
-        const int s = i & 1;
-        mbar_wait(q_full + s, (i >> 1) & 1);
-        if (i >= 1) mbar_wait(s_empty, (i - 1) & 1);   // softmax finished reading S^T / dP^T of tile i-1
+        const int w = i & 1, u = i >> 1, st = i % BWD_STAGES;
+        mbar_wait(p_full + w, u & 1);         // P^T and dS^T of tile i are in smem
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // S^T = K Q^T
-          umma_bf16(tST, desc_kmajor(aK, k), desc_kmajor(aQ + s * T8K, k), idesc_s, k > 0);
+        for (int k = 0; k < 4; ++k)           // dV += P^T dO      (K = 64 queries)
+          umma_bf16(tDV, desc_kmajor(aPT + w * T16K, k), desc_mnmajor(aDO + st * T8K, k), idesc_g, (i > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // dP^T = V dO^T
-          umma_bf16(tDPT, desc_kmajor(aV, k), desc_kmajor(aDO + s * T8K, k), idesc_s, k > 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, i & 1);     // P^T and dS^T are in smem
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)   // dV += P^T dO      (K = 64 queries)
-          umma_bf16(tDV, desc_kmajor(aPT, k), desc_mnmajor(aDO + s * T8K, k), idesc_g, (i > 0 || k > 0));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)   // dK += dS^T Q
-          umma_bf16(tDK, desc_kmajor(aDST, k), desc_mnmajor(aQ + s * T8K, k), idesc_g, (i > 0 || k > 0));
-        umma_commit(q_empty + s);     // Q/dO stage (and the P^T/dS^T buffers) free once these finish
+        for (int k = 0; k < 4; ++k)           // dK += dS^T Q
+          umma_bf16(tDK, desc_kmajor(aDST + w * T16K, k), desc_mnmajor(aQ + st * T8K, k), idesc_g, (i > 0 || k > 0));
+        umma_commit(q_empty + st);
+        // issued after the dV/dK MMAs of tile i: when s_full of tile i+2 fires, warpgroup w may
+        // also overwrite its P^T / dS^T buffers (in-order tensor pipe)
+        if (i + 2 < nq) issue_scores(i + 2);
       }
       umma_commit(acc_full);
     }
   } else {
+    const int w = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;     // key row inside the tile
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int tid = threadIdx.x - 64;        // 0..127
+    const int tid = (threadIdx.x - 64) & 127;
     const bool key_ok = k0 + row < p.T;
     const float *lse_b = p.lse + ((size_t)b * p.H + h) * p.T;
     const float *d_b = p.dvec + ((size_t)b * p.H + h) * p.T;
-    for (int i = 0; i < nq; ++i) {
-      named_bar_sync(1, 128);                // everyone is done reading sLse/sD of the previous tile
+    float *myLse = sLse + w * HALF, *myD = sD + w * HALF;
+    uint8_t *myPT = sPT + w * T16K, *myDST = sDST + w * T16K;
+    int u = 0;
+    for (int i = w; i < nq; i += 2, ++u) {
+      named_bar_sync(1 + w, 128);            // the warpgroup is done reading myLse/myD of its previous tile
       if (tid < HALF) {
         const int qi = i * HALF + tid;
-        sLse[tid] = qi < p.T ? lse_b[qi] * LOG2E : 0.f;
-        sD[tid] = qi < p.T ? d_b[qi] : 0.f;
+        myLse[tid] = qi < p.T ? lse_b[qi] * LOG2E : 0.f;
+        myD[tid] = qi < p.T ? d_b[qi] : 0.f;
       }
-      named_bar_sync(1, 128);
-      // s_full(i) is committed after the dV/dK MMAs of tile i-1 (in-order tensor pipe), so once it
-      // fires the P^T / dS^T buffers are free as well
-      mbar_wait(s_full, i & 1);
+      named_bar_sync(1 + w, 128);
+      mbar_wait(s_full + w, u & 1);
       tc_fence_after();
       const bool tail = i * HALF + HALF > p.T;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         float st[32], dp[32];
-        tmem_ld32(tST + lane_addr + c * 32, st);
-        tmem_ld32(tDPT + lane_addr + c * 32, dp);
+        tmem_ld32(tST + lane_addr + w * HALF + c * 32, st);
+        tmem_ld32(tDPT + lane_addr + w * HALF + c * 32, dp);
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
           const int col = c * 32 + q;
           const bool ok = key_ok && (!tail || i * HALF + col < p.T);
-          const float pr = ok ? fast_exp2(fmaf(st[q], p.scale_log2, -sLse[col])) : 0.f;
+          const float pr = ok ? fast_exp2(fmaf(st[q], p.scale_log2, -myLse[col])) : 0.f;
           st[q] = pr;
-          dp[q] = pr * (dp[q] - sD[col]);
+          dp[q] = pr * (dp[q] - myD[col]);
         }
-        store_row32(sPT, TILE, row, c * 32, st);
-        store_row32(sDST, TILE, row, c * 32, dp);
+        store_row32(myPT, TILE, row, c * 32, st);
+        store_row32(myDST, TILE, row, c * 32, dp);
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty);
-        mbar_arrive(p_full);
+        mbar_arrive(s_empty + w);
+        mbar_arrive(p_full + w);
       }
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    // warpgroup 0 writes dV, warpgroup 1 writes dK
     const int t = k0 + row;
     float acc[64];
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       float v[32];
-      tmem_ld32(tDV + lane_addr + c * 32, v);
+      tmem_ld32((w == 0 ? tDV : tDK) + lane_addr + c * 32, v);
 #pragma unroll
       for (int q = 0; q < 32; ++q) acc[c * 32 + q] = v[q];
     }
-    if (t < p.T) store_out64(p.dqkv + ((size_t)b * p.T + t) * 3 * C + 2 * C + h * HD, acc, 1.f);
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(tDK + lane_addr + c * 32, v);
-#pragma unroll
-      for (int q = 0; q < 32; ++q) acc[c * 32 + q] = v[q];
-    }
-    if (t < p.T) store_out64(p.dqkv + ((size_t)b * p.T + t) * 3 * C + C + h * HD, acc, p.scale);
+    if (t < p.T)
+      store_out64(p.dqkv + ((size_t)b * p.T + t) * 3 * C + (w == 0 ? 2 * C : C) + h * HD, acc, w == 0 ? 1.f : p.scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -491,22 +544,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // backward, dQ: one CTA per (128-query block, head, image); loops over 64-key tiles
 // ------------------------------------------------------------------------------------------------
-constexpr int DQ_SMEM = 2 * T16K /*Q, dO*/ + 2 * 2 * T8K /*K, V x 2 stages*/ + T16K /*dS*/ + 1024 + 128;
-
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sQ = smem;
   uint8_t *sDO = sQ + T16K;
-  uint8_t *sK = sDO + T16K;           // 2 stages x 8 KB
-  uint8_t *sV = sK + 2 * T8K;         // 2 stages x 8 KB
-  uint8_t *sDS = sV + 2 * T8K;        // dS [128 queries x 64 keys]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sDS + T16K);
-  uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = bars + 3, *s_full = bars + 5, *s_empty = bars + 6,
-           *p_full = bars + 7, *acc_full = bars + 8;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 9);
+  uint8_t *sK = sDO + T16K;                // BWD_STAGES x 8 KB
+  uint8_t *sV = sK + BWD_STAGES * T8K;     // BWD_STAGES x 8 KB
+  uint8_t *sDS = sV + BWD_STAGES * T8K;    // dS [128 queries x 64 keys], one per warpgroup
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sDS + 4 * T16K + 2 * 2 * HALF * 4);
+  uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = kv_full + BWD_STAGES, *s_full = kv_empty + BWD_STAGES,
+           *s_empty = s_full + 2, *p_full = s_empty + 2, *acc_full = p_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
@@ -518,13 +569,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tma_prefetch_desc(&tmDO);
     tma_prefetch_desc(&tmKV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < BWD_STAGES; ++i) {
       mbar_init(kv_full + i, 1);
       mbar_init(kv_empty + i, 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(s_empty, 4);
-    mbar_init(p_full, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full + i, 1);
+      mbar_init(s_empty + i, 4);
+      mbar_init(p_full + i, 4);
+    }
     mbar_init(acc_full, 1);
     fence_barrier_init();
   }
@@ -533,7 +586,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tDP = tmem + 64, tDQ = tmem + 128;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;   // S[w] at w*64, dP[w] at 128 + w*64
 
   if (warp == 0) {
     if (lane == 0) {
@@ -541,11 +594,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tma_load_3d(&tmQ, q_full, sQ, h * HD, q0, b);
       tma_load_3d(&tmDO, q_full, sDO, h * HD, q0, b);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        if (j >= 2) mbar_wait(kv_empty + s, ((j >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(kv_full + s, 2 * T8K);
-        tma_load_3d(&tmKV, kv_full + s, sK + s * T8K, C + h * HD, j * HALF, b);
-        tma_load_3d(&tmKV, kv_full + s, sV + s * T8K, 2 * C + h * HD, j * HALF, b);
+        const int st = j % BWD_STAGES, use = j / BWD_STAGES;
+        if (use > 0) mbar_wait(kv_empty + st, (use - 1) & 1);
+        mbar_arrive_expect_tx(kv_full + st, 2 * T8K);
+        tma_load_3d(&tmKV, kv_full + st, sK + st * T8K, C + h * HD, j * HALF, b);
+        tma_load_3d(&tmKV, kv_full + st, sV + st * T8K, 2 * C + h * HD, j * HALF, b);
       }
     }
   } else if (warp == 1) {
@@ -554,28 +607,35 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);
       const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sDS);
       mbar_wait(q_full, 0);
+      auto issue_scores = [&](int j) {      // S = Q K_j^T, dP = dO V_j^T
+        const int w = j & 1, u = j >> 1, st = j % BWD_STAGES;
+        mbar_wait(kv_full + st, (j / BWD_STAGES) & 1);
+        if (u > 0) mbar_wait(s_empty + w, (u - 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tS + w * HALF, desc_kmajor(aQ, k), desc_kmajor(aK + st * T8K, k), idesc_s, k > 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tDP + w * HALF, desc_kmajor(aDO, k), desc_kmajor(aV + st * T8K, k), idesc_s, k > 0);
+        umma_commit(s_full + w);
+      };
+      issue_scores(0);
+      if (nkv > 1) issue_scores(1);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        mbar_wait(kv_full + s, (j >> 1) & 1);
-        if (j >= 1) mbar_wait(s_empty, (j - 1) & 1);
+        const int w = j & 1, u = j >> 1, st = j % BWD_STAGES;
+        mbar_wait(p_full + w, u & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k)   // S = Q K^T
-          umma_bf16(tS, desc_kmajor(aQ, k), desc_kmajor(aK + s * T8K, k), idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)   // dP = dO V^T
-          umma_bf16(tDP, desc_kmajor(aDO, k), desc_kmajor(aV + s * T8K, k), idesc_s, k > 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)   // dQ += dS K      (K = 64 keys)
-          umma_bf16(tDQ, desc_kmajor(aDS, k), desc_mnmajor(aK + s * T8K, k), idesc_g, (j > 0 || k > 0));
-        umma_commit(kv_empty + s);
+        for (int k = 0; k < 4; ++k)           // dQ += dS K      (K = 64 keys)
+          umma_bf16(tDQ, desc_kmajor(aDS + w * T16K, k), desc_mnmajor(aK + st * T8K, k), idesc_g, (j > 0 || k > 0));
+        umma_commit(kv_empty + st);
+        if (j + 2 < nkv) issue_scores(j + 2);
       }
       umma_commit(acc_full);
     }
   } else {
+    const int w = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -583,42 +643,51 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool row_ok = t < p.T;
     const float lse2 = row_ok ? p.lse[((size_t)b * p.H + h) * p.T + t] * LOG2E : 0.f;
     const float dsum = row_ok ? p.dvec[((size_t)b * p.H + h) * p.T + t] : 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, j & 1);
+    uint8_t *myDS = sDS + w * T16K;
+    int u = 0;
+    for (int j = w; j < nkv; j += 2, ++u) {
+      mbar_wait(s_full + w, u & 1);
       tc_fence_after();
       const bool tail = j * HALF + HALF > p.T;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         float sv[32], dp[32];
-        tmem_ld32(tS + lane_addr + c * 32, sv);
-        tmem_ld32(tDP + lane_addr + c * 32, dp);
+        tmem_ld32(tS + lane_addr + w * HALF + c * 32, sv);
+        tmem_ld32(tDP + lane_addr + w * HALF + c * 32, dp);
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
           const bool ok = row_ok && (!tail || j * HALF + c * 32 + q < p.T);
           const float pr = ok ? fast_exp2(fmaf(sv[q], p.scale_log2, -lse2)) : 0.f;
           dp[q] = pr * (dp[q] - dsum);
         }
-        store_row32(sDS, TILE, row, c * 32, dp);
+        store_row32(myDS, TILE, row, c * 32, dp);
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty);
-        mbar_arrive(p_full);
+        mbar_arrive(s_empty + w);
+        mbar_arrive(p_full + w);
       }
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    float acc[64];
+    // each warpgroup writes 32 of the 64 dQ columns
+    float v[32];
+    tmem_ld32(tDQ + lane_addr + w * 32, v);
+    if (row_ok) {
+      bf16 *dst = p.dqkv + ((size_t)b * p.T + t) * 3 * C + h * HD + w * 32;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32(tDQ + lane_addr + c * 32, v);
+      for (int c = 0; c < 4; ++c) {
+        uint32_t pk[4];
 #pragma unroll
-      for (int q = 0; q < 32; ++q) acc[c * 32 + q] = v[q];
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(v[8 * c + 2 * i] * p.scale, v[8 * c + 2 * i + 1] * p.scale);
+          pk[i] = *reinterpret_cast<uint32_t *>(&hh);
+        }
+        reinterpret_cast<uint4 *>(dst)[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
     }
-    if (row_ok) store_out64(p.dqkv + ((size_t)b * p.T + t) * 3 * C + h * HD, acc, p.scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -633,7 +702,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 static int set_smem(const void *fn, int bytes) {
   ASIS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  ASIS_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   return ASIS_OK;
 }
 
@@ -677,8 +745,8 @@ int attention_tc_backward(const void *qkv, const void *out, const float *lse, co
   if (int rc = make_tmap_3d(&tdo64, dout, C, T, B, C, (uint64_t)T * C, HD, HALF, 1)) return rc;
   static bool configured = false;
   if (!configured) {
-    if (int rc = set_smem((const void *)attn_bwd_dkdv_kernel, DKDV_SMEM)) return rc;
-    if (int rc = set_smem((const void *)attn_bwd_dq_kernel, DQ_SMEM)) return rc;
+    if (int rc = set_smem((const void *)attn_bwd_dkdv_kernel, BWD_SMEM)) return rc;
+    if (int rc = set_smem((const void *)attn_bwd_dq_kernel, BWD_SMEM)) return rc;
     configured = true;
   }
   float *dvec = (float *)ws;
@@ -696,9 +764,9 @@ int attention_tc_backward(const void *qkv, const void *out, const float *lse, co
   p.dvec = dvec;
   p.dqkv = (bf16 *)dqkv;
   dim3 grid((T + TILE - 1) / TILE, H, B);
-  attn_bwd_dkdv_kernel<<<grid, ATT_THREADS, DKDV_SMEM, st>>>(tq128, tq64, tdo64, p);
+  attn_bwd_dkdv_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(tq128, tq64, tdo64, p);
   ASIS_LAUNCHED();
-  attn_bwd_dq_kernel<<<grid, ATT_THREADS, DQ_SMEM, st>>>(tq128, tdo128, tq64, p);
+  attn_bwd_dq_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(tq128, tdo128, tq64, p);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }

@@ -102,6 +102,34 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return cdf + x * pdf;
 }
 
+// Fast GELU pair for the bf16 tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7,
+// far below bf16 rounding), one MUFU.RCP + one MUFU.EX2 instead of the ~40-instruction erff.
+// The exponential exp(-x^2/2) is shared between erf(x/sqrt2) and the Gaussian density.
+__device__ __forceinline__ void gelu_parts_fast(float x, float &cdf, float &pdf) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));   // exp(-x^2/2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfz = 1.0f - poly * t * e;            // erf(|x|/sqrt2)
+  cdf = 0.5f * (1.0f + copysignf(erfz, x));
+  pdf = 0.3989422804014327f * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float cdf, pdf;
+  gelu_parts_fast(x, cdf, pdf);
+  return x * cdf;
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  float cdf, pdf;
+  gelu_parts_fast(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
+}
+
 // dispatch on a runtime dtype to a compile-time type
 #define ASIS_DISPATCH_DTYPE(dt, T, ...)          \
   do {                                           \

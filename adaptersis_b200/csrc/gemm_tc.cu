@@ -112,7 +112,7 @@ __device__ __forceinline__ void epi_row32(const GemmTcParams &p, int row, int co
       case ASIS_EPI_GELU:
         if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = gelu_erf(v[i]);
+        for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
         break;
       case ASIS_EPI_SCALE_RESIDUAL: {
         if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
@@ -126,7 +126,7 @@ __device__ __forceinline__ void epi_row32(const GemmTcParams &p, int row, int co
         float h[8];
         load8(e.aux, e.aux_dtype, ai + 8 * g, h);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= dgelu_erf(h[i]);
+        for (int i = 0; i < 8; ++i) v[i] *= dgelu_fast(h[i]);
       } break;
       case ASIS_EPI_ACCUMULATE: {
         float c[8];
