@@ -221,32 +221,43 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       const bool tail = kv0 + TILE > p.T;            // only the last key block has invalid columns
       mbar_wait(s_full + w, u & 1);
       tc_fence_after();
-      // pass 1: row maximum of the raw scores (scale > 0, applied once to the maximum)
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(tS + lane_addr + w * TILE + c * 32, v);
+      // pass 1: row maximum of the raw scores (scale > 0, applied once to the maximum); TMEM loads
+      // two at a time, four independent max chains
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        float v0[32], v1[32];
+        tmem_ld32_issue(tS + lane_addr + w * TILE + c * 32, v0);
+        tmem_ld32_issue(tS + lane_addr + w * TILE + c * 32 + 32, v1);
+        tmem_ld_wait();
         if (tail) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (kv0 + c * 32 + i < p.T) ? v[i] : -INFINITY);
+          for (int i = 0; i < 32; ++i) {
+            mx4[i & 3] = fmaxf(mx4[i & 3], (kv0 + c * 32 + i < p.T) ? v0[i] : -INFINITY);
+            mx4[i & 3] = fmaxf(mx4[i & 3], (kv0 + c * 32 + 32 + i < p.T) ? v1[i] : -INFINITY);
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, v[i]);
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(v0[i], v1[i]));
         }
       }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float alpha = fast_exp2(m_run - m_new);
       // fold in this warpgroup's previous P V (its completion also frees the P buffer), rescale
       if (u > 0) {
         mbar_wait(o_full + w, (u - 1) & 1);
         tc_fence_after();
+        {
+          float v0[32], v1[32];
+          tmem_ld32_issue(tO + lane_addr + w * HD, v0);
+          tmem_ld32_issue(tO + lane_addr + w * HD + 32, v1);
+          tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float v[32];
-          tmem_ld32(tO + lane_addr + w * HD + c * 32, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c * 32 + i] += v[i];
+          for (int i = 0; i < 32; ++i) {
+            o[i] += v0[i];
+            o[32 + i] += v1[i];
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -256,24 +267,33 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           for (int i = 0; i < 64; ++i) o[i] *= alpha;
         }
       }
-      // pass 2: probabilities -> smem (bf16), row sum
-      float l_add = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float v[32];
-        tmem_ld32(tS + lane_addr + w * TILE + c * 32, v);
+      // pass 2: probabilities -> smem (bf16), row sum (four independent chains)
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; c += 2) {
+        float v0[32], v1[32];
+        tmem_ld32_issue(tS + lane_addr + w * TILE + c * 32, v0);
+        tmem_ld32_issue(tS + lane_addr + w * TILE + c * 32 + 32, v1);
+        tmem_ld_wait();
         if (tail) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            v[i] = (kv0 + c * 32 + i < p.T) ? fast_exp2(fmaf(v[i], p.scale_log2, -m_new)) : 0.f;
+          for (int i = 0; i < 32; ++i) {
+            v0[i] = (kv0 + c * 32 + i < p.T) ? fast_exp2(fmaf(v0[i], p.scale_log2, -m_new)) : 0.f;
+            v1[i] = (kv0 + c * 32 + 32 + i < p.T) ? fast_exp2(fmaf(v1[i], p.scale_log2, -m_new)) : 0.f;
+          }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fast_exp2(fmaf(v[i], p.scale_log2, -m_new));
+          for (int i = 0; i < 32; ++i) {
+            v0[i] = fast_exp2(fmaf(v0[i], p.scale_log2, -m_new));
+            v1[i] = fast_exp2(fmaf(v1[i], p.scale_log2, -m_new));
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 32; ++i) l_add += v[i];
-        store_row32(myP, TILE, row, c * 32, v);
+        for (int i = 0; i < 32; ++i) l4[i & 3] += v0[i] + v1[i];
+        store_row32(myP, TILE, row, c * 32, v0);
+        store_row32(myP, TILE, row, c * 32 + 32, v1);
       }
+      const float l_add = (l4[0] + l4[1]) + (l4[2] + l4[3]);
       tc_fence_before();
       fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core
       __syncwarp();
@@ -477,7 +497,6 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
     const int row = quarter * 32 + lane;     // key row inside the tile
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int tid = (threadIdx.x - 64) & 127;
-    const bool key_ok = k0 + row < p.T;
     const float *lse_b = p.lse + ((size_t)b * p.H + h) * p.T;
     const float *d_b = p.dvec + ((size_t)b * p.H + h) * p.T;
     float *myLse = sLse + w * HALF, *myD = sD + w * HALF;
@@ -493,19 +512,27 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
       named_bar_sync(1 + w, 128);
       mbar_wait(s_full + w, u & 1);
       tc_fence_after();
-      const bool tail = i * HALF + HALF > p.T;
+      // No masking is needed here: query columns >= T have zero Q / dO rows (TMA zero fill) and
+      // lse = D = 0, so their P^T multiplies zero dO rows and their dS^T is exactly 0; key rows >= T
+      // only pollute their own (never stored) dV / dK rows.
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         float st[32], dp[32];
-        tmem_ld32(tST + lane_addr + w * HALF + c * 32, st);
-        tmem_ld32(tDPT + lane_addr + w * HALF + c * 32, dp);
+        tmem_ld32_issue(tST + lane_addr + w * HALF + c * 32, st);
+        tmem_ld32_issue(tDPT + lane_addr + w * HALF + c * 32, dp);
+        tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const int col = c * 32 + q;
-          const bool ok = key_ok && (!tail || i * HALF + col < p.T);
-          const float pr = ok ? fast_exp2(fmaf(st[q], p.scale_log2, -myLse[col])) : 0.f;
-          st[q] = pr;
-          dp[q] = pr * (dp[q] - myD[col]);
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 L = reinterpret_cast<const float4 *>(myLse)[c * 8 + q4];
+          const float4 Dv = reinterpret_cast<const float4 *>(myD)[c * 8 + q4];
+          const float ls[4] = {L.x, L.y, L.z, L.w}, ds[4] = {Dv.x, Dv.y, Dv.z, Dv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int q = q4 * 4 + k;
+            const float pr = fast_exp2(fmaf(st[q], p.scale_log2, -ls[k]));
+            st[q] = pr;
+            dp[q] = pr * (dp[q] - ds[k]);
+          }
         }
         store_row32(myPT, TILE, row, c * 32, st);
         store_row32(myDST, TILE, row, c * 32, dp);
@@ -648,18 +675,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     for (int j = w; j < nkv; j += 2, ++u) {
       mbar_wait(s_full + w, u & 1);
       tc_fence_after();
-      const bool tail = j * HALF + HALF > p.T;
+      // No masking: key columns >= T multiply zero K rows in dQ += dS K; query rows >= T only
+      // pollute their own (never stored) dQ rows.
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         float sv[32], dp[32];
-        tmem_ld32(tS + lane_addr + w * HALF + c * 32, sv);
-        tmem_ld32(tDP + lane_addr + w * HALF + c * 32, dp);
+        tmem_ld32_issue(tS + lane_addr + w * HALF + c * 32, sv);
+        tmem_ld32_issue(tDP + lane_addr + w * HALF + c * 32, dp);
+        tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const bool ok = row_ok && (!tail || j * HALF + c * 32 + q < p.T);
-          const float pr = ok ? fast_exp2(fmaf(sv[q], p.scale_log2, -lse2)) : 0.f;
-          dp[q] = pr * (dp[q] - dsum);
-        }
+        for (int q = 0; q < 32; ++q) dp[q] = fast_exp2(fmaf(sv[q], p.scale_log2, -lse2)) * (dp[q] - dsum);
         store_row32(myDS, TILE, row, c * 32, dp);
       }
       tc_fence_before();

@@ -76,68 +76,80 @@ __device__ __forceinline__ void store8(void *base, int dtype, size_t idx, const 
   }
 }
 
-// epilogue for 32 consecutive columns of one row
+// epilogue for 32 consecutive columns of one row; KIND is a compile-time constant so that the
+// accumulator array is only ever indexed with constants (it must stay in registers)
+template <int KIND>
 __device__ __forceinline__ void epi_row32(const GemmTcParams &p, int row, int col0, const float (&acc)[32], bool vec_ok) {
   const EpiArgs &e = p.epi;
   if (row >= p.M || col0 >= p.N) return;
   if (!vec_ok || col0 + 32 > p.N) {
-    for (int j = 0; j < 32 && col0 + j < p.N; ++j) {
-      if (p.atomic_out)
-        atomicAdd(reinterpret_cast<float *>(e.C) + (size_t)row * e.ldc + col0 + j, acc[j]);
-      else
-        epi_scalar(e, row, col0 + j, acc[j]);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (col0 + j < p.N) {
+        if (p.atomic_out)
+          atomicAdd(reinterpret_cast<float *>(e.C) + (size_t)row * e.ldc + col0 + j, acc[j]);
+        else
+          epi_scalar(e, row, col0 + j, acc[j]);
+      }
     }
     return;
   }
   const size_t ci = (size_t)row * e.ldc + col0;
   const size_t ai = (size_t)row * e.ldaux + col0;
+  if (p.atomic_out) {
+    float *c = reinterpret_cast<float *>(e.C) + ci;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) atomicAdd(c + i, acc[i]);
+    return;
+  }
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = acc[8 * g + i];
-    if (p.atomic_out) {
-      float *c = reinterpret_cast<float *>(e.C) + ci + 8 * g;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(c + i, v[i]);
-      continue;
-    }
-    if (e.bias && e.kind != ASIS_EPI_DGELU && e.kind != ASIS_EPI_ACCUMULATE) {
+    if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE && e.bias) {
       float b[8];
       load8f(e.bias + col0 + 8 * g, b);
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] += b[i];
     }
-    switch (e.kind) {
-      case ASIS_EPI_GELU:
-        if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
+    if (KIND == ASIS_EPI_GELU) {
+      if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
-        break;
-      case ASIS_EPI_SCALE_RESIDUAL: {
-        if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
-        float r[8], gm[8];
-        load8f(e.residual + ci + 8 * g, r);
-        load8f(e.gamma + col0 + 8 * g, gm);
+      for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
+    } else if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
+      if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
+      float r[8], gm[8];
+      load8f(e.residual + ci + 8 * g, r);
+      load8f(e.gamma + col0 + 8 * g, gm);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = r[i] + gm[i] * v[i];
-      } break;
-      case ASIS_EPI_DGELU: {
-        float h[8];
-        load8(e.aux, e.aux_dtype, ai + 8 * g, h);
+      for (int i = 0; i < 8; ++i) v[i] = r[i] + gm[i] * v[i];
+    } else if (KIND == ASIS_EPI_DGELU) {
+      float h[8];
+      load8(e.aux, e.aux_dtype, ai + 8 * g, h);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] *= dgelu_fast(h[i]);
-      } break;
-      case ASIS_EPI_ACCUMULATE: {
-        float c[8];
-        load8f(reinterpret_cast<const float *>(e.C) + ci + 8 * g, c);
+      for (int i = 0; i < 8; ++i) v[i] *= dgelu_fast(h[i]);
+    } else if (KIND == ASIS_EPI_ACCUMULATE) {
+      float c[8];
+      load8f(reinterpret_cast<const float *>(e.C) + ci + 8 * g, c);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] += c[i];
-      } break;
-      default:
-        break;
+      for (int i = 0; i < 8; ++i) v[i] += c[i];
     }
     store8(e.C, e.c_dtype, ci + 8 * g, v);
+  }
+}
+
+// the epilogue of one 32-row x 128-column slab: TMEM loads issued two at a time
+template <int KIND>
+__device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, int row, int col_base, bool vec_ok) {
+#pragma unroll
+  for (int c = 0; c < 4; c += 2) {
+    float v0[32], v1[32];
+    tmem_ld32_issue(taddr + c * 32, v0);
+    tmem_ld32_issue(taddr + c * 32 + 32, v1);
+    tmem_ld_wait();
+    epi_row32<KIND>(p, row, col_base + c * 32, v0, vec_ok);
+    epi_row32<KIND>(p, row, col_base + c * 32 + 32, v1, vec_ok);
   }
 }
 
@@ -283,12 +295,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const int row = m_blk * BM + quarter * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int col_in_tile = half * 128 + c * 32;
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + col_in_tile, v);
-        epi_row32(p, row, n_blk * BN + col_in_tile, v, vec_ok);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+      const int col_base = n_blk * BN + half * 128;
+      switch (p.epi.kind) {
+        case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, row, col_base, vec_ok); break;
+        case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, row, col_base, vec_ok); break;
+        case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, row, col_base, vec_ok); break;
+        case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, row, col_base, vec_ok); break;
+        default: epi_slab<ASIS_EPI_NONE>(p, taddr, row, col_base, vec_ok); break;
       }
       tc_fence_before();
       __syncwarp();
