@@ -30,7 +30,7 @@ constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = BN * BK * 2;           // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int BOX_BYTES = 64 * BK * 2;         // one 64 x 64 MN-major TMA box: 8 KB
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 8;   // (16 epilogue warps measured slower: 96-register cap, spills)
 constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
 constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 

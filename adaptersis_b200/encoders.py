@@ -30,7 +30,11 @@ class FeatureEncoder(nn.Module):
 
     def forward(self, x, need_c1=True):
         # fp32 parity mode: keep the library convolutions out of TF32
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=get_precision() != "fp32"):
+        lowp = get_precision() == "bf16" and x.is_cuda
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=get_precision() != "fp32"), \
+                torch.autocast("cuda", dtype=torch.bfloat16, enabled=lowp):
+            if lowp:
+                x = x.contiguous(memory_format=torch.channels_last)
             return self._forward(x, need_c1)
 
     def _forward(self, x, need_c1):

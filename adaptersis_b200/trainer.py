@@ -39,6 +39,9 @@ class TrainStep(nn.Module):
         self.seg_decoder = FeatureDecoder(embed_dim=C, num_classes=num_classes, features=feats)
         self.num_classes = num_classes
         self.to(device)
+        if precision == "bf16":
+            self.seg_decoder.to(memory_format=torch.channels_last)
+            self.encoder.backbone_encoder.to(memory_format=torch.channels_last)
         self.encoder.model.eval()
         if not train_backbone:
             for p in self.encoder.model.parameters():
@@ -52,7 +55,13 @@ class TrainStep(nn.Module):
     def forward_loss(self, inp, target):
         with Fn.precision(self.precision):
             feat = self.encoder(inp)["feat"]
-            out = self.seg_decoder(feat.float())
+            # the decoder is still library code: in bf16 mode let cuDNN run it in
+            # bf16 / channels-last, like the rest of the step
+            lowp = self.precision == "bf16"
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=lowp):
+                x = feat.contiguous(memory_format=torch.channels_last) if lowp else feat.float()
+                out = self.seg_decoder(x)
+            out = out.float()
             H, W = target.shape[1], target.shape[2]
             out = F.interpolate(out, size=(H, W), mode="bilinear")
             out = torch.softmax(out, 1)
