@@ -8,12 +8,18 @@
 // coalesced 4*D-byte segment, and grids laid out (queries fastest, then head, then image) so the
 // value slice of one (image, head) stays L2/L1 resident while it is being gathered.
 //
+// Every kernel first builds a per-block table of sampling points in shared memory (4 corner
+// offsets + 4 weights per point, computed ONCE per (query, head, level, point) instead of once per
+// lane): the first version recomputed the footprint in all D/4 lanes and was issue-bound at 1550
+// warp instructions per (query, head) for 48 corner loads (profiles/r1a_msda_ncu_full.md).
+//
 // Backward, grad_value: contributions (query, level, point, corner) -> value pixel are a many-to-one
-// scatter.  Instead of floating-point atomics: (1) count contributions per (image, head, pixel)
-// [integer counters], (2) exclusive scan per (image, head), (3) fill (weight, id) entries into the
-// pixel's bucket, (4) one thread group per (image, pixel, head) orders its bucket by contribution
-// id (rank sort in registers) and reduces it -> every grad_value element is written exactly once,
-// in a fixed summation order: run-to-run deterministic, no float atomics.
+// scatter.  Instead of floating-point atomics: (1) count contributions per (image, head, pixel,
+// query chunk) [integer counters], (2) exclusive scan per (image, head), (3) fill (id, weight)
+// entries into the bucket, (4) one thread group per (image, pixel, head) walks its buckets in chunk
+// order, orders each by contribution id (rank sort in registers) and reduces it -> every grad_value
+// element is written exactly once, in a fixed summation order: run-to-run deterministic, no float
+// atomics.  Query chunks keep buckets short (about 16 entries) whatever Lq / S is.
 #include "common.cuh"
 
 namespace asis {
@@ -59,60 +65,75 @@ __device__ __forceinline__ Footprint footprint(float lx, float ly, int H, int W)
 
 // ---------------------------------------------------------------------------------------------
 // forward: one group of GP lanes per (n, q, m); lane g owns channels [4g, 4g+4)
-// grid = (ceil(Lq / groups_per_block), M, N)
+// grid = (ceil(Lq / items_per_block), M, N); dynamic smem = items_per_block * L*P * 32 bytes
 // ---------------------------------------------------------------------------------------------
-template <typename VT>
-__device__ __forceinline__ void fwd_point(const VT *__restrict__ vb, size_t MD, int H, int W, float2 xy, float a,
-                                          float (&acc)[4]) {
-  // branch-free: out-of-range corners read a clamped (valid) address with weight 0, so the four
-  // 16-byte loads of every point are unconditional and can all be in flight together
+struct __align__(16) PointFwd {
+  int off[4];     // element offsets (pixel * M*D) of the 4 corners inside the image's value tensor, clamped
+  float w[4];     // bilinear weight * attention weight, 0 for corners outside the map
+};
+
+__device__ __forceinline__ void make_point(PointFwd &pt, const LevelInfo &lv, int l, float2 xy, float a, int MD) {
+  const int H = lv.H[l], W = lv.W[l];
   const Footprint f = footprint(xy.x, xy.y, H, W);
   const bool xl = f.any && f.x0 >= 0, xr = f.any && f.x0 + 1 < W, yt = f.y0 >= 0, yb = f.y0 + 1 < H;
   const int xa = max(f.x0, 0), xb = min(f.x0 + 1, W - 1), ya = max(f.y0, 0), yc = min(f.y0 + 1, H - 1);
-  float v00[4], v01[4], v10[4], v11[4];
-  load4(vb + ((size_t)ya * W + xa) * MD, v00);
-  load4(vb + ((size_t)ya * W + xb) * MD, v01);
-  load4(vb + ((size_t)yc * W + xa) * MD, v10);
-  load4(vb + ((size_t)yc * W + xb) * MD, v11);
+  const int base = lv.start[l];
+  pt.off[0] = (base + ya * W + xa) * MD;
+  pt.off[1] = (base + ya * W + xb) * MD;
+  pt.off[2] = (base + yc * W + xa) * MD;
+  pt.off[3] = (base + yc * W + xb) * MD;
   const float ofx = 1.f - f.fx, ofy = 1.f - f.fy;
-  const float w00 = (yt && xl) ? ofx * ofy * a : 0.f, w01 = (yt && xr) ? f.fx * ofy * a : 0.f;
-  const float w10 = (yb && xl) ? ofx * f.fy * a : 0.f, w11 = (yb && xr) ? f.fx * f.fy * a : 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) acc[i] += w00 * v00[i] + w01 * v01[i] + w10 * v10[i] + w11 * v11[i];
+  pt.w[0] = (yt && xl) ? ofx * ofy * a : 0.f;
+  pt.w[1] = (yt && xr) ? f.fx * ofy * a : 0.f;
+  pt.w[2] = (yb && xl) ? ofx * f.fy * a : 0.f;
+  pt.w[3] = (yb && xr) ? f.fx * f.fy * a : 0.f;
 }
 
-template <typename VT, typename OT, int GP, int PT>
+template <typename VT, typename OT, int GP>
 __global__ void __launch_bounds__(256) msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ ss,
                                                        const int64_t *__restrict__ lsi,
                                                        const float *__restrict__ loc, const float *__restrict__ aw,
                                                        OT *__restrict__ out, int S, int M, int D, int Lq, int L,
-                                                       int Prt) {
+                                                       int P) {
+  extern __shared__ __align__(16) uint8_t msda_smem[];
+  PointFwd *tab = reinterpret_cast<PointFwd *>(msda_smem);
   __shared__ LevelInfo lv;
   load_levels(lv, ss, lsi, L);
-  const int P = PT > 0 ? PT : Prt;
-  const int G = D >> 2;
-  const int g = threadIdx.x % GP;
-  const int q = blockIdx.x * (blockDim.x / GP) + threadIdx.x / GP;
+  const int LP = L * P;
+  const int ipb = blockDim.x / GP;                 // (query, head) items per block
+  const int q_first = blockIdx.x * ipb;
   const int m = blockIdx.y, n = blockIdx.z;
-  if (q >= Lq || g >= G) return;
-
-  const size_t item = ((size_t)n * Lq + q) * M + m;
-  const float2 *locp = reinterpret_cast<const float2 *>(loc) + item * (size_t)(L * P);
-  const float *awp = aw + item * (size_t)(L * P);
-  const size_t MD = (size_t)M * D;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-
-  for (int l = 0; l < L; ++l) {
-    const int H = lv.H[l], W = lv.W[l];
-    const VT *vb = value + ((size_t)n * S + lv.start[l]) * MD + (size_t)m * D + 4 * g;
-    if (PT > 0) {
-#pragma unroll
-      for (int p = 0; p < PT; ++p) fwd_point(vb, MD, H, W, __ldg(locp + l * PT + p), __ldg(awp + l * PT + p), acc);
-    } else {
-      for (int p = 0; p < P; ++p) fwd_point(vb, MD, H, W, __ldg(locp + l * P + p), __ldg(awp + l * P + p), acc);
-    }
+  const int MD = M * D;
+  // phase 1: the block's sampling points, one thread per point
+  for (int t = threadIdx.x; t < ipb * LP; t += blockDim.x) {
+    const int it = t / LP, lp = t - it * LP;
+    const int q = min(q_first + it, Lq - 1);
+    const size_t item = ((size_t)n * Lq + q) * M + m;
+    make_point(tab[t], lv, lp / P, __ldg(reinterpret_cast<const float2 *>(loc) + item * LP + lp),
+               __ldg(aw + item * LP + lp), MD);
   }
-  store4(out + item * (size_t)D + 4 * g, acc);
+  __syncthreads();
+  // phase 2: gather
+  const int G = D >> 2;
+  const int g = threadIdx.x % GP, it = threadIdx.x / GP;
+  const int q = q_first + it;
+  if (q >= Lq || g >= G) return;
+  const VT *vb = value + (size_t)n * S * MD + (size_t)m * D + 4 * g;
+  const PointFwd *mine = tab + it * LP;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+  for (int lp = 0; lp < LP; ++lp) {
+    const int4 o = *reinterpret_cast<const int4 *>(mine[lp].off);
+    const float4 w = *reinterpret_cast<const float4 *>(mine[lp].w);
+    float v00[4], v01[4], v10[4], v11[4];
+    load4(vb + o.x, v00);
+    load4(vb + o.y, v01);
+    load4(vb + o.z, v10);
+    load4(vb + o.w, v11);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += w.x * v00[i] + w.y * v01[i] + w.z * v10[i] + w.w * v11[i];
+  }
+  store4(out + (((size_t)n * Lq + q) * M + m) * (size_t)D + 4 * g, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -125,7 +146,19 @@ __device__ __forceinline__ float group_sum(float v) {
   for (int o = GP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, GP);
   return v;
 }
+template <>
+__device__ __forceinline__ float group_sum<1>(float v) { return v; }
 
+struct __align__(16) PointBwd {
+  int off[4];      // clamped corner offsets (as PointFwd)
+  float mask[4];   // 1 for corners inside the map, else 0
+  float fx, fy, a, pad;
+};
+
+// One group of GP lanes per (n, q, m); lane g owns the float4 channel vectors {g + GP*k, k < 4}
+// (16 channels per lane when D = 128: 8 lanes per item, so the three per-point reductions over D
+// cost 3 shuffle steps instead of 5 and a warp works on 4 items at once).
+// Also counts the contributions per (pixel, query chunk) for the grad_value buckets.
 template <typename VT, typename GT, int GP>
 __global__ void __launch_bounds__(256) msda_bwd_locaw_kernel(const VT *__restrict__ value, const int64_t *__restrict__ ss,
                                                              const int64_t *__restrict__ lsi,
@@ -133,71 +166,99 @@ __global__ void __launch_bounds__(256) msda_bwd_locaw_kernel(const VT *__restric
                                                              const float *__restrict__ aw,
                                                              const GT *__restrict__ gout, float *__restrict__ gloc,
                                                              float *__restrict__ gaw, int *__restrict__ counts,
-                                                             int S, int M, int D, int Lq, int L, int P) {
+                                                             int S, int M, int D, int Lq, int L, int P, int KC,
+                                                             int qchunk) {
+  extern __shared__ __align__(16) uint8_t msda_smem[];
+  PointBwd *tab = reinterpret_cast<PointBwd *>(msda_smem);
   __shared__ LevelInfo lv;
   load_levels(lv, ss, lsi, L);
-  const int G = D >> 2;
-  const int g = threadIdx.x % GP;
-  int q = blockIdx.x * (blockDim.x / GP) + threadIdx.x / GP;
+  const int LP = L * P;
+  const int ipb = blockDim.x / GP;
+  const int q_first = blockIdx.x * ipb;
   const int m = blockIdx.y, n = blockIdx.z;
-  // whole groups past the end still take part in the shuffles below (a warp may hold several
-  // groups); they work on a clamped query and skip every store
+  const int MD = M * D;
+  int *cnt = counts + ((size_t)n * M + m) * S * KC;
+  for (int t = threadIdx.x; t < ipb * LP; t += blockDim.x) {
+    const int it = t / LP, lp = t - it * LP;
+    const int q = q_first + it;
+    const int qc = min(q, Lq - 1);
+    const size_t item = ((size_t)n * Lq + qc) * M + m;
+    const int l = lp / P;
+    const int H = lv.H[l], W = lv.W[l];
+    const float2 xy = __ldg(reinterpret_cast<const float2 *>(loc) + item * LP + lp);
+    const Footprint f = footprint(xy.x, xy.y, H, W);
+    const bool xl = f.any && f.x0 >= 0, xr = f.any && f.x0 + 1 < W, yt = f.y0 >= 0, yb = f.y0 + 1 < H;
+    const int xa = max(f.x0, 0), xb = min(f.x0 + 1, W - 1), ya = max(f.y0, 0), yc = min(f.y0 + 1, H - 1);
+    const int base = lv.start[l];
+    PointBwd &pt = tab[t];
+    const int p00 = base + ya * W + xa, p01 = base + ya * W + xb, p10 = base + yc * W + xa, p11 = base + yc * W + xb;
+    pt.off[0] = p00 * MD; pt.off[1] = p01 * MD; pt.off[2] = p10 * MD; pt.off[3] = p11 * MD;
+    pt.mask[0] = (yt && xl) ? 1.f : 0.f;
+    pt.mask[1] = (yt && xr) ? 1.f : 0.f;
+    pt.mask[2] = (yb && xl) ? 1.f : 0.f;
+    pt.mask[3] = (yb && xr) ? 1.f : 0.f;
+    pt.fx = f.fx; pt.fy = f.fy; pt.a = __ldg(aw + item * LP + lp); pt.pad = 0.f;
+    if (q < Lq) {
+      const int ch = q / qchunk;
+      if (yt && xl) atomicAdd(cnt + (size_t)p00 * KC + ch, 1);
+      if (yt && xr) atomicAdd(cnt + (size_t)p01 * KC + ch, 1);
+      if (yb && xl) atomicAdd(cnt + (size_t)p10 * KC + ch, 1);
+      if (yb && xr) atomicAdd(cnt + (size_t)p11 * KC + ch, 1);
+    }
+  }
+  __syncthreads();
+
+  const int NV = D >> 2;                      // float4 vectors per (pixel, head)
+  const int g = threadIdx.x % GP, it = threadIdx.x / GP;
+  int q = q_first + it;
   const bool live = q < Lq;
   if (!live) q = Lq - 1;
-  const bool lane_on = g < G;
-
   const size_t item = ((size_t)n * Lq + q) * M + m;
-  const float *locp = loc + item * (size_t)(L * P * 2);
-  const float *awp = aw + item * (size_t)(L * P);
-  const size_t MD = (size_t)M * D;
-  float go[4] = {0, 0, 0, 0};
-  if (lane_on) load4(gout + item * (size_t)D + 4 * g, go);
-  int *cnt = counts + ((size_t)n * M + m) * S;
-
-  for (int l = 0; l < L; ++l) {
-    const int H = lv.H[l], W = lv.W[l];
-    const VT *vb = value + ((size_t)n * S + lv.start[l]) * MD + (size_t)m * D + 4 * g;
-    for (int p = 0; p < P; ++p) {
-      const float2 xy = __ldg(reinterpret_cast<const float2 *>(locp) + l * P + p);
-      const float a = __ldg(awp + l * P + p);
-      const Footprint f = footprint(xy.x, xy.y, H, W);
-      float d_a = 0.f, d_x = 0.f, d_y = 0.f;
-      if (f.any) {  // uniform across the group
-        const bool xl = f.x0 >= 0, xr = f.x0 + 1 < W, yt = f.y0 >= 0, yb = f.y0 + 1 < H;
-        float v00[4] = {0, 0, 0, 0}, v01[4] = {0, 0, 0, 0}, v10[4] = {0, 0, 0, 0}, v11[4] = {0, 0, 0, 0};
-        const VT *r0 = vb + ((size_t)f.y0 * W + f.x0) * MD;
-        if (lane_on) {
-          if (yt && xl) load4(r0, v00);
-          if (yt && xr) load4(r0 + MD, v01);
-          if (yb && xl) load4(r0 + (size_t)W * MD, v10);
-          if (yb && xr) load4(r0 + (size_t)W * MD + MD, v11);
-        }
-        const float ofx = 1.f - f.fx, ofy = 1.f - f.fy;
+  const VT *vb = value + (size_t)n * S * MD + (size_t)m * D;
+  float go[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int v = g + GP * k;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) go[k][i] = 0.f;
+    if (v < NV) load4(gout + item * (size_t)D + 4 * v, go[k]);
+  }
+  const PointBwd *mine = tab + it * LP;
+  for (int lp = 0; lp < LP; ++lp) {
+    const int4 o = *reinterpret_cast<const int4 *>(mine[lp].off);
+    const float4 mk = *reinterpret_cast<const float4 *>(mine[lp].mask);
+    const float4 fr = *reinterpret_cast<const float4 *>(&mine[lp].fx);
+    const float ofx = 1.f - fr.x, ofy = 1.f - fr.y;
+    float d_a = 0.f, d_x = 0.f, d_y = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int v = g + GP * k;
+      if (v < NV) {
+        float v00[4], v01[4], v10[4], v11[4];
+        load4(vb + o.x + 4 * v, v00);
+        load4(vb + o.y + 4 * v, v01);
+        load4(vb + o.z + 4 * v, v10);
+        load4(vb + o.w + 4 * v, v11);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float top = ofx * v00[i] + f.fx * v01[i];
-          const float bot = ofx * v10[i] + f.fx * v11[i];
-          d_a += go[i] * (ofy * top + f.fy * bot);
-          d_x += go[i] * (ofy * (v01[i] - v00[i]) + f.fy * (v11[i] - v10[i]));
-          d_y += go[i] * (bot - top);
-        }
-        if (g == 0 && live) {
-          const int base = lv.start[l] + f.y0 * W + f.x0;
-          if (yt && xl) atomicAdd(cnt + base, 1);
-          if (yt && xr) atomicAdd(cnt + base + 1, 1);
-          if (yb && xl) atomicAdd(cnt + base + W, 1);
-          if (yb && xr) atomicAdd(cnt + base + W + 1, 1);
+          const float a00 = v00[i] * mk.x, a01 = v01[i] * mk.y, a10 = v10[i] * mk.z, a11 = v11[i] * mk.w;
+          const float top = ofx * a00 + fr.x * a01;
+          const float bot = ofx * a10 + fr.x * a11;
+          d_a += go[k][i] * (ofy * top + fr.y * bot);
+          d_x += go[k][i] * (ofy * (a01 - a00) + fr.y * (a11 - a10));
+          d_y += go[k][i] * (bot - top);
         }
       }
-      d_a = group_sum<GP>(d_a);
-      d_x = group_sum<GP>(d_x);
-      d_y = group_sum<GP>(d_y);
-      if (g == 0 && live) {
-        const size_t o = item * (size_t)(L * P) + l * P + p;
-        gaw[o] = d_a;
-        // d pixel / d loc = size (x_pix = loc * W - 0.5)
-        reinterpret_cast<float2 *>(gloc)[o] = make_float2(a * d_x * (float)W, a * d_y * (float)H);
-      }
+    }
+    d_a = group_sum<GP>(d_a);
+    d_x = group_sum<GP>(d_x);
+    d_y = group_sum<GP>(d_y);
+    if (g == 0 && live) {
+      const int l = lp / P;
+      const size_t oidx = item * (size_t)LP + lp;
+      gaw[oidx] = d_a;
+      // d pixel / d loc = size (x_pix = loc * W - 0.5)
+      reinterpret_cast<float2 *>(gloc)[oidx] = make_float2(fr.z * d_x * (float)lv.W[l], fr.z * d_y * (float)lv.H[l]);
     }
   }
 }
@@ -205,7 +266,7 @@ __global__ void __launch_bounds__(256) msda_bwd_locaw_kernel(const VT *__restric
 // exclusive scan of the S counters of one (n, m); bucket storage of (n, m) starts at
 // (n*M+m) * cap where cap = Lq*L*P*4 (the most contributions one (n, m) can have).
 __global__ void __launch_bounds__(1024) msda_bwd_scan_kernel(const int *counts, int *__restrict__ rowptr,
-                                                             int *cursor, int S, int cap) {
+                                                             int *cursor, int S /* = pixels * query chunks */, int cap) {
   __shared__ int warp_tot[32];
   __shared__ int chunk_tot;
   __shared__ int carry_s;
@@ -251,12 +312,14 @@ __global__ void __launch_bounds__(1024) msda_bwd_scan_kernel(const int *counts, 
 }
 
 // fill: one thread per (n, q, m, l, p); entry = (contribution id within (n, m), weight).
-// id = ((q*L + l)*P + p)*4 + corner: unique per (n, m), so ordering a bucket by id is total.
+// id = (q << idshift) + (l*P + p)*4 + corner with 2^idshift >= L*P*4: unique per (n, m), increasing
+// in q, and the query index comes back with one shift.  Bucket = (pixel, query chunk).
 __global__ void __launch_bounds__(256) msda_bwd_fill_kernel(const int64_t *__restrict__ ss, const int64_t *__restrict__ lsi,
                                                             const float *__restrict__ loc,
                                                             const float *__restrict__ aw, int *__restrict__ cursor,
                                                             int2 *__restrict__ entries, int S, int M, int Lq,
-                                                            int L, int P, size_t total) {
+                                                            int L, int P, int KC, int qchunk, int idshift,
+                                                            size_t total) {
   __shared__ LevelInfo lv;
   load_levels(lv, ss, lsi, L);
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -276,25 +339,26 @@ __global__ void __launch_bounds__(256) msda_bwd_fill_kernel(const int64_t *__res
   const Footprint f = footprint(xy.x, xy.y, H, W);
   if (!f.any) return;
   const bool xl = f.x0 >= 0, xr = f.x0 + 1 < W, yt = f.y0 >= 0, yb = f.y0 + 1 < H;
-  int *cu = cursor + ((size_t)n * M + m) * S;
+  int *cu = cursor + ((size_t)n * M + m) * S * KC + q / qchunk;
   const int base = lv.start[l] + f.y0 * W + f.x0;
-  const int id = ((q * L + l) * P + p) * 4;
+  const int id = (q << idshift) + (l * P + p) * 4;
   const float ofx = 1.f - f.fx, ofy = 1.f - f.fy;
-  if (yt && xl) entries[atomicAdd(cu + base, 1)] = make_int2(id + 0, __float_as_int(ofx * ofy * a));
-  if (yt && xr) entries[atomicAdd(cu + base + 1, 1)] = make_int2(id + 1, __float_as_int(f.fx * ofy * a));
-  if (yb && xl) entries[atomicAdd(cu + base + W, 1)] = make_int2(id + 2, __float_as_int(ofx * f.fy * a));
-  if (yb && xr) entries[atomicAdd(cu + base + W + 1, 1)] = make_int2(id + 3, __float_as_int(f.fx * f.fy * a));
+  if (yt && xl) entries[atomicAdd(cu + (size_t)base * KC, 1)] = make_int2(id + 0, __float_as_int(ofx * ofy * a));
+  if (yt && xr) entries[atomicAdd(cu + (size_t)(base + 1) * KC, 1)] = make_int2(id + 1, __float_as_int(f.fx * ofy * a));
+  if (yb && xl) entries[atomicAdd(cu + (size_t)(base + W) * KC, 1)] = make_int2(id + 2, __float_as_int(ofx * f.fy * a));
+  if (yb && xr) entries[atomicAdd(cu + (size_t)(base + W + 1) * KC, 1)] = make_int2(id + 3, __float_as_int(f.fx * f.fy * a));
 }
 
-// gather: one group of GP lanes per (n, s, m).  The bucket [rowptr, cursor) is brought into
-// registers (kSlots entries per lane), every entry is ranked by id with one shuffle per entry,
-// written to its rank position in a per-group shared-memory strip, then consumed in rank order.
+// gather: one group of GP lanes per (n, s, m).  The pixel's KC buckets are walked in chunk order;
+// each bucket [rowptr, cursor) is brought into registers (kSlots entries per lane), every entry is
+// ranked by id with one shuffle per entry, written to its rank position in a per-group
+// shared-memory strip, then consumed in rank order.
 template <typename GT, int GP>
 __global__ void __launch_bounds__(256) msda_bwd_gather_kernel(const GT *__restrict__ gout, const int *__restrict__ rowptr,
                                                               const int *__restrict__ cursor,
                                                               const int2 *__restrict__ entries,
                                                               GT *__restrict__ gvalue, int S, int M, int D, int Lq,
-                                                              int LP4) {
+                                                              int KC, int idshift) {
   constexpr int kSlots = 4;
   __shared__ int2 strip[256 * kSlots];
   const int G = D >> 2;
@@ -304,87 +368,91 @@ __global__ void __launch_bounds__(256) msda_bwd_gather_kernel(const GT *__restri
   const bool live = s < S;
   if (!live) s = S - 1;
   const bool lane_on = g < G;
-  const size_t seg = ((size_t)n * M + m) * S + s;
-  const int beg = rowptr[seg];
-  const int len = live ? cursor[seg] - beg : 0;
+  const size_t seg0 = (((size_t)n * M + m) * S + s) * KC;
   const GT *gb = gout + (size_t)n * Lq * M * D + (size_t)m * D + 4 * g;
   const size_t MD = (size_t)M * D;
   float acc[4] = {0, 0, 0, 0};
   const unsigned lane = threadIdx.x & 31;
   const unsigned gbase = lane & ~(unsigned)(GP - 1);
   int2 *mystrip = strip + (threadIdx.x / GP) * (GP * kSlots);
-  // the longest bucket in the warp decides which path every group of the warp takes, so that the
-  // full-mask shuffles below stay convergent
-  int wlen = len;
-#pragma unroll
-  for (int o = 16; o >= GP; o >>= 1) wlen = max(wlen, __shfl_xor_sync(0xffffffffu, wlen, o));
 
-  if (wlen <= kSlots * GP) {
-    int id[kSlots], wbits[kSlots], rank[kSlots];
+  for (int kc = 0; kc < KC; ++kc) {
+    const int beg = rowptr[seg0 + kc];
+    const int len = live ? cursor[seg0 + kc] - beg : 0;
+    // the longest bucket in the warp decides which path every group of the warp takes, so that
+    // the full-mask shuffles below stay convergent
+    int wlen = len;
 #pragma unroll
-    for (int k = 0; k < kSlots; ++k) {
-      const int e = k * GP + g;
-      int2 t = make_int2(0x7fffffff, 0);
-      if (e < len) t = entries[beg + e];
-      id[k] = t.x;
-      wbits[k] = t.y;
-      rank[k] = 0;
-    }
+    for (int o = 16; o >= GP; o >>= 1) wlen = max(wlen, __shfl_xor_sync(0xffffffffu, wlen, o));
+    if (wlen == 0) continue;
+
+    if (wlen <= kSlots * GP) {
+      int id[kSlots], wbits[kSlots], rank[kSlots];
 #pragma unroll
-    for (int k = 0; k < kSlots; ++k) {
-      for (int j = 0; j < GP && k * GP + j < wlen; ++j) {
-        const int other = __shfl_sync(0xffffffffu, id[k], gbase + j);
-#pragma unroll
-        for (int kk = 0; kk < kSlots; ++kk) rank[kk] += (other < id[kk]) ? 1 : 0;
+      for (int k = 0; k < kSlots; ++k) {
+        const int e = k * GP + g;
+        int2 t = make_int2(0x7fffffff, 0);
+        if (e < len) t = entries[beg + e];
+        id[k] = t.x;
+        wbits[k] = t.y;
+        rank[k] = 0;
       }
-    }
 #pragma unroll
-    for (int k = 0; k < kSlots; ++k)
-      if (k * GP + g < len) mystrip[rank[k]] = make_int2(id[k], wbits[k]);
-    __syncwarp();
-    if (lane_on) {
-      for (int r = 0; r < len; ++r) {
-        const int2 t = mystrip[r];
-        const int q = t.x / LP4;
-        float v[4];
-        load4(gb + (size_t)q * MD, v);
-        const float w = __int_as_float(t.y);
+      for (int k = 0; k < kSlots; ++k) {
+        for (int j = 0; j < GP && k * GP + j < wlen; ++j) {
+          const int other = __shfl_sync(0xffffffffu, id[k], gbase + j);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[i] += w * v[i];
-      }
-    }
-  } else {
-    // long bucket (pathological sampling patterns): selection by successive minima, still in id
-    // order, O(len^2 / GP) but correct for any length
-    int last = -1;
-    for (int r = 0; r < wlen; ++r) {
-      int best = 0x7fffffff;
-      float bw = 0.f;
-      for (int e = g; e < len; e += GP) {
-        const int2 t = entries[beg + e];
-        if (t.x > last && t.x < best) {
-          best = t.x;
-          bw = __int_as_float(t.y);
+          for (int kk = 0; kk < kSlots; ++kk) rank[kk] += (other < id[kk]) ? 1 : 0;
         }
       }
+      __syncwarp();   // previous bucket's strip reads are done
 #pragma unroll
-      for (int o = GP / 2; o > 0; o >>= 1) {
-        const int ob = __shfl_xor_sync(0xffffffffu, best, o, GP);
-        const float ow = __shfl_xor_sync(0xffffffffu, bw, o, GP);
-        if (ob < best) {
-          best = ob;
-          bw = ow;
-        }
-      }
-      if (best != 0x7fffffff) {
-        if (lane_on) {
-          const int q = best / LP4;
+      for (int k = 0; k < kSlots; ++k)
+        if (k * GP + g < len) mystrip[rank[k]] = make_int2(id[k], wbits[k]);
+      __syncwarp();
+      if (lane_on) {
+#pragma unroll 2
+        for (int r = 0; r < len; ++r) {
+          const int2 t = mystrip[r];
           float v[4];
-          load4(gb + (size_t)q * MD, v);
+          load4(gb + (size_t)(t.x >> idshift) * MD, v);
+          const float w = __int_as_float(t.y);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] += bw * v[i];
+          for (int i = 0; i < 4; ++i) acc[i] += w * v[i];
         }
-        last = best;
+      }
+    } else {
+      // long bucket (pathological sampling patterns): selection by successive minima, still in id
+      // order, O(len^2 / GP) but correct for any length
+      int last = -1;
+      for (int r = 0; r < wlen; ++r) {
+        int best = 0x7fffffff;
+        float bw = 0.f;
+        for (int e = g; e < len; e += GP) {
+          const int2 t = entries[beg + e];
+          if (t.x > last && t.x < best) {
+            best = t.x;
+            bw = __int_as_float(t.y);
+          }
+        }
+#pragma unroll
+        for (int o = GP / 2; o > 0; o >>= 1) {
+          const int ob = __shfl_xor_sync(0xffffffffu, best, o, GP);
+          const float ow = __shfl_xor_sync(0xffffffffu, bw, o, GP);
+          if (ob < best) {
+            best = ob;
+            bw = ow;
+          }
+        }
+        if (best != 0x7fffffff) {
+          if (lane_on) {
+            float v[4];
+            load4(gb + (size_t)(best >> idshift) * MD, v);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += bw * v[i];
+          }
+          last = best;
+        }
       }
     }
   }
@@ -486,7 +554,7 @@ __global__ void __launch_bounds__(256) msda_prep_bwd_kernel(const float *__restr
 // host side
 // ---------------------------------------------------------------------------------------------
 static int group_pad(int G) {
-  int gp = 4;
+  int gp = 1;
   while (gp < G) gp <<= 1;
   return gp;
 }
@@ -494,27 +562,53 @@ static int group_pad(int G) {
 static int check_msda_dims(int N, int S, int M, int D, int Lq, int L, int P) {
   ASIS_REQUIRE(N > 0 && S > 0 && M > 0 && D > 0 && Lq > 0 && L > 0 && P > 0, "msda: non-positive dimension");
   ASIS_REQUIRE(L <= kMaxLevels, "msda: n_levels %d > %d", L, kMaxLevels);
+  ASIS_REQUIRE(L * P <= 64, "msda: n_levels * n_points = %d > 64", L * P);
   ASIS_REQUIRE(D % 4 == 0 && D <= 128, "msda: head dim %d must be a multiple of 4 and <= 128", D);
   ASIS_REQUIRE(M <= 65535 && N <= 65535, "msda: n_heads / batch exceed grid limits");
-  ASIS_REQUIRE((size_t)Lq * L * P * 4 < ((size_t)1 << 31), "msda: too many sampling points per image");
+  ASIS_REQUIRE((size_t)S * M * D < ((size_t)1 << 31), "msda: one image's value tensor must have < 2^31 elements");
   return ASIS_OK;
+}
+
+// items (query, head pairs) per block so that the point table fits comfortably in shared memory
+static int items_per_block(int gp, int LP, int entry_bytes) {
+  int ipb = 256 / gp;
+  // at least one full warp per block (the kernels use full-mask shuffles)
+  while (ipb * gp > 32 && ipb * LP * entry_bytes > 40 * 1024) ipb >>= 1;
+  return ipb;
+}
+
+template <typename K>
+static int allow_smem(K kernel, size_t smem) {
+  if (smem > 48 * 1024) ASIS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return ASIS_OK;
+}
+
+// query chunks per pixel bucket: about 16 contributions per bucket on average
+static int query_chunks(int S, int Lq, int L, int P) {
+  const long long per_pixel = ((long long)Lq * L * P * 4 + S - 1) / S;
+  long long kc = (per_pixel + 15) / 16;
+  if (kc < 1) kc = 1;
+  if (kc > 64) kc = 64;
+  if (kc > Lq) kc = Lq;
+  return (int)kc;
+}
+
+static int id_shift(int L, int P) {
+  int sh = 0;
+  while ((1 << sh) < L * P * 4) ++sh;
+  return sh;
 }
 
 template <typename VT, typename OT>
 static int launch_fwd(const void *value, const int64_t *ss, const int64_t *lsi, const float *loc, const float *aw,
                       void *out, int N, int S, int M, int D, int Lq, int L, int P, cudaStream_t st) {
-  const int gp = group_pad(D / 4);
-  const int qpb = 256 / gp;
-  dim3 grid((Lq + qpb - 1) / qpb, M, N);
-#define ASIS_FWD(GPV)                                                                                             \
-  do {                                                                                                            \
-    if (P == 4)                                                                                                   \
-      msda_fwd_kernel<VT, OT, GPV, 4><<<grid, 256, 0, st>>>((const VT *)value, ss, lsi, loc, aw, (OT *)out, S, M, \
-                                                            D, Lq, L, P);                                         \
-    else                                                                                                          \
-      msda_fwd_kernel<VT, OT, GPV, 0><<<grid, 256, 0, st>>>((const VT *)value, ss, lsi, loc, aw, (OT *)out, S, M, \
-                                                            D, Lq, L, P);                                         \
-  } while (0)
+  const int gp = group_pad((D + 3) / 4) < 4 ? 4 : group_pad((D + 3) / 4);
+  const int ipb = items_per_block(gp, L * P, (int)sizeof(PointFwd));
+  const int threads = ipb * gp;
+  const size_t smem = (size_t)ipb * L * P * sizeof(PointFwd);
+  dim3 grid((Lq + ipb - 1) / ipb, M, N);
+#define ASIS_FWD(GPV) \
+  msda_fwd_kernel<VT, OT, GPV><<<grid, threads, smem, st>>>((const VT *)value, ss, lsi, loc, aw, (OT *)out, S, M, D, Lq, L, P)
   switch (gp) {
     case 4: ASIS_FWD(4); break;
     case 8: ASIS_FWD(8); break;
@@ -530,36 +624,50 @@ template <typename VT, typename GT>
 static int launch_bwd(const void *value, const int64_t *ss, const int64_t *lsi, const float *loc, const float *aw,
                       const void *gout, void *gvalue, float *gloc, float *gaw, int N, int S, int M, int D, int Lq,
                       int L, int P, int *counts, int *rowptr, int2 *entries, cudaStream_t st) {
-  const int gp = group_pad(D / 4);
-  const int ipb = 256 / gp;
-  const size_t nms = (size_t)N * M * S;
-  ASIS_CUDA(cudaMemsetAsync(counts, 0, nms * sizeof(int), st));
+  const int KC = query_chunks(S, Lq, L, P);
+  const int qchunk = (Lq + KC - 1) / KC;
+  const int idshift = id_shift(L, P);
+  ASIS_REQUIRE(((long long)Lq << idshift) < (1LL << 31), "msda_backward: contribution id exceeds int32");
+  const size_t nbuckets = (size_t)N * M * S * KC;
+  ASIS_CUDA(cudaMemsetAsync(counts, 0, nbuckets * sizeof(int), st));
   {
+    // 16 channels per lane: D/16 lanes per (query, head)
+    const int gp = group_pad((D + 15) / 16);
+    const int ipb = items_per_block(gp, L * P, (int)sizeof(PointBwd));
+    const int threads = ipb * gp;
+    const size_t smem = (size_t)ipb * L * P * sizeof(PointBwd);
     dim3 grid((Lq + ipb - 1) / ipb, M, N);
+#define ASIS_LOCAW(GPV)                                                                                            \
+  if (int rc = allow_smem(msda_bwd_locaw_kernel<VT, GT, GPV>, smem)) return rc;                                    \
+  msda_bwd_locaw_kernel<VT, GT, GPV><<<grid, threads, smem, st>>>((const VT *)value, ss, lsi, loc, aw, (const GT *)gout, \
+                                                                   gloc, gaw, counts, S, M, D, Lq, L, P, KC, qchunk)
     switch (gp) {
-      case 4: msda_bwd_locaw_kernel<VT, GT, 4><<<grid, 256, 0, st>>>((const VT *)value, ss, lsi, loc, aw, (const GT *)gout, gloc, gaw, counts, S, M, D, Lq, L, P); break;
-      case 8: msda_bwd_locaw_kernel<VT, GT, 8><<<grid, 256, 0, st>>>((const VT *)value, ss, lsi, loc, aw, (const GT *)gout, gloc, gaw, counts, S, M, D, Lq, L, P); break;
-      case 16: msda_bwd_locaw_kernel<VT, GT, 16><<<grid, 256, 0, st>>>((const VT *)value, ss, lsi, loc, aw, (const GT *)gout, gloc, gaw, counts, S, M, D, Lq, L, P); break;
-      default: msda_bwd_locaw_kernel<VT, GT, 32><<<grid, 256, 0, st>>>((const VT *)value, ss, lsi, loc, aw, (const GT *)gout, gloc, gaw, counts, S, M, D, Lq, L, P); break;
+      case 1: { ASIS_LOCAW(1); } break;
+      case 2: { ASIS_LOCAW(2); } break;
+      case 4: { ASIS_LOCAW(4); } break;
+      default: { ASIS_LOCAW(8); } break;
     }
+#undef ASIS_LOCAW
     ASIS_LAUNCHED();
   }
   const int cap = Lq * L * P * 4;
-  // counts -> rowptr (start) ; counts buffer is then reused as the fill cursor
-  msda_bwd_scan_kernel<<<N * M, 1024, 0, st>>>(counts, rowptr, counts, S, cap);
+  // counts -> rowptr (start) ; the counts buffer is then reused as the fill cursor
+  msda_bwd_scan_kernel<<<N * M, 1024, 0, st>>>(counts, rowptr, counts, S * KC, cap);
   ASIS_LAUNCHED();
   {
     const size_t total = (size_t)N * Lq * M * L * P;
-    msda_bwd_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ss, lsi, loc, aw, counts, entries, S, M, Lq, L, P, total);
+    msda_bwd_fill_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ss, lsi, loc, aw, counts, entries, S, M, Lq, L, P, KC, qchunk, idshift, total);
     ASIS_LAUNCHED();
   }
   {
+    const int gp = group_pad((D + 3) / 4) < 4 ? 4 : group_pad((D + 3) / 4);
+    const int ipb = 256 / gp;
     dim3 grid((S + ipb - 1) / ipb, M, N);
     switch (gp) {
-      case 4: msda_bwd_gather_kernel<GT, 4><<<grid, 256, 0, st>>>((const GT *)gout, rowptr, counts, entries, (GT *)gvalue, S, M, D, Lq, L * P * 4); break;
-      case 8: msda_bwd_gather_kernel<GT, 8><<<grid, 256, 0, st>>>((const GT *)gout, rowptr, counts, entries, (GT *)gvalue, S, M, D, Lq, L * P * 4); break;
-      case 16: msda_bwd_gather_kernel<GT, 16><<<grid, 256, 0, st>>>((const GT *)gout, rowptr, counts, entries, (GT *)gvalue, S, M, D, Lq, L * P * 4); break;
-      default: msda_bwd_gather_kernel<GT, 32><<<grid, 256, 0, st>>>((const GT *)gout, rowptr, counts, entries, (GT *)gvalue, S, M, D, Lq, L * P * 4); break;
+      case 4: msda_bwd_gather_kernel<GT, 4><<<grid, 256, 0, st>>>((const GT *)gout, rowptr, counts, entries, (GT *)gvalue, S, M, D, Lq, KC, idshift); break;
+      case 8: msda_bwd_gather_kernel<GT, 8><<<grid, 256, 0, st>>>((const GT *)gout, rowptr, counts, entries, (GT *)gvalue, S, M, D, Lq, KC, idshift); break;
+      case 16: msda_bwd_gather_kernel<GT, 16><<<grid, 256, 0, st>>>((const GT *)gout, rowptr, counts, entries, (GT *)gvalue, S, M, D, Lq, KC, idshift); break;
+      default: msda_bwd_gather_kernel<GT, 32><<<grid, 256, 0, st>>>((const GT *)gout, rowptr, counts, entries, (GT *)gvalue, S, M, D, Lq, KC, idshift); break;
     }
     ASIS_LAUNCHED();
   }
@@ -586,7 +694,8 @@ extern "C" int asis_msda_forward(const void *value, int value_dtype, const int64
 
 extern "C" size_t asis_msda_backward_workspace_bytes(int N, int S, int M, int D, int Lq, int L, int P) {
   (void)D;
-  const size_t nms = align_up((size_t)N * M * S * sizeof(int), 256);
+  if (N <= 0 || S <= 0 || M <= 0 || Lq <= 0 || L <= 0 || P <= 0) return 0;
+  const size_t nms = align_up((size_t)N * M * S * query_chunks(S, Lq, L, P) * sizeof(int), 256);
   const size_t ent = align_up((size_t)N * M * Lq * L * P * 4 * sizeof(int2), 256);
   return 2 * nms + ent;
 }
@@ -605,7 +714,7 @@ extern "C" int asis_msda_backward(const void *value, int value_dtype, const int6
   const size_t need = asis_msda_backward_workspace_bytes(N, S, M, D, Lq, L, P);
   if (workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "msda_backward: workspace %zu < %zu bytes", workspace_bytes, need);
   ASIS_REQUIRE(aligned16(workspace) && aligned16(value) && aligned16(grad_out) && aligned16(grad_value), "msda_backward: pointers must be 16-byte aligned");
-  const size_t nms = align_up((size_t)N * M * S * sizeof(int), 256);
+  const size_t nms = align_up((size_t)N * M * S * query_chunks(S, Lq, L, P) * sizeof(int), 256);
   int *counts = (int *)workspace;
   int *rowptr = (int *)((char *)workspace + nms);
   int2 *entries = (int2 *)((char *)workspace + 2 * nms);
