@@ -349,6 +349,34 @@ __global__ void __launch_bounds__(256) msda_bwd_fill_kernel(const int64_t *__res
   if (yb && xr) entries[atomicAdd(cu + (size_t)(base + W + 1) * KC, 1)] = make_int2(id + 3, __float_as_int(f.fx * f.fy * a));
 }
 
+// Bring one bucket into registers (NS entries per lane), rank every entry by id (one shuffle per
+// bucket entry, NS compares), and write it to its rank position in the group's smem strip.
+template <int NS, int GP>
+__device__ __forceinline__ void bucket_to_strip(const int2 *__restrict__ entries, int beg, int len, int wlen, int g,
+                                                unsigned gbase, int2 *mystrip) {
+  int id[NS], wbits[NS], rank[NS];
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    const int e = k * GP + g;
+    int2 t = make_int2(0x7fffffff, 0);
+    if (e < len) t = entries[beg + e];
+    id[k] = t.x;
+    wbits[k] = t.y;
+    rank[k] = 0;
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k) {
+    for (int j = 0; j < GP && k * GP + j < wlen; ++j) {
+      const int other = __shfl_sync(0xffffffffu, id[k], gbase + j);
+#pragma unroll
+      for (int kk = 0; kk < NS; ++kk) rank[kk] += (other < id[kk]) ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NS; ++k)
+    if (k * GP + g < len) mystrip[rank[k]] = make_int2(id[k], wbits[k]);
+}
+
 // gather: one group of GP lanes per (n, s, m).  The pixel's KC buckets are walked in chunk order;
 // each bucket [rowptr, cursor) is brought into registers (kSlots entries per lane), every entry is
 // ranked by id with one shuffle per entry, written to its rank position in a per-group
@@ -387,31 +415,14 @@ __global__ void __launch_bounds__(256) msda_bwd_gather_kernel(const GT *__restri
     if (wlen == 0) continue;
 
     if (wlen <= kSlots * GP) {
-      int id[kSlots], wbits[kSlots], rank[kSlots];
-#pragma unroll
-      for (int k = 0; k < kSlots; ++k) {
-        const int e = k * GP + g;
-        int2 t = make_int2(0x7fffffff, 0);
-        if (e < len) t = entries[beg + e];
-        id[k] = t.x;
-        wbits[k] = t.y;
-        rank[k] = 0;
-      }
-#pragma unroll
-      for (int k = 0; k < kSlots; ++k) {
-        for (int j = 0; j < GP && k * GP + j < wlen; ++j) {
-          const int other = __shfl_sync(0xffffffffu, id[k], gbase + j);
-#pragma unroll
-          for (int kk = 0; kk < kSlots; ++kk) rank[kk] += (other < id[kk]) ? 1 : 0;
-        }
-      }
       __syncwarp();   // previous bucket's strip reads are done
-#pragma unroll
-      for (int k = 0; k < kSlots; ++k)
-        if (k * GP + g < len) mystrip[rank[k]] = make_int2(id[k], wbits[k]);
+      // number of register slots per lane this warp needs (warp-uniform): the common case is 1
+      if (wlen <= GP) bucket_to_strip<1, GP>(entries, beg, len, wlen, g, gbase, mystrip);
+      else if (wlen <= 2 * GP) bucket_to_strip<2, GP>(entries, beg, len, wlen, g, gbase, mystrip);
+      else bucket_to_strip<kSlots, GP>(entries, beg, len, wlen, g, gbase, mystrip);
       __syncwarp();
       if (lane_on) {
-#pragma unroll 2
+#pragma unroll 4
         for (int r = 0; r < len; ++r) {
           const int2 t = mystrip[r];
           float v[4];
