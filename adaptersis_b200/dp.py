@@ -52,15 +52,25 @@ class BucketedGradAllReduce:
         if self._pending[i] == 0:
             self._launch(i)
 
-    def _launch(self, i):
+    def _launch(self, i, partial=False):
         if self.world == 1:
             return
         bucket = self.buckets[i]
+        if partial:
+            # parameters that took no part in this step (e.g. cls_token / pos_embed / final norm, which
+            # only the forward-only taps pass touches): reduce the rest of the bucket.  The set is the
+            # same on every rank because the graph is.
+            bucket = [p for p in bucket if p.grad is not None]
+            if not bucket:
+                return
         dev = bucket[0].device
         n = sum(p.numel() for p in bucket)
-        if self._flat[i] is None:
-            self._flat[i] = torch.empty(n, dtype=torch.float32, device=dev)
-        flat = self._flat[i]
+        if partial:
+            flat = torch.empty(n, dtype=torch.float32, device=dev)
+        else:
+            if self._flat[i] is None:
+                self._flat[i] = torch.empty(n, dtype=torch.float32, device=dev)
+            flat = self._flat[i]
         side = self._stream(dev)
         if side is not None:
             side.wait_stream(torch.cuda.current_stream(dev))
@@ -71,21 +81,18 @@ class BucketedGradAllReduce:
         with ctx:
             torch._foreach_copy_(list(flat.split([p.numel() for p in bucket])), [p.grad.reshape(-1).float() for p in bucket])
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._works.append((i, work))
+        self._works.append((bucket, flat, work))
 
     def finish(self):
         """Wait for all buckets, write the reduced (averaged) gradients back."""
         if self.world == 1:
             self.reset()
             return
-        # parameters that never received a gradient this step leave their bucket unreduced
         for i, left in enumerate(self._pending):
-            if left != 0 and left != len(self.buckets[i]):
-                raise RuntimeError("gradient bucket partially filled: unused parameters in a bucket")
-        for i, work in self._works:
+            if left != 0:
+                self._launch(i, partial=True)
+        for bucket, flat, work in self._works:
             work.wait()
-            bucket = self.buckets[i]
-            flat = self._flat[i]
             if self.average:
                 flat.div_(self.world)
             for p, chunk in zip(bucket, flat.split([p.numel() for p in bucket])):

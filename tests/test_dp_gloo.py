@@ -24,7 +24,8 @@ def _worker(rank, world, port, q):
         from adaptersis_b200.dp import BucketedGradAllReduce
         torch.manual_seed(0)
         net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 16), torch.nn.Linear(16, 4))
-        red = BucketedGradAllReduce(net.parameters(), bucket_bytes=600)     # forces several buckets
+        unused = torch.nn.Linear(3, 3)              # never takes part in the step (like cls_token / pos_embed here)
+        red = BucketedGradAllReduce(list(net.parameters()) + list(unused.parameters()), bucket_bytes=600)
         assert len(red.buckets) >= 3
         for step in range(2):
             g = torch.Generator().manual_seed(100 + step)
@@ -32,6 +33,7 @@ def _worker(rank, world, port, q):
             net.zero_grad(set_to_none=True)
             net(data[rank]).square().sum().backward()
             red.finish()
+            assert all(p.grad is None for p in unused.parameters())
             got = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
             ref_net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 16), torch.nn.Linear(16, 4))
             ref_net.load_state_dict(net.state_dict())
