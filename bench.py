@@ -259,11 +259,11 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_ms, t_e2e_ms = float(tt[0]), float(tt[1])
 
-    if rank != 0:
-        return
     # one extra, un-timed step with per-op CUDA events -> roofline of the dominant kernel
+    # (every rank runs it -- the step contains collectives -- only rank 0 records)
     prof = SpanProfiler()
-    kernels.set_profiler(prof)
+    if rank == 0:
+        kernels.set_profiler(prof)
     torch.cuda.synchronize()
     p0 = torch.cuda.Event(enable_timing=True)
     p1 = torch.cuda.Event(enable_timing=True)
@@ -271,6 +271,9 @@ def run_ours(args, rank, world, local_rank):
     ts.step_device(*dev_batches[0])
     p1.record()
     kernels.set_profiler(None)
+    barrier()
+    if rank != 0:
+        return
     agg = prof.summary()
     prof_step_ms = p0.elapsed_time(p1)
     pk, pk_src = peaks()
