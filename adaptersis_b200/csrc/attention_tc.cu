@@ -107,7 +107,8 @@ struct AttnParams {
   float scale;
   bf16 *out;         // fwd: [B, T, H*64]
   float *lse;        // [B, H, T]   natural-log log-sum-exp of the scaled scores
-  const float *dvec; // bwd: [B, H, T]  rowsum(dO * O)
+  const float *dvec; // bwd: [B, H, Tp] rowsum(dO * O), Tp = ceil(T/64)*64, zero tail
+  const float *lse2; // bwd: [B, H, Tp] lse * log2(e), zero tail
   bf16 *dqkv;        // bwd: [B, T, 3, H, 64]
 };
 
@@ -118,7 +119,8 @@ constexpr uint32_t TMEM_COLS = 512;
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-constexpr int FWD_STAGES = 3;
+constexpr int FWD_STAGES = 4;
+constexpr int NSB = 3;              // rotating score buffers in TMEM (tile t uses buffer t % 3)
 constexpr int FWD_SMEM = T16K /*Q*/ + FWD_STAGES * 2 * T16K /*K,V*/ + 2 * T32K /*P per warpgroup*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -131,7 +133,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint8_t *sP = sV + FWD_STAGES * T16K;          // one 32 KB buffer per warpgroup
   uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * T32K);
   uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = kv_full + FWD_STAGES, *s_full = kv_empty + FWD_STAGES,
-           *s_empty = s_full + 2, *p_full = s_empty + 2, *o_full = p_full + 2, *o_empty = o_full + 2;
+           *s_empty = s_full + NSB, *p_full = s_empty + NSB, *o_full = p_full + 2, *o_empty = o_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -146,9 +148,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       mbar_init(kv_full + i, 1);
       mbar_init(kv_empty + i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSB; ++i) {
       mbar_init(s_full + i, 1);
       mbar_init(s_empty + i, 4);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(p_full + i, 4);
       mbar_init(o_full + i, 1);
       mbar_init(o_empty + i, 4);
@@ -160,7 +164,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tO = tmem + 256;     // S[w] at w*128, O[w] at 256 + w*64
+  const uint32_t tS = tmem, tO = tmem + NSB * TILE;     // S[b] at b*128 (b < 3), O[w] at 384 + w*64
 
   if (warp == 0) {
     if (lane == 0) {
@@ -180,18 +184,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       constexpr uint32_t idesc_o = make_idesc(TILE, HD, 0, 1);     // O = P V   : V is MN-major
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
       mbar_wait(q_full, 0);
+      // Scores go round three TMEM buffers, so the S of a warpgroup's next tile is issued when the
+      // *other* warpgroup finishes a tile -- half a tile ahead of its use (with one buffer per
+      // warpgroup the softmax warps spent 30 % of their time waiting for S).
       auto issue_s = [&](int j) {
-        const int w = j & 1, u = j >> 1, st = j % FWD_STAGES;
+        const int sb = j % NSB, ub = j / NSB, st = j % FWD_STAGES;
         mbar_wait(kv_full + st, (j / FWD_STAGES) & 1);
-        if (u > 0) mbar_wait(s_empty + w, (u - 1) & 1);
+        if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tS + w * TILE, desc_kmajor(aQ, k), desc_kmajor(aK + st * T16K, k), idesc_s, k > 0);
-        umma_commit(s_full + w);
+          umma_bf16(tS + sb * TILE, desc_kmajor(aQ, k), desc_kmajor(aK + st * T16K, k), idesc_s, k > 0);
+        umma_commit(s_full + sb);
       };
-      issue_s(0);
-      if (nkv > 1) issue_s(1);
+      for (int j = 0; j < NSB && j < nkv; ++j) issue_s(j);
       for (int j = 0; j < nkv; ++j) {
         const int w = j & 1, u = j >> 1, st = j % FWD_STAGES;
         mbar_wait(p_full + w, u & 1);
@@ -202,7 +208,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
           umma_bf16(tO + w * HD, desc_kmajor(aP + w * T32K, k), desc_mnmajor(aV + st * T16K, k), idesc_o, k > 0);
         umma_commit(o_full + w);
         umma_commit(kv_empty + st);
-        if (j + 2 < nkv) issue_s(j + 2);
+        if (j + NSB < nkv) issue_s(j + NSB);
       }
     }
   } else {
@@ -219,7 +225,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     for (int j = w; j < nkv; j += 2, ++u) {
       const int kv0 = j * TILE;
       const bool tail = kv0 + TILE > p.T;            // only the last key block has invalid columns
-      mbar_wait(s_full + w, u & 1);
+      const int sb = j % NSB;
+      mbar_wait(s_full + sb, (j / NSB) & 1);
       tc_fence_after();
       // pass 1: row maximum of the raw scores (scale > 0, applied once to the maximum); TMEM loads
       // two at a time, four independent max chains
@@ -227,8 +234,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll
       for (int c = 0; c < 4; c += 2) {
         float v0[32], v1[32];
-        tmem_ld32_issue(tS + lane_addr + w * TILE + c * 32, v0);
-        tmem_ld32_issue(tS + lane_addr + w * TILE + c * 32 + 32, v1);
+        tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32, v0);
+        tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32 + 32, v1);
         tmem_ld_wait();
         if (tail) {
 #pragma unroll
@@ -272,8 +279,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 #pragma unroll
       for (int c = 0; c < 4; c += 2) {
         float v0[32], v1[32];
-        tmem_ld32_issue(tS + lane_addr + w * TILE + c * 32, v0);
-        tmem_ld32_issue(tS + lane_addr + w * TILE + c * 32 + 32, v1);
+        tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32, v0);
+        tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32 + 32, v1);
         tmem_ld_wait();
         if (tail) {
 #pragma unroll
@@ -298,7 +305,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty + w);
+        mbar_arrive(s_empty + sb);
         mbar_arrive(p_full + w);
       }
       l_run = l_run * alpha + l_add;
@@ -352,18 +359,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward prep: D[b,h,t] = sum_e dO[b,t,h,e] * O[b,t,h,e]
+// backward prep: D[b,h,t] = sum_e dO[b,t,h,e] * O[b,t,h,e] and lse * log2(e), both written with a
+// row pitch Tp = ceil(T/64)*64 (zero tail), so that the kernels can bulk-copy 64-entry tiles and
+// never need a bounds check
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16 *__restrict__ out, const bf16 *__restrict__ dout,
-                                                            float *__restrict__ dvec, int B, int T, int H) {
-  // one 8-lane group per (b, t, h): 8 lanes x 8 bf16 = 64 elements
+                                                            const float *__restrict__ lse, float *__restrict__ dvec,
+                                                            float *__restrict__ lse2, int B, int T, int Tp, int H) {
+  // one 8-lane group per (b, t, h) with t < Tp: 8 lanes x 8 bf16 = 64 elements
   const size_t gidx = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
   const int sub = threadIdx.x & 7;
-  const size_t total = (size_t)B * T * H;
+  const size_t total = (size_t)B * Tp * H;
+  const bool in = gidx < total;
+  const int h = in ? (int)(gidx % H) : 0;
+  const size_t bt = in ? gidx / H : 0;
+  const int t = (int)(bt % Tp);
+  const int b = (int)(bt / Tp);
+  const bool real = in && t < T;
   float acc = 0.f;
-  if (gidx < total) {
-    const uint4 a = *reinterpret_cast<const uint4 *>(out + gidx * HD + sub * 8);
-    const uint4 d = *reinterpret_cast<const uint4 *>(dout + gidx * HD + sub * 8);
+  if (real) {
+    const size_t src = (((size_t)b * T + t) * H + h) * HD + sub * 8;
+    const uint4 a = *reinterpret_cast<const uint4 *>(out + src);
+    const uint4 d = *reinterpret_cast<const uint4 *>(dout + src);
     const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -375,12 +392,10 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16 *__restri
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
   acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (gidx < total && sub == 0) {
-    const int h = (int)(gidx % H);
-    const size_t bt = gidx / H;
-    const int t = (int)(bt % T);
-    const int b = (int)(bt / T);
-    dvec[((size_t)b * H + h) * T + t] = acc;
+  if (in && sub == 0) {
+    const size_t o = ((size_t)b * H + h) * Tp + t;
+    dvec[o] = real ? acc : 0.f;
+    lse2[o] = real ? lse[((size_t)b * H + h) * T + t] * LOG2E : 0.f;
   }
 }
 
@@ -389,7 +404,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16 *__restri
 // ------------------------------------------------------------------------------------------------
 constexpr int BWD_STAGES = 4;
 constexpr int BWD_SMEM = 2 * T16K /*resident pair*/ + BWD_STAGES * 2 * T8K /*streamed pair*/ + 2 * 2 * T16K /*2 bufs x 2 WGs*/ +
-                         2 * 2 * HALF * 4 + 1024 + 256;
+                         BWD_STAGES * 2 * HALF * 4 /*lse, D tiles*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ,
@@ -402,17 +417,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
   uint8_t *sDO = sQ + BWD_STAGES * T8K;    // BWD_STAGES x 8 KB
   uint8_t *sPT = sDO + BWD_STAGES * T8K;   // P^T   [128 keys x 64 queries], one per warpgroup
   uint8_t *sDST = sPT + 2 * T16K;          // dS^T, one per warpgroup
-  float *sLse = reinterpret_cast<float *>(sDST + 2 * T16K);   // [2][64]
-  float *sD = sLse + 2 * HALF;                                // [2][64]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sD + 2 * HALF);
+  float *sLse = reinterpret_cast<float *>(sDST + 2 * T16K);   // [BWD_STAGES][64]  lse * log2e of the stage's queries
+  float *sD = sLse + BWD_STAGES * HALF;                       // [BWD_STAGES][64]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sD + BWD_STAGES * HALF);
   uint64_t *kv_full = bars, *q_full = bars + 1, *q_empty = q_full + BWD_STAGES, *s_full = q_empty + BWD_STAGES,
-           *s_empty = s_full + 2, *p_full = s_empty + 2, *acc_full = p_full + 2;
+           *s_empty = s_full + NSB, *p_full = s_empty + NSB, *pbuf_free = p_full + 2, *acc_full = pbuf_free + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
   const int C = p.H * HD;
   const int nq = (p.T + HALF - 1) / HALF;
+  const int Tp = nq * HALF;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmKV);
@@ -423,10 +439,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
       mbar_init(q_full + i, 1);
       mbar_init(q_empty + i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSB; ++i) {
       mbar_init(s_full + i, 1);
       mbar_init(s_empty + i, 4);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(p_full + i, 4);
+      mbar_init(pbuf_free + i, 1);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -436,20 +455,24 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // S^T[w] at w*64, dP^T[w] at 128 + w*64, dV at 256, dK at 320
-  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 320;
+  // score buffer sb (tile i uses i % 3): S^T at sb*128, dP^T at sb*128 + 64; dV at 384, dK at 448
+  const uint32_t tSC = tmem, tDV = tmem + NSB * 2 * HALF, tDK = tDV + HD;
 
   if (warp == 0) {
     if (lane == 0) {
+      const float *lse_b = p.lse2 + ((size_t)b * p.H + h) * Tp;
+      const float *d_b = p.dvec + ((size_t)b * p.H + h) * Tp;
       mbar_arrive_expect_tx(kv_full, 2 * T16K);
       tma_load_3d(&tmKV, kv_full, sK, C + h * HD, k0, b);
       tma_load_3d(&tmKV, kv_full, sV, 2 * C + h * HD, k0, b);
       for (int i = 0; i < nq; ++i) {
         const int st = i % BWD_STAGES, use = i / BWD_STAGES;
         if (use > 0) mbar_wait(q_empty + st, (use - 1) & 1);
-        mbar_arrive_expect_tx(q_full + st, 2 * T8K);
+        mbar_arrive_expect_tx(q_full + st, 2 * T8K + 2 * HALF * 4);
         tma_load_3d(&tmQ, q_full + st, sQ + st * T8K, h * HD, i * HALF, b);
         tma_load_3d(&tmDO, q_full + st, sDO + st * T8K, h * HD, i * HALF, b);
+        bulk_load_1d(q_full + st, sLse + st * HALF, lse_b + i * HALF, HALF * 4);
+        bulk_load_1d(q_full + st, sD + st * HALF, d_b + i * HALF, HALF * 4);
       }
     }
   } else if (warp == 1) {
@@ -459,21 +482,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO),
                      aPT = smem_u32(sPT), aDST = smem_u32(sDST);
       mbar_wait(kv_full, 0);
-      auto issue_scores = [&](int i) {      // S^T = K Q_i^T, dP^T = V dO_i^T into warpgroup (i & 1)'s buffers
-        const int w = i & 1, u = i >> 1, st = i % BWD_STAGES;
+      auto issue_scores = [&](int i) {      // S^T = K Q_i^T, dP^T = V dO_i^T into score buffer i % 3
+        const int sb = i % NSB, ub = i / NSB, st = i % BWD_STAGES;
         mbar_wait(q_full + st, (i / BWD_STAGES) & 1);
-        if (u > 0) mbar_wait(s_empty + w, (u - 1) & 1);
+        if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tST + w * HALF, desc_kmajor(aK, k), desc_kmajor(aQ + st * T8K, k), idesc_s, k > 0);
+          umma_bf16(tSC + sb * 2 * HALF, desc_kmajor(aK, k), desc_kmajor(aQ + st * T8K, k), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tDPT + w * HALF, desc_kmajor(aV, k), desc_kmajor(aDO + st * T8K, k), idesc_s, k > 0);
-        umma_commit(s_full + w);
+          umma_bf16(tSC + sb * 2 * HALF + HALF, desc_kmajor(aV, k), desc_kmajor(aDO + st * T8K, k), idesc_s, k > 0);
+        umma_commit(s_full + sb);
       };
-      issue_scores(0);
-      if (nq > 1) issue_scores(1);
+      for (int i = 0; i < NSB && i < nq; ++i) issue_scores(i);
       for (int i = 0; i < nq; ++i) {
         const int w = i & 1, u = i >> 1, st = i % BWD_STAGES;
         mbar_wait(p_full + w, u & 1);         // P^T and dS^T of tile i are in smem
@@ -484,10 +506,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
 #pragma unroll
         for (int k = 0; k < 4; ++k)           // dK += dS^T Q
           umma_bf16(tDK, desc_kmajor(aDST + w * T16K, k), desc_mnmajor(aQ + st * T8K, k), idesc_g, (i > 0 || k > 0));
-        umma_commit(q_empty + st);
-        // issued after the dV/dK MMAs of tile i: when s_full of tile i+2 fires, warpgroup w may
-        // also overwrite its P^T / dS^T buffers (in-order tensor pipe)
-        if (i + 2 < nq) issue_scores(i + 2);
+        umma_commit(q_empty + st);            // the Q/dO/lse/D stage may be refilled
+        umma_commit(pbuf_free + w);           // warpgroup w may overwrite its P^T / dS^T buffers
+        if (i + NSB < nq) issue_scores(i + NSB);
       }
       umma_commit(acc_full);
     }
@@ -496,30 +517,23 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;     // key row inside the tile
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const int tid = (threadIdx.x - 64) & 127;
-    const float *lse_b = p.lse + ((size_t)b * p.H + h) * p.T;
-    const float *d_b = p.dvec + ((size_t)b * p.H + h) * p.T;
-    float *myLse = sLse + w * HALF, *myD = sD + w * HALF;
     uint8_t *myPT = sPT + w * T16K, *myDST = sDST + w * T16K;
     int u = 0;
     for (int i = w; i < nq; i += 2, ++u) {
-      named_bar_sync(1 + w, 128);            // the warpgroup is done reading myLse/myD of its previous tile
-      if (tid < HALF) {
-        const int qi = i * HALF + tid;
-        myLse[tid] = qi < p.T ? lse_b[qi] * LOG2E : 0.f;
-        myD[tid] = qi < p.T ? d_b[qi] : 0.f;
-      }
-      named_bar_sync(1 + w, 128);
-      mbar_wait(s_full + w, u & 1);
+      const int sb = i % NSB, st = i % BWD_STAGES;
+      mbar_wait(q_full + st, (i / BWD_STAGES) & 1);   // lse / D tile of this stage (bulk copies) has landed
+      mbar_wait(s_full + sb, (i / NSB) & 1);
       tc_fence_after();
+      if (u > 0) mbar_wait(pbuf_free + w, (u - 1) & 1);
+      const float *myLse = sLse + st * HALF, *myD = sD + st * HALF;
       // No masking is needed here: query columns >= T have zero Q / dO rows (TMA zero fill) and
       // lse = D = 0, so their P^T multiplies zero dO rows and their dS^T is exactly 0; key rows >= T
       // only pollute their own (never stored) dV / dK rows.
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        float st[32], dp[32];
-        tmem_ld32_issue(tST + lane_addr + w * HALF + c * 32, st);
-        tmem_ld32_issue(tDPT + lane_addr + w * HALF + c * 32, dp);
+        float st_[32], dp[32];
+        tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + c * 32, st_);
+        tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + HALF + c * 32, dp);
         tmem_ld_wait();
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
@@ -529,19 +543,19 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int q = q4 * 4 + k;
-            const float pr = fast_exp2(fmaf(st[q], p.scale_log2, -ls[k]));
-            st[q] = pr;
+            const float pr = fast_exp2(fmaf(st_[q], p.scale_log2, -ls[k]));
+            st_[q] = pr;
             dp[q] = pr * (dp[q] - ds[k]);
           }
         }
-        store_row32(myPT, TILE, row, c * 32, st);
+        store_row32(myPT, TILE, row, c * 32, st_);
         store_row32(myDST, TILE, row, c * 32, dp);
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty + w);
+        mbar_arrive(s_empty + sb);
         mbar_arrive(p_full + w);
       }
     }
@@ -550,12 +564,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
     // warpgroup 0 writes dV, warpgroup 1 writes dK
     const int t = k0 + row;
     float acc[64];
+    {
+      float v0[32], v1[32];
+      tmem_ld32_issue((w == 0 ? tDV : tDK) + lane_addr, v0);
+      tmem_ld32_issue((w == 0 ? tDV : tDK) + lane_addr + 32, v1);
+      tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      float v[32];
-      tmem_ld32((w == 0 ? tDV : tDK) + lane_addr + c * 32, v);
-#pragma unroll
-      for (int q = 0; q < 32; ++q) acc[c * 32 + q] = v[q];
+      for (int q = 0; q < 32; ++q) {
+        acc[q] = v0[q];
+        acc[32 + q] = v1[q];
+      }
     }
     if (t < p.T)
       store_out64(p.dqkv + ((size_t)b * p.T + t) * 3 * C + (w == 0 ? 2 * C : C) + h * HD, acc, w == 0 ? 1.f : p.scale);
@@ -581,15 +599,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t *sK = sDO + T16K;                // BWD_STAGES x 8 KB
   uint8_t *sV = sK + BWD_STAGES * T8K;     // BWD_STAGES x 8 KB
   uint8_t *sDS = sV + BWD_STAGES * T8K;    // dS [128 queries x 64 keys], one per warpgroup
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sDS + 4 * T16K + 2 * 2 * HALF * 4);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sDS + 4 * T16K + BWD_STAGES * 2 * HALF * 4);
   uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = kv_full + BWD_STAGES, *s_full = kv_empty + BWD_STAGES,
-           *s_empty = s_full + 2, *p_full = s_empty + 2, *acc_full = p_full + 2;
+           *s_empty = s_full + NSB, *p_full = s_empty + NSB, *pbuf_free = p_full + 2, *acc_full = pbuf_free + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
   const int C = p.H * HD;
   const int nkv = (p.T + HALF - 1) / HALF;
+  const int Tp = nkv * HALF;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -600,10 +619,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(kv_full + i, 1);
       mbar_init(kv_empty + i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NSB; ++i) {
       mbar_init(s_full + i, 1);
       mbar_init(s_empty + i, 4);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(p_full + i, 4);
+      mbar_init(pbuf_free + i, 1);
     }
     mbar_init(acc_full, 1);
     fence_barrier_init();
@@ -613,7 +635,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tDP = tmem + 128, tDQ = tmem + 256;   // S[w] at w*64, dP[w] at 128 + w*64
+  const uint32_t tSC = tmem, tDQ = tmem + NSB * 2 * HALF;   // S at sb*128, dP at sb*128 + 64; dQ at 384
 
   if (warp == 0) {
     if (lane == 0) {
@@ -634,21 +656,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);
       const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sDS);
       mbar_wait(q_full, 0);
-      auto issue_scores = [&](int j) {      // S = Q K_j^T, dP = dO V_j^T
-        const int w = j & 1, u = j >> 1, st = j % BWD_STAGES;
+      auto issue_scores = [&](int j) {      // S = Q K_j^T, dP = dO V_j^T into score buffer j % 3
+        const int sb = j % NSB, ub = j / NSB, st = j % BWD_STAGES;
         mbar_wait(kv_full + st, (j / BWD_STAGES) & 1);
-        if (u > 0) mbar_wait(s_empty + w, (u - 1) & 1);
+        if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tS + w * HALF, desc_kmajor(aQ, k), desc_kmajor(aK + st * T8K, k), idesc_s, k > 0);
+          umma_bf16(tSC + sb * 2 * HALF, desc_kmajor(aQ, k), desc_kmajor(aK + st * T8K, k), idesc_s, k > 0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(tDP + w * HALF, desc_kmajor(aDO, k), desc_kmajor(aV + st * T8K, k), idesc_s, k > 0);
-        umma_commit(s_full + w);
+          umma_bf16(tSC + sb * 2 * HALF + HALF, desc_kmajor(aDO, k), desc_kmajor(aV + st * T8K, k), idesc_s, k > 0);
+        umma_commit(s_full + sb);
       };
-      issue_scores(0);
-      if (nkv > 1) issue_scores(1);
+      for (int j = 0; j < NSB && j < nkv; ++j) issue_scores(j);
       for (int j = 0; j < nkv; ++j) {
         const int w = j & 1, u = j >> 1, st = j % BWD_STAGES;
         mbar_wait(p_full + w, u & 1);
@@ -657,7 +678,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         for (int k = 0; k < 4; ++k)           // dQ += dS K      (K = 64 keys)
           umma_bf16(tDQ, desc_kmajor(aDS + w * T16K, k), desc_mnmajor(aK + st * T8K, k), idesc_g, (j > 0 || k > 0));
         umma_commit(kv_empty + st);
-        if (j + 2 < nkv) issue_scores(j + 2);
+        umma_commit(pbuf_free + w);
+        if (j + NSB < nkv) issue_scores(j + NSB);
       }
       umma_commit(acc_full);
     }
@@ -668,20 +690,22 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const int t = q0 + row;
     const bool row_ok = t < p.T;
-    const float lse2 = row_ok ? p.lse[((size_t)b * p.H + h) * p.T + t] * LOG2E : 0.f;
-    const float dsum = row_ok ? p.dvec[((size_t)b * p.H + h) * p.T + t] : 0.f;
+    const float lse2 = t < Tp ? p.lse2[((size_t)b * p.H + h) * Tp + t] : 0.f;
+    const float dsum = t < Tp ? p.dvec[((size_t)b * p.H + h) * Tp + t] : 0.f;
     uint8_t *myDS = sDS + w * T16K;
     int u = 0;
     for (int j = w; j < nkv; j += 2, ++u) {
-      mbar_wait(s_full + w, u & 1);
+      const int sb = j % NSB;
+      mbar_wait(s_full + sb, (j / NSB) & 1);
       tc_fence_after();
+      if (u > 0) mbar_wait(pbuf_free + w, (u - 1) & 1);
       // No masking: key columns >= T multiply zero K rows in dQ += dS K; query rows >= T only
       // pollute their own (never stored) dQ rows.
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         float sv[32], dp[32];
-        tmem_ld32_issue(tS + lane_addr + w * HALF + c * 32, sv);
-        tmem_ld32_issue(tDP + lane_addr + w * HALF + c * 32, dp);
+        tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + c * 32, sv);
+        tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + HALF + c * 32, dp);
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 32; ++q) dp[q] = fast_exp2(fmaf(sv[q], p.scale_log2, -lse2)) * (dp[q] - dsum);
@@ -691,7 +715,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive(s_empty + w);
+        mbar_arrive(s_empty + sb);
         mbar_arrive(p_full + w);
       }
     }
@@ -753,9 +777,11 @@ int attention_tc_forward(const void *qkv, void *out, float *lse, int B, int T, i
   return ASIS_OK;
 }
 
+static int padded_T(int T) { return (T + HALF - 1) / HALF * HALF; }
+
 size_t attention_tc_bwd_ws(int B, int T, int H, int hd) {
   (void)hd;
-  return align_up((size_t)B * H * T * sizeof(float), 256);
+  return 2 * align_up((size_t)B * H * padded_T(T) * sizeof(float), 256);
 }
 
 int attention_tc_backward(const void *qkv, const void *out, const float *lse, const void *dout, void *dqkv, int B,
@@ -774,11 +800,13 @@ int attention_tc_backward(const void *qkv, const void *out, const float *lse, co
     if (int rc = set_smem((const void *)attn_bwd_dq_kernel, BWD_SMEM)) return rc;
     configured = true;
   }
+  const int Tp = padded_T(T);
   float *dvec = (float *)ws;
+  float *lse2 = (float *)((char *)ws + align_up((size_t)B * H * Tp * sizeof(float), 256));
   {
-    const size_t groups = (size_t)B * T * H;
+    const size_t groups = (size_t)B * Tp * H;
     const unsigned blocks = (unsigned)((groups * 8 + 255) / 256);
-    attn_bwd_prep_kernel<<<blocks, 256, 0, st>>>((const bf16 *)out, (const bf16 *)dout, dvec, B, T, H);
+    attn_bwd_prep_kernel<<<blocks, 256, 0, st>>>((const bf16 *)out, (const bf16 *)dout, lse, dvec, lse2, B, T, Tp, H);
     ASIS_LAUNCHED();
   }
   AttnParams p{};
@@ -787,6 +815,7 @@ int attention_tc_backward(const void *qkv, const void *out, const float *lse, co
   p.scale_log2 = p.scale * LOG2E;
   p.lse = const_cast<float *>(lse);
   p.dvec = dvec;
+  p.lse2 = lse2;
   p.dqkv = (bf16 *)dqkv;
   dim3 grid((T + TILE - 1) / TILE, H, B);
   attn_bwd_dkdv_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(tq128, tq64, tdo64, p);

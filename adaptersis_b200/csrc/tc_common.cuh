@@ -70,6 +70,13 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap *m, uint64_t *bar,
       : "memory");
 }
 
+// plain 1-D bulk copy global -> shared (16-byte aligned, size multiple of 16), completes on `bar`
+__device__ __forceinline__ void bulk_load_1d(uint64_t *bar, void *dst, const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // multicast: the box lands at the same CTA-relative smem offset in every CTA of `mask`, and each
 // destination CTA's mbarrier (same offset) receives the complete_tx
 __device__ __forceinline__ void tma_load_2d_mc(const CUtensorMap *m, uint64_t *bar, void *dst, int c0, int c1, uint16_t mask) {
