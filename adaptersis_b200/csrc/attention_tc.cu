@@ -26,7 +26,8 @@ namespace asis {
 
 using namespace tc;
 
-constexpr int ATT_THREADS = 320;      // TMA warp, MMA warp, 2 x 4 softmax warps
+constexpr int ATT_THREADS = 320;      // forward: TMA warp, MMA warp, 2 x 4 softmax warps
+constexpr int BWD_THREADS = 576;      // backward: TMA warp, MMA warp, 2 x 8 softmax warps (two threads per row)
 constexpr int TILE = 128;      // query / key rows per tile
 constexpr int HD = 64;
 constexpr int T16K = TILE * HD * 2;           // one 128 x 64 bf16 tile
@@ -64,6 +65,19 @@ __device__ __forceinline__ void store_row32_sw128(uint8_t *tile, int row, int co
 __device__ __forceinline__ void store_out64(bf16 *dst, const float (&o)[64], float scale) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(o[8 * c + 2 * i] * scale, o[8 * c + 2 * i + 1] * scale);
+      w[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    reinterpret_cast<uint4 *>(dst)[c] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__device__ __forceinline__ void store_out32(bf16 *dst, const float (&o)[32], float scale) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -406,7 +420,7 @@ constexpr int BWD_STAGES = 4;
 constexpr int BWD_SMEM = 2 * T16K /*resident pair*/ + BWD_STAGES * 2 * T8K /*streamed pair*/ + 2 * 2 * T16K /*2 bufs x 2 WGs*/ +
                          BWD_STAGES * 2 * HALF * 4 /*lse, D tiles*/ + 1024 + 256;
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_constant__ CUtensorMap tmQ,
                      const __grid_constant__ CUtensorMap tmDO, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -441,10 +455,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
     }
     for (int i = 0; i < NSB; ++i) {
       mbar_init(s_full + i, 1);
-      mbar_init(s_empty + i, 4);
+      mbar_init(s_empty + i, 8);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(p_full + i, 4);
+      mbar_init(p_full + i, 8);
       mbar_init(pbuf_free + i, 1);
     }
     mbar_init(acc_full, 1);
@@ -513,7 +527,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
       umma_commit(acc_full);
     }
   } else {
-    const int w = (warp - 2) >> 2;
+    // 8 warps per warpgroup: two threads per key row, each owns 32 of the tile's 64 query columns
+    const int w = (warp - 2) >> 3;
+    const int c = ((warp - 2) >> 2) & 1;     // column half
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;     // key row inside the tile
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -529,8 +545,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
       // No masking is needed here: query columns >= T have zero Q / dO rows (TMA zero fill) and
       // lse = D = 0, so their P^T multiplies zero dO rows and their dS^T is exactly 0; key rows >= T
       // only pollute their own (never stored) dV / dK rows.
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
         float st_[32], dp[32];
         tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + c * 32, st_);
         tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + HALF + c * 32, dp);
@@ -561,22 +576,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    // warpgroup 0 writes dV, warpgroup 1 writes dK
+    // warpgroup 0 writes dV, warpgroup 1 writes dK; each thread 32 of the 64 columns
     const int t = k0 + row;
-    float acc[64];
-    {
-      float v0[32], v1[32];
-      tmem_ld32_issue((w == 0 ? tDV : tDK) + lane_addr, v0);
-      tmem_ld32_issue((w == 0 ? tDV : tDK) + lane_addr + 32, v1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 32; ++q) {
-        acc[q] = v0[q];
-        acc[32 + q] = v1[q];
-      }
-    }
+    float v[32];
+    tmem_ld32((w == 0 ? tDV : tDK) + lane_addr + c * 32, v);
     if (t < p.T)
-      store_out64(p.dqkv + ((size_t)b * p.T + t) * 3 * C + (w == 0 ? 2 * C : C) + h * HD, acc, w == 0 ? 1.f : p.scale);
+      store_out32(p.dqkv + ((size_t)b * p.T + t) * 3 * C + (w == 0 ? 2 * C : C) + h * HD + c * 32, v, w == 0 ? 1.f : p.scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -589,7 +594,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // backward, dQ: one CTA per (128-query block, head, image); loops over 64-key tiles
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmDO,
                    const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -621,10 +626,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (int i = 0; i < NSB; ++i) {
       mbar_init(s_full + i, 1);
-      mbar_init(s_empty + i, 4);
+      mbar_init(s_empty + i, 8);
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(p_full + i, 4);
+      mbar_init(p_full + i, 8);
       mbar_init(pbuf_free + i, 1);
     }
     mbar_init(acc_full, 1);
@@ -684,7 +689,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       umma_commit(acc_full);
     }
   } else {
-    const int w = (warp - 2) >> 2;
+    const int w = (warp - 2) >> 3;
+    const int c = ((warp - 2) >> 2) & 1;     // column half
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -701,8 +707,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (u > 0) mbar_wait(pbuf_free + w, (u - 1) & 1);
       // No masking: key columns >= T multiply zero K rows in dQ += dS K; query rows >= T only
       // pollute their own (never stored) dQ rows.
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
         float sv[32], dp[32];
         tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + c * 32, sv);
         tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + HALF + c * 32, dp);
@@ -721,21 +726,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    // each warpgroup writes 32 of the 64 dQ columns
-    float v[32];
-    tmem_ld32(tDQ + lane_addr + w * 32, v);
-    if (row_ok) {
-      bf16 *dst = p.dqkv + ((size_t)b * p.T + t) * 3 * C + h * HD + w * 32;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          __nv_bfloat162 hh = __floats2bfloat162_rn(v[8 * c + 2 * i] * p.scale, v[8 * c + 2 * i + 1] * p.scale);
-          pk[i] = *reinterpret_cast<uint32_t *>(&hh);
-        }
-        reinterpret_cast<uint4 *>(dst)[c] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-      }
+    // the column-half-0 warps of each warpgroup write 32 of the 64 dQ columns
+    if (c == 0) {
+      float v[32];
+      tmem_ld32(tDQ + lane_addr + w * 32, v);
+      if (row_ok) store_out32(p.dqkv + ((size_t)b * p.T + t) * 3 * C + h * HD + w * 32, v, p.scale);
     }
   }
   tc_fence_before();
@@ -818,9 +813,9 @@ int attention_tc_backward(const void *qkv, const void *out, const float *lse, co
   p.lse2 = lse2;
   p.dqkv = (bf16 *)dqkv;
   dim3 grid((T + TILE - 1) / TILE, H, B);
-  attn_bwd_dkdv_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(tq128, tq64, tdo64, p);
+  attn_bwd_dkdv_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tq128, tq64, tdo64, p);
   ASIS_LAUNCHED();
-  attn_bwd_dq_kernel<<<grid, ATT_THREADS, BWD_SMEM, st>>>(tq128, tdo128, tq64, p);
+  attn_bwd_dq_kernel<<<grid, BWD_THREADS, BWD_SMEM, st>>>(tq128, tdo128, tq64, p);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }
