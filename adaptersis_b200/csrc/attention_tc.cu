@@ -180,20 +180,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tO = tmem + NSB * TILE;     // S[b] at b*128 (b < 3), O[w] at 384 + w*64
 
+  // The TMA and MMA roles run warp-uniformly (every lane executes the loops and the barrier waits;
+  // only the TMA / tcgen05 instructions sit under elect_one): operands then live in uniform registers
+  // and the MMAs issue back to back instead of through per-instruction R2UR waterfall loops.
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, T16K);
       tma_load_3d(&tmQKV, q_full, sQ, h * HD, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j % FWD_STAGES, use = j / FWD_STAGES;
-        if (use > 0) mbar_wait(kv_empty + st, (use - 1) & 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j % FWD_STAGES, use = j / FWD_STAGES;
+      if (use > 0) mbar_wait(kv_empty + st, (use - 1) & 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(kv_full + st, 2 * T16K);
         tma_load_3d(&tmQKV, kv_full + st, sK + st * T16K, C + h * HD, j * TILE, b);
         tma_load_3d(&tmQKV, kv_full + st, sV + st * T16K, 2 * C + h * HD, j * TILE, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = make_idesc(TILE, TILE, 0, 0);   // S = Q K^T : both K-major
       constexpr uint32_t idesc_o = make_idesc(TILE, HD, 0, 1);     // O = P V   : V is MN-major
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
@@ -206,10 +213,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         mbar_wait(kv_full + st, (j / FWD_STAGES) & 1);
         if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tS + sb * TILE, desc_kmajor(aQ, k), desc_kmajor(aK + st * T16K, k), idesc_s, k > 0);
-        umma_commit(s_full + sb);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tS + sb * TILE, desc_kmajor(aQ, k), desc_kmajor(aK + st * T16K, k), idesc_s, k > 0);
+          umma_commit(s_full + sb);
+        }
+        __syncwarp();
       };
       for (int j = 0; j < NSB && j < nkv; ++j) issue_s(j);
       for (int j = 0; j < nkv; ++j) {
@@ -217,11 +227,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         mbar_wait(p_full + w, u & 1);
         if (u > 0) mbar_wait(o_empty + w, (u - 1) & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tO + w * HD, desc_kmajor(aP + w * T32K, k), desc_mnmajor(aV + st * T16K, k), idesc_o, k > 0);
-        umma_commit(o_full + w);
-        umma_commit(kv_empty + st);
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tO + w * HD, desc_kmajor(aP + w * T32K, k), desc_mnmajor(aV + st * T16K, k), idesc_o, k > 0);
+          umma_commit(o_full + w);
+          umma_commit(kv_empty + st);
+        }
+        __syncwarp();
         if (j + NSB < nkv) issue_s(j + NSB);
       }
     }
@@ -473,24 +486,28 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
   const uint32_t tSC = tmem, tDV = tmem + NSB * 2 * HALF, tDK = tDV + HD;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const float *lse_b = p.lse2 + ((size_t)b * p.H + h) * Tp;
-      const float *d_b = p.dvec + ((size_t)b * p.H + h) * Tp;
+    const float *lse_b = p.lse2 + ((size_t)b * p.H + h) * Tp;
+    const float *d_b = p.dvec + ((size_t)b * p.H + h) * Tp;
+    if (elect_one()) {
       mbar_arrive_expect_tx(kv_full, 2 * T16K);
       tma_load_3d(&tmKV, kv_full, sK, C + h * HD, k0, b);
       tma_load_3d(&tmKV, kv_full, sV, 2 * C + h * HD, k0, b);
-      for (int i = 0; i < nq; ++i) {
-        const int st = i % BWD_STAGES, use = i / BWD_STAGES;
-        if (use > 0) mbar_wait(q_empty + st, (use - 1) & 1);
+    }
+    __syncwarp();
+    for (int i = 0; i < nq; ++i) {
+      const int st = i % BWD_STAGES, use = i / BWD_STAGES;
+      if (use > 0) mbar_wait(q_empty + st, (use - 1) & 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(q_full + st, 2 * T8K + 2 * HALF * 4);
         tma_load_3d(&tmQ, q_full + st, sQ + st * T8K, h * HD, i * HALF, b);
         tma_load_3d(&tmDO, q_full + st, sDO + st * T8K, h * HD, i * HALF, b);
         bulk_load_1d(q_full + st, sLse + st * HALF, lse_b + i * HALF, HALF * 4);
         bulk_load_1d(q_full + st, sD + st * HALF, d_b + i * HALF, HALF * 4);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = make_idesc(TILE, HALF, 0, 0);   // [128 keys] x [64 queries]
       constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);     // [128 keys] x [64 hd], B MN-major
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO),
@@ -501,30 +518,36 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
         mbar_wait(q_full + st, (i / BWD_STAGES) & 1);
         if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tSC + sb * 2 * HALF, desc_kmajor(aK, k), desc_kmajor(aQ + st * T8K, k), idesc_s, k > 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tSC + sb * 2 * HALF, desc_kmajor(aK, k), desc_kmajor(aQ + st * T8K, k), idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tSC + sb * 2 * HALF + HALF, desc_kmajor(aV, k), desc_kmajor(aDO + st * T8K, k), idesc_s, k > 0);
-        umma_commit(s_full + sb);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tSC + sb * 2 * HALF + HALF, desc_kmajor(aV, k), desc_kmajor(aDO + st * T8K, k), idesc_s, k > 0);
+          umma_commit(s_full + sb);
+        }
+        __syncwarp();
       };
       for (int i = 0; i < NSB && i < nq; ++i) issue_scores(i);
       for (int i = 0; i < nq; ++i) {
         const int w = i & 1, u = i >> 1, st = i % BWD_STAGES;
         mbar_wait(p_full + w, u & 1);         // P^T and dS^T of tile i are in smem
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)           // dV += P^T dO      (K = 64 queries)
-          umma_bf16(tDV, desc_kmajor(aPT + w * T16K, k), desc_mnmajor(aDO + st * T8K, k), idesc_g, (i > 0 || k > 0));
+          for (int k = 0; k < 4; ++k)         // dV += P^T dO      (K = 64 queries)
+            umma_bf16(tDV, desc_kmajor(aPT + w * T16K, k), desc_mnmajor(aDO + st * T8K, k), idesc_g, (i > 0 || k > 0));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)           // dK += dS^T Q
-          umma_bf16(tDK, desc_kmajor(aDST + w * T16K, k), desc_mnmajor(aQ + st * T8K, k), idesc_g, (i > 0 || k > 0));
-        umma_commit(q_empty + st);            // the Q/dO/lse/D stage may be refilled
-        umma_commit(pbuf_free + w);           // warpgroup w may overwrite its P^T / dS^T buffers
+          for (int k = 0; k < 4; ++k)         // dK += dS^T Q
+            umma_bf16(tDK, desc_kmajor(aDST + w * T16K, k), desc_mnmajor(aQ + st * T8K, k), idesc_g, (i > 0 || k > 0));
+          umma_commit(q_empty + st);          // the Q/dO/lse/D stage may be refilled
+          umma_commit(pbuf_free + w);         // warpgroup w may overwrite its P^T / dS^T buffers
+          if (i == nq - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
         if (i + NSB < nq) issue_scores(i + NSB);
       }
-      umma_commit(acc_full);
     }
   } else {
     // 8 warps per warpgroup: two threads per key row, each owns 32 of the tile's 64 query columns
@@ -643,20 +666,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t tSC = tmem, tDQ = tmem + NSB * 2 * HALF;   // S at sb*128, dP at sb*128 + 64; dQ at 384
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * T16K);
       tma_load_3d(&tmQ, q_full, sQ, h * HD, q0, b);
       tma_load_3d(&tmDO, q_full, sDO, h * HD, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j % BWD_STAGES, use = j / BWD_STAGES;
-        if (use > 0) mbar_wait(kv_empty + st, (use - 1) & 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkv; ++j) {
+      const int st = j % BWD_STAGES, use = j / BWD_STAGES;
+      if (use > 0) mbar_wait(kv_empty + st, (use - 1) & 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(kv_full + st, 2 * T8K);
         tma_load_3d(&tmKV, kv_full + st, sK + st * T8K, C + h * HD, j * HALF, b);
         tma_load_3d(&tmKV, kv_full + st, sV + st * T8K, 2 * C + h * HD, j * HALF, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = make_idesc(TILE, HALF, 0, 0);
       constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);
       const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sDS);
@@ -666,27 +693,33 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(kv_full + st, (j / BWD_STAGES) & 1);
         if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tSC + sb * 2 * HALF, desc_kmajor(aQ, k), desc_kmajor(aK + st * T8K, k), idesc_s, k > 0);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tSC + sb * 2 * HALF, desc_kmajor(aQ, k), desc_kmajor(aK + st * T8K, k), idesc_s, k > 0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tSC + sb * 2 * HALF + HALF, desc_kmajor(aDO, k), desc_kmajor(aV + st * T8K, k), idesc_s, k > 0);
-        umma_commit(s_full + sb);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tSC + sb * 2 * HALF + HALF, desc_kmajor(aDO, k), desc_kmajor(aV + st * T8K, k), idesc_s, k > 0);
+          umma_commit(s_full + sb);
+        }
+        __syncwarp();
       };
       for (int j = 0; j < NSB && j < nkv; ++j) issue_scores(j);
       for (int j = 0; j < nkv; ++j) {
         const int w = j & 1, u = j >> 1, st = j % BWD_STAGES;
         mbar_wait(p_full + w, u & 1);
         tc_fence_after();
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)           // dQ += dS K      (K = 64 keys)
-          umma_bf16(tDQ, desc_kmajor(aDS + w * T16K, k), desc_mnmajor(aK + st * T8K, k), idesc_g, (j > 0 || k > 0));
-        umma_commit(kv_empty + st);
-        umma_commit(pbuf_free + w);
+          for (int k = 0; k < 4; ++k)         // dQ += dS K      (K = 64 keys)
+            umma_bf16(tDQ, desc_kmajor(aDS + w * T16K, k), desc_mnmajor(aK + st * T8K, k), idesc_g, (j > 0 || k > 0));
+          umma_commit(kv_empty + st);
+          umma_commit(pbuf_free + w);
+          if (j == nkv - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
         if (j + NSB < nkv) issue_scores(j + NSB);
       }
-      umma_commit(acc_full);
     }
   } else {
     const int w = (warp - 2) >> 3;

@@ -191,19 +191,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int total_tiles = p.m_groups * p.n_tiles * p.splits;   // per cluster: CL adjacent m-tiles at once
 
+  // Producer and MMA roles run WARP-UNIFORMLY (all 32 lanes execute the loops and the barrier waits;
+  // only the TMA / tcgen05 instructions themselves sit under elect_one).  With the whole role under
+  // `if (lane == 0)` the loop state lives in per-thread registers and every TMA / MMA operand has
+  // to be moved to uniform registers through an ELECT / R2UR.BROADCAST waterfall loop: the MMA
+  // thread then needs ~100 issue cycles per 128-cycle MMA and the tensor pipe starves.
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int m_blk = (tile % p.m_groups) * CL + crank;
-        const int rest = tile / p.m_groups;
-        const int n_blk = rest % p.n_tiles;
-        const int split = rest / p.n_tiles;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar + stage, phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m_blk = (tile % p.m_groups) * CL + crank;
+      const int rest = tile / p.m_groups;
+      const int n_blk = rest % p.n_tiles;
+      const int split = rest / p.n_tiles;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        if (elect_one()) {
           uint8_t *sa = smem + stage * STAGE_BYTES;
           uint8_t *sb = sa + A_BYTES;
           mbar_arrive_expect_tx(full_bar + stage, STAGE_BYTES);   // own A + the CL slices of B
@@ -234,52 +239,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                n_blk * BN + crank * ROWS + j * 64, kb * BK, kMask);
             }
           }
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int split = (tile / p.m_groups) / p.n_tiles;
-        const int kb0 = split * p.kb_per_split;
-        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+    constexpr uint32_t idesc = make_idesc(BM, BN, A_MN, B_MN);
+    // descriptor = constant part | (smem address >> 4); K-major: +32 B per 16-element k-step inside the
+    // 128 B swizzle row, MN-major: +2 groups of 8 k-rows (2048 B)
+    const uint64_t da0 = A_MN == 0 ? smem_desc(0, 16, 1024) : smem_desc(0, BOX_BYTES, 1024);
+    const uint64_t db0 = B_MN == 0 ? smem_desc(0, 16, 1024) : smem_desc(0, BOX_BYTES, 1024);
+    constexpr uint32_t a_step = (A_MN == 0 ? 32 : 2048) >> 4, b_step = (B_MN == 0 ? 32 : 2048) >> 4;
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int split = (tile / p.m_groups) / p.n_tiles;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + stage, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar + stage, phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+        if (elect_one()) {
+          const uint32_t sa = (smem_base + stage * STAGE_BYTES) >> 4;
+          const uint32_t sb = sa + (A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: +32 B per 16 k inside the 128 B swizzle row.  MN-major: +2 groups of 8 k-rows.
-            const uint64_t da = A_MN == 0 ? smem_desc(sa + k * 32, 16, 1024) : smem_desc(sa + k * 2048, BOX_BYTES, 1024);
-            const uint64_t db = B_MN == 0 ? smem_desc(sb + k * 32, 16, 1024) : smem_desc(sb + k * 2048, BOX_BYTES, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(d_tmem, da0 + (sa + k * a_step), db0 + (sb + k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           // frees the smem stage (in every CTA of the cluster) when the MMAs above have read it
           if (CL == 1) umma_commit(empty_bar + stage);
           else umma_commit_mc(empty_bar + stage, kMask);
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
+          if (kb == kb1 - 1) umma_commit(tfull_bar + acc);  // accumulator complete
         }
-        umma_commit(tfull_bar + acc);  // accumulator complete
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else {
