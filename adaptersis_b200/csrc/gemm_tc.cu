@@ -208,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
-        if (elect_one()) {
+        if (lane == 0) {
           uint8_t *sa = smem + stage * STAGE_BYTES;
           uint8_t *sb = sa + A_BYTES;
           mbar_arrive_expect_tx(full_bar + stage, STAGE_BYTES);   // own A + the CL slices of B
@@ -270,11 +270,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(full_bar + stage, phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = (smem_base + stage * STAGE_BYTES) >> 4;
-          const uint32_t sb = sa + (A_BYTES >> 4);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(d_tmem, da0 + (sa + k * a_step), db0 + (sb + k * b_step), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = A_MN == 0 ? smem_desc(sa + k * 32, 16, 1024) : smem_desc(sa + k * 2048, BOX_BYTES, 1024);
+            const uint64_t db = B_MN == 0 ? smem_desc(sb + k * 32, 16, 1024) : smem_desc(sb + k * 2048, BOX_BYTES, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           // frees the smem stage (in every CTA of the cluster) when the MMAs above have read it
           if (CL == 1) umma_commit(empty_bar + stage);
           else umma_commit_mc(empty_bar + stage, kMask);
