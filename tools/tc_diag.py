@@ -128,6 +128,12 @@ def perf():
     bias = torch.randn(4096, device=dev)
     ms = timeit(lambda: K.gemm(BF16, A, MAJOR_K, W1, MAJOR_K, R, 4096, 1024, torch.bfloat16, epilogue=EPI_GELU, bias=bias, want_aux_dtype=torch.bfloat16))
     print(f"gemm fc1+bias+GELU(+aux): {ms * 1e3:8.1f} us  {2.0 * R * 4096 * 1024 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    ms = timeit(lambda: K.gemm(BF16, A, MAJOR_K, W1, MAJOR_K, R, 4096, 1024, torch.bfloat16, epilogue=EPI_GELU, bias=bias))
+    print(f"gemm fc1+bias+GELU (no aux): {ms * 1e3:8.1f} us  {2.0 * R * 4096 * 1024 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    ms = timeit(lambda: K.gemm(BF16, A, MAJOR_K, W1, MAJOR_K, R, 4096, 1024, torch.float32))
+    print(f"gemm fc1 plain, fp32 out (2x store bytes): {ms * 1e3:8.1f} us  {2.0 * R * 4096 * 1024 / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    ms = timeit(lambda: K.gemm(BF16, A, MAJOR_K, W1, MAJOR_K, R, 4096, 1024, torch.bfloat16, bias=bias))
+    print(f"gemm fc1+bias: {ms * 1e3:8.1f} us  {2.0 * R * 4096 * 1024 / ms / 1e9:7.1f} TFLOP/s", flush=True)
     G = torch.randn(R, 4096, device=dev).bfloat16()
     W2 = torch.randn(1024, 4096, device=dev).bfloat16()
     res = torch.randn(R, 1024, device=dev)
