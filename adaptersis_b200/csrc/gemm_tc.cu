@@ -4,8 +4,9 @@
 //   warp 0      TMA producer   cp.async.bulk.tensor -> 128B-swizzled smem ring (4 stages x 48 KB)
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::f16, 128 x 256 x 16 per instruction,
 //                              fp32 accumulators in TMEM (2 x 256 columns, double buffered)
-//   warps 2..9  epilogue       tcgen05.ld -> registers -> fused epilogue (bias / exact GELU /
-//                              LayerScale + residual / GELU' / accumulate) -> 16-byte global stores
+//   warps 2..9  epilogue       tcgen05.ld -> registers -> per-warp smem transposition -> fused epilogue
+//                              (bias / exact GELU / LayerScale + residual / GELU' / accumulate) with
+//                              row-contiguous (coalesced) global loads and stores
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue).
 // Thread-block clusters of CL CTAs along M share the B tile: each CTA fetches 1/CL of it and TMA
 // multicasts the slice into every CTA of the cluster (a 128x256 tile per CTA alone needs
@@ -32,7 +33,8 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int BOX_BYTES = 64 * BK * 2;         // one 64 x 64 MN-major TMA box: 8 KB
 constexpr int NUM_EPI_WARPS = 8;   // (16 epilogue warps measured slower: 96-register cap, spills)
 constexpr int GEMM_THREADS = 64 + NUM_EPI_WARPS * 32;
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = NUM_EPI_WARPS * 32 * 32 * 4;   // 4 KB transposition buffer per epilogue warp
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct GemmTcParams {
   int M, N, K;
@@ -41,115 +43,117 @@ struct GemmTcParams {
   EpiArgs epi;
 };
 
-__device__ __forceinline__ void load8f(const float *p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4 *>(p);
-  const float4 b = *reinterpret_cast<const float4 *>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void load8(const void *base, int dtype, size_t idx, float (&v)[8]) {
+// ---- epilogue -------------------------------------------------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (TMEM lane); storing from that layout makes each
+// warp store touch 32 different rows with 16 bytes each (32 partial-sector requests per instruction:
+// the first version's epilogue was bound by exactly that -- an fp32 output or a second (aux) output
+// cost as much as the whole MMA main loop).  So every epilogue warp transposes its 32 x 32 fp32 chunk
+// through a private, XOR-swizzled 4 KB smem buffer and then works in a COALESCED layout: lane ->
+// (row it*4 + lane/8, 4 columns (lane%8)*4..+3), i.e. 128 contiguous bytes (fp32) / 64 (bf16) per row
+// for every global load (residual, aux, C) and store (C, aux).
+constexpr int EPI_STAGE_FLOATS = 32 * 32;   // per warp
+
+__device__ __forceinline__ void load4_any(const void *base, int dtype, size_t idx, float (&v)[4]) {
   if (dtype == ASIS_F32) {
-    load8f(reinterpret_cast<const float *>(base) + idx, v);
+    const float4 t = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(base) + idx);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   } else {
-    const uint4 t = *reinterpret_cast<const uint4 *>(reinterpret_cast<const bf16 *>(base) + idx);
-    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162 *>(&w[i]);
-      v[2 * i] = __low2float(h);
-      v[2 * i + 1] = __high2float(h);
-    }
+    const uint2 t = *reinterpret_cast<const uint2 *>(reinterpret_cast<const bf16 *>(base) + idx);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&t.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162 *>(&t.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
   }
 }
-__device__ __forceinline__ void store8(void *base, int dtype, size_t idx, const float (&v)[8]) {
-  if (dtype == ASIS_F32) {
-    float *p = reinterpret_cast<float *>(base) + idx;
-    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  } else {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t *>(&h);
-    }
-    *reinterpret_cast<uint4 *>(reinterpret_cast<bf16 *>(base) + idx) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
+__device__ __forceinline__ void store4_any(void *base, int dtype, size_t idx, const float (&v)[4]) {
+  if (dtype == ASIS_F32) store4(reinterpret_cast<float *>(base) + idx, v);
+  else store4(reinterpret_cast<bf16 *>(base) + idx, v);
 }
 
-// epilogue for 32 consecutive columns of one row; KIND is a compile-time constant so that the
-// accumulator array is only ever indexed with constants (it must stay in registers)
+// the 4-column group of one row in the coalesced layout; KIND is a compile-time constant
 template <int KIND>
-__device__ __forceinline__ void epi_row32(const GemmTcParams &p, int row, int col0, const float (&acc)[32], bool vec_ok) {
+__device__ __forceinline__ void epi_group4(const GemmTcParams &p, int row, int col, float (&v)[4], const float (&b4)[4],
+                                           const float (&g4)[4], bool vec_ok) {
   const EpiArgs &e = p.epi;
-  if (row >= p.M || col0 >= p.N) return;
-  if (!vec_ok || col0 + 32 > p.N) {
+  if (!vec_ok || col + 4 > p.N) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (col0 + j < p.N) {
-        if (p.atomic_out)
-          atomicAdd(reinterpret_cast<float *>(e.C) + (size_t)row * e.ldc + col0 + j, acc[j]);
-        else
-          epi_scalar(e, row, col0 + j, acc[j]);
+    for (int j = 0; j < 4; ++j) {
+      if (col + j < p.N) {
+        if (p.atomic_out) atomicAdd(reinterpret_cast<float *>(e.C) + (size_t)row * e.ldc + col + j, v[j]);
+        else epi_scalar(e, row, col + j, v[j]);
       }
     }
     return;
   }
-  const size_t ci = (size_t)row * e.ldc + col0;
-  const size_t ai = (size_t)row * e.ldaux + col0;
+  const size_t ci = (size_t)row * e.ldc + col;
+  const size_t ai = (size_t)row * e.ldaux + col;
   if (p.atomic_out) {
-    float *c = reinterpret_cast<float *>(e.C) + ci;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) atomicAdd(c + i, acc[i]);
+    atomicAdd(reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.C) + ci), make_float4(v[0], v[1], v[2], v[3]));
     return;
   }
+  if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    float v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = acc[8 * g + i];
-    if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE && e.bias) {
-      float b[8];
-      load8f(e.bias + col0 + 8 * g, b);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += b[i];
-    }
-    if (KIND == ASIS_EPI_GELU) {
-      if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i]);
-    } else if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
-      if (e.aux) store8(e.aux, e.aux_dtype, ai + 8 * g, v);
-      float r[8], gm[8];
-      load8f(e.residual + ci + 8 * g, r);
-      load8f(e.gamma + col0 + 8 * g, gm);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = r[i] + gm[i] * v[i];
-    } else if (KIND == ASIS_EPI_DGELU) {
-      float h[8];
-      load8(e.aux, e.aux_dtype, ai + 8 * g, h);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] *= dgelu_fast(h[i]);
-    } else if (KIND == ASIS_EPI_ACCUMULATE) {
-      float c[8];
-      load8f(reinterpret_cast<const float *>(e.C) + ci + 8 * g, c);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += c[i];
-    }
-    store8(e.C, e.c_dtype, ci + 8 * g, v);
+    for (int i = 0; i < 4; ++i) v[i] += b4[i];
   }
+  if (KIND == ASIS_EPI_GELU) {
+    if (e.aux) store4_any(e.aux, e.aux_dtype, ai, v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = gelu_fast(v[i]);
+  } else if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
+    if (e.aux) store4_any(e.aux, e.aux_dtype, ai, v);
+    float r[4];
+    load4_any(e.residual, ASIS_F32, ci, r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = fmaf(g4[i], v[i], r[i]);
+  } else if (KIND == ASIS_EPI_DGELU) {
+    float h[4];
+    load4_any(e.aux, e.aux_dtype, ai, h);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= dgelu_fast(h[i]);
+  } else if (KIND == ASIS_EPI_ACCUMULATE) {
+    float c[4];
+    load4_any(e.C, ASIS_F32, ci, c);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] += c[i];
+  }
+  store4_any(e.C, e.c_dtype, ci, v);
 }
 
-// the epilogue of one 32-row x 128-column slab: TMEM loads issued two at a time
+// the epilogue of one 32-row x 128-column slab owned by one warp
 template <int KIND>
-__device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, int row, int col_base, bool vec_ok) {
-#pragma unroll
-  for (int c = 0; c < 4; c += 2) {
-    float v0[32], v1[32];
-    tmem_ld32_issue(taddr + c * 32, v0);
-    tmem_ld32_issue(taddr + c * 32 + 32, v1);
+__device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, float *stage, int row0, int col_base,
+                                         bool vec_ok, int lane) {
+  const EpiArgs &e = p.epi;
+  const int cg = lane & 7, r = lane >> 3;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    float v[32];
+    tmem_ld32_issue(taddr + c * 32, v);
     tmem_ld_wait();
-    epi_row32<KIND>(p, row, col_base + c * 32, v0, vec_ok);
-    epi_row32<KIND>(p, row, col_base + c * 32 + 32, v1, vec_ok);
+    // thread = row  ->  smem, 16-byte groups XOR-swizzled by the row (conflict-free both ways)
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      *reinterpret_cast<float4 *>(stage + lane * 32 + ((g ^ (lane & 7)) << 2)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+    __syncwarp();
+    const int col = col_base + c * 32 + cg * 4;
+    if (col < p.N) {
+      float b4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE && e.bias) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) b4[i] = (col + i < p.N) ? __ldg(e.bias + col + i) : 0.f;
+      }
+      if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) g4[i] = (col + i < p.N) ? __ldg(e.gamma + col + i) : 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rl = it * 4 + r;
+        const float4 t = *reinterpret_cast<const float4 *>(stage + rl * 32 + ((cg ^ (rl & 7)) << 2));
+        float w[4] = {t.x, t.y, t.z, t.w};
+        if (row0 + rl < p.M) epi_group4<KIND>(p, row0 + rl, col, w, b4, g4, vec_ok);
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -158,7 +162,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  float *epi_stage = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *tfull_bar = empty_bar + STAGES;
   uint64_t *tempty_bar = tfull_bar + 2;
@@ -300,21 +305,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = ew >> 2;          // column half: [half*128, half*128+128)
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool vec_ok = (p.epi.ldc % 8 == 0) && (!p.epi.aux || p.epi.ldaux % 8 == 0);
+    const bool vec_ok = (p.epi.ldc % 4 == 0) && (!p.epi.aux || p.epi.ldaux % 4 == 0);
+    float *stage = epi_stage + ew * EPI_STAGE_FLOATS;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_blk = (tile % p.m_groups) * CL + crank;
       const int n_blk = (tile / p.m_groups) % p.n_tiles;
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
+      const int row0 = m_blk * BM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
       const int col_base = n_blk * BN + half * 128;
       switch (p.epi.kind) {
-        case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, row, col_base, vec_ok); break;
-        case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, row, col_base, vec_ok); break;
-        case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, row, col_base, vec_ok); break;
-        case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, row, col_base, vec_ok); break;
-        default: epi_slab<ASIS_EPI_NONE>(p, taddr, row, col_base, vec_ok); break;
+        case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
+        case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
+        case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
+        case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
+        default: epi_slab<ASIS_EPI_NONE>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
       }
       tc_fence_before();
       __syncwarp();
