@@ -69,10 +69,31 @@ __device__ __forceinline__ void store4_any(void *base, int dtype, size_t idx, co
   else store4(reinterpret_cast<bf16 *>(base) + idx, v);
 }
 
-// the 4-column group of one row in the coalesced layout; KIND is a compile-time constant
+// raw 16-byte (fp32 x4) or 8-byte (bf16 x4) global load kept undecoded, so that nothing depends on
+// the load until the values are used one chunk later
+__device__ __forceinline__ uint4 ldraw4(const void *base, int dtype, size_t idx) {
+  if (dtype == ASIS_F32) return *reinterpret_cast<const uint4 *>(reinterpret_cast<const float *>(base) + idx);
+  const uint2 t = *reinterpret_cast<const uint2 *>(reinterpret_cast<const bf16 *>(base) + idx);
+  return make_uint4(t.x, t.y, 0u, 0u);
+}
+__device__ __forceinline__ void decode4(const uint4 &r, int dtype, float (&v)[4]) {
+  if (dtype == ASIS_F32) {
+    v[0] = __uint_as_float(r.x); v[1] = __uint_as_float(r.y); v[2] = __uint_as_float(r.z); v[3] = __uint_as_float(r.w);
+  } else {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162 *>(&r.x);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162 *>(&r.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+  }
+}
+
+// which epilogues read a second [M, N] operand (the residual, the saved pre-activation, or C itself)
+template <int KIND> struct EpiReads { static constexpr bool value = KIND == ASIS_EPI_SCALE_RESIDUAL || KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_ACCUMULATE; };
+
+// the 4-column group of one row in the coalesced layout; KIND is a compile-time constant; `pre` is
+// the prefetched operand (valid on the vector path only)
 template <int KIND>
 __device__ __forceinline__ void epi_group4(const GemmTcParams &p, int row, int col, float (&v)[4], const float (&b4)[4],
-                                           const float (&g4)[4], bool vec_ok) {
+                                           const float (&g4)[4], const uint4 &pre, bool vec_ok) {
   const EpiArgs &e = p.epi;
   if (!vec_ok || col + 4 > p.N) {
 #pragma unroll
@@ -101,29 +122,55 @@ __device__ __forceinline__ void epi_group4(const GemmTcParams &p, int row, int c
   } else if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
     if (e.aux) store4_any(e.aux, e.aux_dtype, ai, v);
     float r[4];
-    load4_any(e.residual, ASIS_F32, ci, r);
+    decode4(pre, ASIS_F32, r);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = fmaf(g4[i], v[i], r[i]);
   } else if (KIND == ASIS_EPI_DGELU) {
     float h[4];
-    load4_any(e.aux, e.aux_dtype, ai, h);
+    decode4(pre, e.aux_dtype, h);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] *= dgelu_fast(h[i]);
   } else if (KIND == ASIS_EPI_ACCUMULATE) {
     float c[4];
-    load4_any(e.C, ASIS_F32, ci, c);
+    decode4(pre, ASIS_F32, c);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] += c[i];
   }
   store4_any(e.C, e.c_dtype, ci, v);
 }
 
+// prefetch the 8 row groups of chunk c (this lane's 4 columns) of the epilogue's second operand.
+// The compiler may not hoist these loads above earlier stores (possible aliasing), so without the
+// explicit software pipeline every one of the 32 (chunk, row group) steps of a tile waited a full
+// global-memory round trip: the residual / GELU' epilogues cost 2-3x the MMA main loop.
+template <int KIND>
+__device__ __forceinline__ void epi_prefetch(const GemmTcParams &p, int row0, int col, int r, bool vec_ok, uint4 (&pre)[8]) {
+  if (!EpiReads<KIND>::value) return;
+  const EpiArgs &e = p.epi;
+  if (!vec_ok || p.atomic_out || col + 4 > p.N) return;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = row0 + it * 4 + r;
+    if (row < p.M) {
+      if (KIND == ASIS_EPI_SCALE_RESIDUAL) pre[it] = ldraw4(e.residual, ASIS_F32, (size_t)row * e.ldc + col);
+      else if (KIND == ASIS_EPI_DGELU) pre[it] = ldraw4(e.aux, e.aux_dtype, (size_t)row * e.ldaux + col);
+      else pre[it] = ldraw4(e.C, ASIS_F32, (size_t)row * e.ldc + col);
+    }
+  }
+}
+
 // the epilogue of one 32-row x 128-column slab owned by one warp
 template <int KIND>
 __device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, float *stage, int row0, int col_base,
-                                         bool vec_ok, int lane) {
+                                         bool vec_ok, int lane, uint64_t *tfull, uint32_t tfull_phase) {
   const EpiArgs &e = p.epi;
   const int cg = lane & 7, r = lane >> 3;
+  uint4 pre[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pre[i] = make_uint4(0u, 0u, 0u, 0u);
+  epi_prefetch<KIND>(p, row0, col_base + cg * 4, r, vec_ok, pre);   // in flight while the MMAs of this tile finish
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     float v[32];
@@ -135,6 +182,10 @@ __device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, 
       *reinterpret_cast<float4 *>(stage + lane * 32 + ((g ^ (lane & 7)) << 2)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
     __syncwarp();
     const int col = col_base + c * 32 + cg * 4;
+    uint4 cur[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur[i] = pre[i];
+    if (c + 1 < 4) epi_prefetch<KIND>(p, row0, col + 32, r, vec_ok, pre);
     if (col < p.N) {
       float b4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {0.f, 0.f, 0.f, 0.f};
       if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE && e.bias) {
@@ -150,7 +201,7 @@ __device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, 
         const int rl = it * 4 + r;
         const float4 t = *reinterpret_cast<const float4 *>(stage + rl * 32 + ((cg ^ (rl & 7)) << 2));
         float w[4] = {t.x, t.y, t.z, t.w};
-        if (row0 + rl < p.M) epi_group4<KIND>(p, row0 + rl, col, w, b4, g4, vec_ok);
+        if (row0 + rl < p.M) epi_group4<KIND>(p, row0 + rl, col, w, b4, g4, cur[it], vec_ok);
       }
     }
     __syncwarp();
@@ -310,17 +361,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_blk = (tile % p.m_groups) * CL + crank;
       const int n_blk = (tile / p.m_groups) % p.n_tiles;
-      mbar_wait(tfull_bar + acc, acc_phase);
-      tc_fence_after();
       const int row0 = m_blk * BM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
       const int col_base = n_blk * BN + half * 128;
       switch (p.epi.kind) {
-        case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
-        case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
-        case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
-        case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
-        default: epi_slab<ASIS_EPI_NONE>(p, taddr, stage, row0, col_base, vec_ok, lane); break;
+        case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
+        case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
+        case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
+        case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
+        default: epi_slab<ASIS_EPI_NONE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
       }
       tc_fence_before();
       __syncwarp();

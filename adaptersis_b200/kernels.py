@@ -23,9 +23,9 @@ def set_profiler(p):
 class _Span:
     __slots__ = ("tok",)
 
-    def __init__(self, name, work, unit):
+    def __init__(self, name, work, unit, detail=None):
         p = _PROF[0]
-        self.tok = p.begin(name, work, unit) if p is not None else None
+        self.tok = p.begin(name, work, unit, detail) if p is not None else None
 
     def __enter__(self):
         return self
@@ -171,7 +171,11 @@ def gemm(compute, A, a_major, B, b_major, M, N, K, out_dtype, epilogue=EPI_NONE,
     if residual is not None:
         residual = _c(residual)
         assert residual.dtype == torch.float32 and residual.shape[-1] == N
-    with _Span("gemm_bf16" if compute == BF16 else "gemm_f32", 2.0 * M * N * K, "FLOP"):
+    detail = None
+    if _PROF[0] is not None:
+        detail = (f"M={M} N={N} K={K} {'KM'[a_major]}/{'KM'[b_major]} epi={epilogue} out={'bf16' if out.dtype == torch.bfloat16 else 'f32'}"
+                  f"{' aux' if aux is not None else ''}{' bias' if bias is not None else ''}")
+    with _Span("gemm_bf16" if compute == BF16 else "gemm_f32", 2.0 * M * N * K, "FLOP", detail):
         check(_lib.load().asis_gemm(compute, ptr(A), a_major, A.stride(0), ptr(B), b_major, B.stride(0), ptr(out),
                                     dt(out), out.stride(0), M, N, K, epilogue, ptr(bias), ptr(gamma), ptr(residual),
                                     ptr(aux), dt(aux) if aux is not None else 0,

@@ -94,11 +94,11 @@ class SpanProfiler:
     def __init__(self):
         self.spans = []
 
-    def begin(self, name, work, unit):
+    def begin(self, name, work, unit, detail=None):
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        return (name, work, unit, e0, e1)
+        return (name, work, unit, e0, e1, detail)
 
     def end(self, tok):
         tok[4].record()
@@ -107,12 +107,27 @@ class SpanProfiler:
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for name, work, unit, e0, e1 in self.spans:
+        self.detail = {}
+        for name, work, unit, e0, e1, detail in self.spans:
             a = agg.setdefault(name, {"n": 0, "ms": 0.0, "work": 0.0, "unit": unit})
+            ms = e0.elapsed_time(e1)
             a["n"] += 1
-            a["ms"] += e0.elapsed_time(e1)
+            a["ms"] += ms
             a["work"] += work
+            if detail is not None:
+                d = self.detail.setdefault((name, detail), {"n": 0, "ms": 0.0, "work": 0.0})
+                d["n"] += 1
+                d["ms"] += ms
+                d["work"] += work
         return agg
+
+    def detail_table(self):
+        """per-shape breakdown (call after summary()): markdown rows sorted by time"""
+        rows = sorted(self.detail.items(), key=lambda kv: -kv[1]["ms"])
+        out = ["| ms | launches | us/launch | TFLOP/s | op | shape |", "|---:|---:|---:|---:|---|---|"]
+        for (name, detail), d in rows:
+            out.append(f"| {d['ms']:.2f} | {d['n']} | {1e3 * d['ms'] / d['n']:.1f} | {d['work'] / d['ms'] / 1e9:.0f} | {name} | {detail} |")
+        return "\n".join(out)
 
 
 def synth_batch(B, size, n_cls, seed):
@@ -305,6 +320,8 @@ def run_ours(args, rank, world, local_rank):
     table = {k: {"n": v["n"], "ms": round(v["ms"], 3)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
     print("[bench] per-op time inside one profiled step (ms):", json.dumps(table), file=sys.stderr)
     print(f"[bench] profiled step {prof_step_ms:.1f} ms; timed step {t_ms / args.steps:.1f} ms", file=sys.stderr)
+    if args.detail:
+        print("[bench] per-shape breakdown of the profiled step:\n" + prof.detail_table(), file=sys.stderr)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -350,6 +367,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--frozen-backbone", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="print the per-shape GEMM breakdown of the profiled step")
     ap.add_argument("--only-timed", action="store_true", help="warm-up + timed loop only (used under ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
