@@ -102,32 +102,32 @@ __device__ __forceinline__ float dgelu_erf(float x) {
   return cdf + x * pdf;
 }
 
-// Fast GELU pair for the bf16 tensor-core epilogues: erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7,
+// Fast GELU pair for the bf16 tensor-core epilogues: erfc by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7,
 // far below bf16 rounding), one MUFU.RCP + one MUFU.EX2 instead of the ~40-instruction erff.
-// The exponential exp(-x^2/2) is shared between erf(x/sqrt2) and the Gaussian density.
-__device__ __forceinline__ void gelu_parts_fast(float x, float &cdf, float &pdf) {
-  const float z = fabsf(x) * 0.70710678118654752f;
+//   h(x) = 0.5 * erfc(|x|/sqrt2) = 0.5 * poly(t) * t * exp(-x^2/2),  t = 1 / (1 + p |x|/sqrt2)
+//   Phi(x) = x >= 0 ? 1 - h : h          gelu(x) = x Phi(x) = max(x, 0) - |x| h
+// (the 0.5 is folded into the polynomial, the 1/sqrt2 into p; exp(-x^2/2) is shared with the density)
+__device__ __forceinline__ float gelu_half_erfc(float x, float &e) {
+  const float ax = fabsf(x);
   float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));   // exp(-x^2/2)
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float erfz = 1.0f - poly * t * e;            // erf(|x|/sqrt2)
-  cdf = 0.5f * (1.0f + copysignf(erfz, x));
-  pdf = 0.3989422804014327f * e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(ax, 0.3275911f * 0.70710678118654752f, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * (-0.5f * 1.4426950408889634f)));   // exp(-x^2/2)
+  float poly = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  return (poly * t) * e;
 }
 __device__ __forceinline__ float gelu_fast(float x) {
-  float cdf, pdf;
-  gelu_parts_fast(x, cdf, pdf);
-  return x * cdf;
+  float e;
+  const float h = gelu_half_erfc(x, e);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float dgelu_fast(float x) {
-  float cdf, pdf;
-  gelu_parts_fast(x, cdf, pdf);
-  return fmaf(x, pdf, cdf);
+  float e;
+  const float h = gelu_half_erfc(x, e);
+  const float cdf = 0.5f + copysignf(0.5f - h, x);
+  return fmaf(x * e, 0.3989422804014327f, cdf);
 }
 
 // dispatch on a runtime dtype to a compile-time type

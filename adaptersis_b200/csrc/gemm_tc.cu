@@ -89,28 +89,13 @@ __device__ __forceinline__ void decode4(const uint4 &r, int dtype, float (&v)[4]
 // which epilogues read a second [M, N] operand (the residual, the saved pre-activation, or C itself)
 template <int KIND> struct EpiReads { static constexpr bool value = KIND == ASIS_EPI_SCALE_RESIDUAL || KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_ACCUMULATE; };
 
-// the 4-column group of one row in the coalesced layout; KIND is a compile-time constant; `pre` is
-// the prefetched operand (valid on the vector path only)
+// the 4-column group of one row in the coalesced layout, vector path (col + 4 <= N, 16-byte aligned
+// pitches, no split-K); KIND is a compile-time constant; `pre` is the prefetched second operand
 template <int KIND>
-__device__ __forceinline__ void epi_group4(const GemmTcParams &p, int row, int col, float (&v)[4], const float (&b4)[4],
-                                           const float (&g4)[4], const uint4 &pre, bool vec_ok) {
-  const EpiArgs &e = p.epi;
-  if (!vec_ok || col + 4 > p.N) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (col + j < p.N) {
-        if (p.atomic_out) atomicAdd(reinterpret_cast<float *>(e.C) + (size_t)row * e.ldc + col + j, v[j]);
-        else epi_scalar(e, row, col + j, v[j]);
-      }
-    }
-    return;
-  }
+__device__ __forceinline__ void epi_group4(const EpiArgs &e, int row, int col, float (&v)[4], const float (&b4)[4],
+                                           const float (&g4)[4], const uint4 &pre) {
   const size_t ci = (size_t)row * e.ldc + col;
   const size_t ai = (size_t)row * e.ldaux + col;
-  if (p.atomic_out) {
-    atomicAdd(reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.C) + ci), make_float4(v[0], v[1], v[2], v[3]));
-    return;
-  }
   if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] += b4[i];
@@ -137,6 +122,25 @@ __device__ __forceinline__ void epi_group4(const GemmTcParams &p, int row, int c
     for (int i = 0; i < 4; ++i) v[i] += c[i];
   }
   store4_any(e.C, e.c_dtype, ci, v);
+}
+
+// everything else (N tails, unaligned pitches, split-K reduction): rolled loops, so that the hot
+// path above stays small (fully unrolled and inlined 32x, the generic path quadrupled the code size
+// and the epilogue warps stalled on instruction fetch)
+__device__ __forceinline__ void epi_group4_slow(const GemmTcParams &p, int row, int col, const float4 &t, bool vec_ok) {
+  const EpiArgs &e = p.epi;
+  if (p.atomic_out && vec_ok && col + 4 <= p.N) {
+    atomicAdd(reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.C) + (size_t)row * e.ldc + col), t);
+    return;
+  }
+#pragma unroll 1
+  for (int j = 0; j < 4; ++j) {
+    const float vj = j == 0 ? t.x : j == 1 ? t.y : j == 2 ? t.z : t.w;
+    if (col + j < p.N) {
+      if (p.atomic_out) atomicAdd(reinterpret_cast<float *>(e.C) + (size_t)row * e.ldc + col + j, vj);
+      else epi_scalar(e, row, col + j, vj);
+    }
+  }
 }
 
 // prefetch the 8 row groups of chunk c (this lane's 4 columns) of the epilogue's second operand.
@@ -196,12 +200,22 @@ __device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, 
 #pragma unroll
         for (int i = 0; i < 4; ++i) g4[i] = (col + i < p.N) ? __ldg(e.gamma + col + i) : 0.f;
       }
+      const bool fast = vec_ok && !p.atomic_out && col + 4 <= p.N;
+      if (fast) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rl = it * 4 + r;
-        const float4 t = *reinterpret_cast<const float4 *>(stage + rl * 32 + ((cg ^ (rl & 7)) << 2));
-        float w[4] = {t.x, t.y, t.z, t.w};
-        if (row0 + rl < p.M) epi_group4<KIND>(p, row0 + rl, col, w, b4, g4, cur[it], vec_ok);
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + r;
+          const float4 t = *reinterpret_cast<const float4 *>(stage + rl * 32 + ((cg ^ (rl & 7)) << 2));
+          float w[4] = {t.x, t.y, t.z, t.w};
+          if (row0 + rl < p.M) epi_group4<KIND>(e, row0 + rl, col, w, b4, g4, cur[it]);
+        }
+      } else {
+#pragma unroll 1
+        for (int it = 0; it < 8; ++it) {
+          const int rl = it * 4 + r;
+          const float4 t = *reinterpret_cast<const float4 *>(stage + rl * 32 + ((cg ^ (rl & 7)) << 2));
+          if (row0 + rl < p.M) epi_group4_slow(p, row0 + rl, col, t, vec_ok);
+        }
       }
     }
     __syncwarp();
