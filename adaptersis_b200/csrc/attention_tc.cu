@@ -99,9 +99,13 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kstep) {
 }
 
 // pack 32 floats to bf16 and write them as row `row`, columns [col0, col0+32) of a K-major 128B-swizzled
-// tile whose 64-column sub-tiles hold `rows` rows each
+// tile whose 64-column sub-tiles hold `rows` rows each.  32-bit shared-window addresses and
+// st.shared (generic 64-bit pointers cost two registers per precomputed address and spilled).
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void store_row32(uint8_t *tile, int rows, int row, int col0, const float (&v)[32]) {
-  uint8_t *sub = tile + (col0 >> 6) * (rows * 128) + (row >> 3) * 1024 + (row & 7) * 128;
+  const uint32_t sub = smem_u32(tile) + (col0 >> 6) * (rows * 128) + (row >> 3) * 1024 + (row & 7) * 128;
   const int ch0 = (col0 & 63) >> 3;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -111,7 +115,7 @@ __device__ __forceinline__ void store_row32(uint8_t *tile, int rows, int row, in
       __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * c + 2 * i], v[8 * c + 2 * i + 1]);
       w[i] = *reinterpret_cast<uint32_t *>(&h);
     }
-    *reinterpret_cast<uint4 *>(sub + (((ch0 + c) ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    st_shared_v4(sub + (((ch0 + c) ^ (row & 7)) << 4), w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -147,8 +151,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   uint8_t *sP = sV + FWD_STAGES * T16K;          // one 32 KB buffer per warpgroup
   uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * T32K);
   uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = kv_full + FWD_STAGES, *s_full = kv_empty + FWD_STAGES,
-           *s_empty = s_full + NSB, *p_full = s_empty + NSB, *o_full = p_full + 2, *o_empty = o_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 2);
+           *s_empty = s_full + NSB, *p_full = s_empty + NSB, *o_full = p_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
@@ -169,7 +173,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(p_full + i, 4);
       mbar_init(o_full + i, 1);
-      mbar_init(o_empty + i, 4);
     }
     fence_barrier_init();
   }
@@ -225,12 +228,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
       for (int j = 0; j < nkv; ++j) {
         const int w = j & 1, u = j >> 1, st = j % FWD_STAGES;
         mbar_wait(p_full + w, u & 1);
-        if (u > 0) mbar_wait(o_empty + w, (u - 1) & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tO + w * HD, desc_kmajor(aP + w * T32K, k), desc_mnmajor(aV + st * T16K, k), idesc_o, k > 0);
+          for (int k = 0; k < 8; ++k)     // O[w] += P V, accumulated in TMEM over this warpgroup's tiles
+            umma_bf16(tO + w * HD, desc_kmajor(aP + w * T32K, k), desc_mnmajor(aV + st * T16K, k), idesc_o, (u > 0 || k > 0));
           umma_commit(o_full + w);
           umma_commit(kv_empty + st);
         }
@@ -244,100 +246,83 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     const int row = quarter * 32 + lane;            // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     uint8_t *myP = sP + w * T32K;
-    float o[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    // Running state in the log2 domain.  O[w] lives in TMEM and is accumulated there by the MMAs; it
+    // is only touched here when the running maximum grows by more than 2^8 (lazy rescaling: until
+    // then the probabilities are formed against the stale maximum m_use, at most 256x too large --
+    // harmless in fp32 / bf16 -- and (m_use, l, O) stay mutually consistent).
+    float m_use = -INFINITY, l_run = 0.f;
     int u = 0;
     for (int j = w; j < nkv; j += 2, ++u) {
       const int kv0 = j * TILE;
-      const bool tail = kv0 + TILE > p.T;            // only the last key block has invalid columns
       const int sb = j % NSB;
       mbar_wait(s_full + sb, (j / NSB) & 1);
       tc_fence_after();
-      // pass 1: row maximum of the raw scores (scale > 0, applied once to the maximum); TMEM loads
-      // two at a time, four independent max chains
-      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      // the whole score row into registers with one wait; the TMEM buffer is free again right away
+      float s[4][32];
 #pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        float v0[32], v1[32];
-        tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32, v0);
-        tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32 + 32, v1);
-        tmem_ld_wait();
-        if (tail) {
+      for (int c = 0; c < 4; ++c) tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32, s[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty + sb);
+      if (kv0 + TILE > p.T) {                          // only the last key block has invalid columns
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            mx4[i & 3] = fmaxf(mx4[i & 3], (kv0 + c * 32 + i < p.T) ? v0[i] : -INFINITY);
-            mx4[i & 3] = fmaxf(mx4[i & 3], (kv0 + c * 32 + 32 + i < p.T) ? v1[i] : -INFINITY);
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (kv0 + c * 32 + i >= p.T) s[c][i] = -INFINITY;
+      }
+      float mx4[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        mx4[c] = fmaxf(s[c][0], s[c][1]);
+#pragma unroll
+        for (int i = 2; i < 32; i += 2) mx4[c] = fmaxf(mx4[c], fmaxf(s[c][i], s[c][i + 1]));
+      }
+      const float m_new = fmaxf(m_use, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2);
+      bool waited = false;
+      if (u == 0) {
+        m_use = m_new;
+      } else {
+        const bool grow = m_new - m_use > 8.f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2(m_use - m_new) : 1.f;
+          if (grow) m_use = m_new;
+          l_run *= alpha;
+          mbar_wait(o_full + w, (u - 1) & 1);          // every P V issued so far for this warpgroup is complete
+          waited = true;
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {                // 32 columns at a time: the score row owns the registers
+            float o0[32];
+            tmem_ld32(tO + lane_addr + w * HD + c * 32, o0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o0[i] *= alpha;
+            tmem_st32(tO + lane_addr + w * HD + c * 32, o0);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], fmaxf(v0[i], v1[i]));
+          tmem_st_wait();
         }
       }
-      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = fast_exp2(m_run - m_new);
-      // fold in this warpgroup's previous P V (its completion also frees the P buffer), rescale
-      if (u > 0) {
-        mbar_wait(o_full + w, (u - 1) & 1);
-        tc_fence_after();
-        {
-          float v0[32], v1[32];
-          tmem_ld32_issue(tO + lane_addr + w * HD, v0);
-          tmem_ld32_issue(tO + lane_addr + w * HD + 32, v1);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            o[i] += v0[i];
-            o[32 + i] += v1[i];
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(o_empty + w);
-        if (alpha != 1.f) {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) o[i] *= alpha;
-        }
-      }
-      // pass 2: probabilities -> smem (bf16), row sum (four independent chains)
       float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c = 0; c < 4; c += 2) {
-        float v0[32], v1[32];
-        tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32, v0);
-        tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32 + 32, v1);
-        tmem_ld_wait();
-        if (tail) {
+      for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v0[i] = (kv0 + c * 32 + i < p.T) ? fast_exp2(fmaf(v0[i], p.scale_log2, -m_new)) : 0.f;
-            v1[i] = (kv0 + c * 32 + 32 + i < p.T) ? fast_exp2(fmaf(v1[i], p.scale_log2, -m_new)) : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            v0[i] = fast_exp2(fmaf(v0[i], p.scale_log2, -m_new));
-            v1[i] = fast_exp2(fmaf(v1[i], p.scale_log2, -m_new));
-          }
+        for (int i = 0; i < 32; ++i) {
+          s[c][i] = fast_exp2(fmaf(s[c][i], p.scale_log2, -m_use));
+          l4[i & 3] += s[c][i];
         }
+      l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      // this warpgroup's previous P V must have finished reading the P buffer
+      if (u > 0 && !waited) mbar_wait(o_full + w, (u - 1) & 1);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) l4[i & 3] += v0[i] + v1[i];
-        store_row32(myP, TILE, row, c * 32, v0);
-        store_row32(myP, TILE, row, c * 32 + 32, v1);
-      }
-      const float l_add = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+      for (int c = 0; c < 4; ++c) store_row32(myP, TILE, row, c * 32, s[c]);
       tc_fence_before();
       fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty + sb);
-        mbar_arrive(p_full + w);
-      }
-      l_run = l_run * alpha + l_add;
-      m_run = m_new;
+      if (lane == 0) mbar_arrive(p_full + w);
     }
+    float o[64];
+    float m_run = m_use;
     if (u > 0) {
       mbar_wait(o_full + w, (u - 1) & 1);
       tc_fence_after();
@@ -346,8 +331,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
         float v[32];
         tmem_ld32(tO + lane_addr + w * HD + c * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] += v[i];
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = v[i];
       }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 64; ++i) o[i] = 0.f;
     }
     // merge the two warpgroups' partial softmax states (all P V reads of smem are complete: every
     // o_full has fired).  Warpgroup 1 publishes (m, l, O) through the P buffers.
