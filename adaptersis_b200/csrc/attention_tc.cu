@@ -138,30 +138,45 @@ constexpr uint32_t TMEM_COLS = 512;
 // forward
 // ------------------------------------------------------------------------------------------------
 constexpr int FWD_STAGES = 4;
-constexpr int NSB = 3;              // rotating score buffers in TMEM (tile t uses buffer t % 3)
-constexpr int FWD_SMEM = T16K /*Q*/ + FWD_STAGES * 2 * T16K /*K,V*/ + 2 * T32K /*P per warpgroup*/ + 1024 + 256;
+constexpr int NSB = 3;              // rotating score buffers in TMEM (global tile g uses buffer g % 3)
+constexpr int FWD_SMEM = 2 * T16K /*Q, double buffered*/ + FWD_STAGES * 2 * T16K /*K,V*/ + 2 * T32K /*P per warpgroup*/ +
+                         1024 /*(m, l) exchange*/ + 1024 /*align*/ + 256 /*barriers*/;
 
+// Persistent: one CTA per SM walks over its (query block, head, image) items; the TMA and MMA warps
+// run ahead across item boundaries (next Q into the other Q buffer, next K/V into the ring, the first
+// score tiles of the next item into the free TMEM buffers) while the softmax warpgroups finish the
+// current item -- with one CTA per item the softmax warps spent ~20 % of their time waiting for the
+// first scores and the tensor pipe idled through every prologue / epilogue.
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const int num_items, const int nqb) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *sQ = smem;
-  uint8_t *sK = sQ + T16K;                       // FWD_STAGES tiles
+  uint8_t *sQ = smem;                            // 2 tiles
+  uint8_t *sK = sQ + 2 * T16K;                   // FWD_STAGES tiles
   uint8_t *sV = sK + FWD_STAGES * T16K;          // FWD_STAGES tiles
   uint8_t *sP = sV + FWD_STAGES * T16K;          // one 32 KB buffer per warpgroup
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * T32K);
-  uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = kv_full + FWD_STAGES, *s_full = kv_empty + FWD_STAGES,
-           *s_empty = s_full + NSB, *p_full = s_empty + NSB, *o_full = p_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_full + 2);
+  float *sML = reinterpret_cast<float *>(sP + 2 * T32K);   // [2][128]: warpgroup 1's (m, l) for the merge
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sP + 2 * T32K + 1024);
+  uint64_t *q_full = bars, *q_empty = q_full + 2, *kv_full = q_empty + 2, *kv_empty = kv_full + FWD_STAGES,
+           *s_full = kv_empty + FWD_STAGES, *s_empty = s_full + NSB, *p_full = s_empty + NSB, *o_full = p_full + 2,
+           *o_empty = o_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
   const int C = p.H * HD;
   const int nkv = (p.T + TILE - 1) / TILE;
+  const int n_my = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
+  const int G = n_my * nkv;                                                               // its key tiles, in order
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQKV);
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + i, 1);
+      mbar_init(q_empty + i, 1);
+      mbar_init(p_full + i, 4);
+      mbar_init(o_full + i, 1);
+      mbar_init(o_empty + i, 4);
+    }
     for (int i = 0; i < FWD_STAGES; ++i) {
       mbar_init(kv_full + i, 1);
       mbar_init(kv_empty + i, 1);
@@ -169,10 +184,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
     for (int i = 0; i < NSB; ++i) {
       mbar_init(s_full + i, 1);
       mbar_init(s_empty + i, 4);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(p_full + i, 4);
-      mbar_init(o_full + i, 1);
     }
     fence_barrier_init();
   }
@@ -187,181 +198,199 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   // only the TMA / tcgen05 instructions sit under elect_one): operands then live in uniform registers
   // and the MMAs issue back to back instead of through per-instruction R2UR waterfall loops.
   if (warp == 0) {
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, T16K);
-      tma_load_3d(&tmQKV, q_full, sQ, h * HD, q0, b);
-    }
-    __syncwarp();
-    for (int j = 0; j < nkv; ++j) {
-      const int st = j % FWD_STAGES, use = j / FWD_STAGES;
-      if (use > 0) mbar_wait(kv_empty + st, (use - 1) & 1);
+    int g = 0;
+    for (int k = 0; k < n_my; ++k) {
+      const int item = (int)blockIdx.x + k * (int)gridDim.x;
+      const int qb = item % nqb, bh = item / nqb, h = bh % p.H, b = bh / p.H;
+      const int qbuf = k & 1;
+      if (k >= 2) mbar_wait(q_empty + qbuf, ((k >> 1) - 1) & 1);
       if (elect_one()) {
-        mbar_arrive_expect_tx(kv_full + st, 2 * T16K);
-        tma_load_3d(&tmQKV, kv_full + st, sK + st * T16K, C + h * HD, j * TILE, b);
-        tma_load_3d(&tmQKV, kv_full + st, sV + st * T16K, 2 * C + h * HD, j * TILE, b);
+        mbar_arrive_expect_tx(q_full + qbuf, T16K);
+        tma_load_3d(&tmQKV, q_full + qbuf, sQ + qbuf * T16K, h * HD, qb * TILE, b);
       }
       __syncwarp();
-    }
-  } else if (warp == 1) {
-    {
-      constexpr uint32_t idesc_s = make_idesc(TILE, TILE, 0, 0);   // S = Q K^T : both K-major
-      constexpr uint32_t idesc_o = make_idesc(TILE, HD, 0, 1);     // O = P V   : V is MN-major
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
-      mbar_wait(q_full, 0);
-      // Scores go round three TMEM buffers, so the S of a warpgroup's next tile is issued when the
-      // *other* warpgroup finishes a tile -- half a tile ahead of its use (with one buffer per
-      // warpgroup the softmax warps spent 30 % of their time waiting for S).
-      auto issue_s = [&](int j) {
-        const int sb = j % NSB, ub = j / NSB, st = j % FWD_STAGES;
-        mbar_wait(kv_full + st, (j / FWD_STAGES) & 1);
-        if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
-        tc_fence_after();
+      for (int j = 0; j < nkv; ++j, ++g) {
+        const int st = g % FWD_STAGES, use = g / FWD_STAGES;
+        if (use > 0) mbar_wait(kv_empty + st, (use - 1) & 1);
         if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tS + sb * TILE, desc_kmajor(aQ, k), desc_kmajor(aK + st * T16K, k), idesc_s, k > 0);
-          umma_commit(s_full + sb);
+          mbar_arrive_expect_tx(kv_full + st, 2 * T16K);
+          tma_load_3d(&tmQKV, kv_full + st, sK + st * T16K, C + h * HD, j * TILE, b);
+          tma_load_3d(&tmQKV, kv_full + st, sV + st * T16K, 2 * C + h * HD, j * TILE, b);
         }
         __syncwarp();
-      };
-      for (int j = 0; j < NSB && j < nkv; ++j) issue_s(j);
-      for (int j = 0; j < nkv; ++j) {
-        const int w = j & 1, u = j >> 1, st = j % FWD_STAGES;
-        mbar_wait(p_full + w, u & 1);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k)     // O[w] += P V, accumulated in TMEM over this warpgroup's tiles
-            umma_bf16(tO + w * HD, desc_kmajor(aP + w * T32K, k), desc_mnmajor(aV + st * T16K, k), idesc_o, (u > 0 || k > 0));
-          umma_commit(o_full + w);
-          umma_commit(kv_empty + st);
-        }
-        __syncwarp();
-        if (j + NSB < nkv) issue_s(j + NSB);
       }
     }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = make_idesc(TILE, TILE, 0, 0);   // S = Q K^T : both K-major
+    constexpr uint32_t idesc_o = make_idesc(TILE, HD, 0, 1);     // O = P V   : V is MN-major
+    const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
+    // Scores go round three TMEM buffers and are issued three tiles ahead of the P V that consumes
+    // them, across item boundaries.
+    auto issue_s = [&](int g) {
+      const int k = g / nkv, j = g - k * nkv, qbuf = k & 1;
+      const int sb = g % NSB, ub = g / NSB, st = g % FWD_STAGES;
+      if (j == 0) mbar_wait(q_full + qbuf, (k >> 1) & 1);
+      mbar_wait(kv_full + st, (g / FWD_STAGES) & 1);
+      if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tS + sb * TILE, desc_kmajor(aQ + qbuf * T16K, kk), desc_kmajor(aK + st * T16K, kk), idesc_s, kk > 0);
+        umma_commit(s_full + sb);
+        if (j == nkv - 1) umma_commit(q_empty + qbuf);      // the Q buffer may be refilled (item k + 2)
+      }
+      __syncwarp();
+    };
+    for (int g = 0; g < NSB && g < G; ++g) issue_s(g);
+    for (int g = 0; g < G; ++g) {
+      const int k = g / nkv, j = g - k * nkv;
+      const int w = g & 1, st = g % FWD_STAGES;
+      mbar_wait(p_full + w, (g >> 1) & 1);
+      if (j == 0 && k > 0) {                                // both warpgroups have read the previous item's O
+        mbar_wait(o_empty + 0, (k - 1) & 1);
+        mbar_wait(o_empty + 1, (k - 1) & 1);
+      }
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)     // O[w] (+)= P V, accumulated in TMEM over this warpgroup's tiles of the item
+          umma_bf16(tO + w * HD, desc_kmajor(aP + w * T32K, kk), desc_mnmajor(aV + st * T16K, kk), idesc_o, (j >= 2 || kk > 0));
+        umma_commit(o_full + w);
+        umma_commit(kv_empty + st);
+      }
+      __syncwarp();
+      if (g + NSB < G) issue_s(g + NSB);
+    }
   } else {
-    const int w = (warp - 2) >> 2;                  // warpgroup: key tiles j == w (mod 2)
+    const int w = (warp - 2) >> 2;                  // warpgroup: global key tiles g == w (mod 2)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;            // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     uint8_t *myP = sP + w * T32K;
-    // Running state in the log2 domain.  O[w] lives in TMEM and is accumulated there by the MMAs; it
-    // is only touched here when the running maximum grows by more than 2^8 (lazy rescaling: until
-    // then the probabilities are formed against the stale maximum m_use, at most 256x too large --
-    // harmless in fp32 / bf16 -- and (m_use, l, O) stay mutually consistent).
-    float m_use = -INFINITY, l_run = 0.f;
-    int u = 0;
-    for (int j = w; j < nkv; j += 2, ++u) {
-      const int kv0 = j * TILE;
-      const int sb = j % NSB;
-      mbar_wait(s_full + sb, (j / NSB) & 1);
-      tc_fence_after();
-      // the whole score row into registers with one wait; the TMEM buffer is free again right away
-      float s[4][32];
+    float *xch = reinterpret_cast<float *>(sP);     // [64][128] floats = warpgroup 0's P buffer
+    for (int k = 0; k < n_my; ++k) {
+      const int item = (int)blockIdx.x + k * (int)gridDim.x;
+      const int qb = item % nqb, bh = item / nqb, h = bh % p.H, b = bh / p.H;
+      const int g0 = k * nkv;
+      // Running state in the log2 domain.  O[w] lives in TMEM and is accumulated there by the MMAs; it
+      // is only touched here when the running maximum grows by more than 2^8 (lazy rescaling: until
+      // then the probabilities are formed against the stale maximum m_use, at most 256x too large --
+      // harmless in fp32 / bf16 -- and (m_use, l, O) stay mutually consistent).
+      float m_use = -INFINITY, l_run = 0.f;
+      int u = 0, g_last = -1;
+      for (int g = g0 + ((g0 ^ w) & 1); g < g0 + nkv; g += 2, ++u) {
+        const int kv0 = (g - g0) * TILE;
+        const int sb = g % NSB;
+        g_last = g;
+        mbar_wait(s_full + sb, (g / NSB) & 1);
+        tc_fence_after();
+        // the whole score row into registers with one wait; the TMEM buffer is free again right away
+        float s[4][32];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32, s[c]);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty + sb);
-      if (kv0 + TILE > p.T) {                          // only the last key block has invalid columns
+        for (int c = 0; c < 4; ++c) tmem_ld32_issue(tS + lane_addr + sb * TILE + c * 32, s[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty + sb);
+        if (kv0 + TILE > p.T) {                          // only the last key block has invalid columns
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+          for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (kv0 + c * 32 + i >= p.T) s[c][i] = -INFINITY;
-      }
-      float mx4[4];
+            for (int i = 0; i < 32; ++i)
+              if (kv0 + c * 32 + i >= p.T) s[c][i] = -INFINITY;
+        }
+        float mx4[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        mx4[c] = fmaxf(s[c][0], s[c][1]);
+        for (int c = 0; c < 4; ++c) {
+          mx4[c] = fmaxf(s[c][0], s[c][1]);
 #pragma unroll
-        for (int i = 2; i < 32; i += 2) mx4[c] = fmaxf(mx4[c], fmaxf(s[c][i], s[c][i + 1]));
-      }
-      const float m_new = fmaxf(m_use, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2);
-      bool waited = false;
-      if (u == 0) {
-        m_use = m_new;
-      } else {
-        const bool grow = m_new - m_use > 8.f;
-        if (__any_sync(0xffffffffu, grow)) {
-          const float alpha = grow ? fast_exp2(m_use - m_new) : 1.f;
-          if (grow) m_use = m_new;
-          l_run *= alpha;
-          mbar_wait(o_full + w, (u - 1) & 1);          // every P V issued so far for this warpgroup is complete
-          waited = true;
-          tc_fence_after();
+          for (int i = 2; i < 32; i += 2) mx4[c] = fmaxf(mx4[c], fmaxf(s[c][i], s[c][i + 1]));
+        }
+        const float m_new = fmaxf(m_use, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2);
+        // this warpgroup's previous P V (global per-warpgroup tile (g >> 1) - 1) must have finished
+        // reading the P buffer; it was issued a whole tile ago, so the wait is normally already
+        // satisfied.  It sits before the exponentials so that those and the bf16 packing / smem stores
+        // form one block the scheduler can interleave.
+        if (u > 0) mbar_wait(o_full + w, ((g >> 1) - 1) & 1);
+        if (u == 0) {
+          m_use = m_new;
+        } else {
+          const bool grow = m_new - m_use > 8.f;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float alpha = grow ? fast_exp2(m_use - m_new) : 1.f;
+            if (grow) m_use = m_new;
+            l_run *= alpha;
+            tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 2; ++c) {                // 32 columns at a time: the score row owns the registers
-            float o0[32];
-            tmem_ld32(tO + lane_addr + w * HD + c * 32, o0);
+            for (int c = 0; c < 2; ++c) {                // 32 columns at a time: the score row owns the registers
+              float o0[32];
+              tmem_ld32(tO + lane_addr + w * HD + c * 32, o0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o0[i] *= alpha;
-            tmem_st32(tO + lane_addr + w * HD + c * 32, o0);
+              for (int i = 0; i < 32; ++i) o0[i] *= alpha;
+              tmem_st32(tO + lane_addr + w * HD + c * 32, o0);
+            }
+            tmem_st_wait();
           }
-          tmem_st_wait();
         }
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s[c][i] = fast_exp2(fmaf(s[c][i], p.scale_log2, -m_use));
+            l4[i & 3] += s[c][i];
+          }
+          store_row32(myP, TILE, row, c * 32, s[c]);
+        }
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        tc_fence_before();
+        fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + w);
       }
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};
+      // ---- item epilogue: read O[w], release it, merge the two warpgroups' partial softmax states
+      float o[64];
+      if (u > 0) {
+        mbar_wait(o_full + w, (g_last >> 1) & 1);
+        tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c) {
+          float v[32];
+          tmem_ld32(tO + lane_addr + w * HD + c * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s[c][i] = fast_exp2(fmaf(s[c][i], p.scale_log2, -m_use));
-          l4[i & 3] += s[c][i];
+          for (int i = 0; i < 32; ++i) o[c * 32 + i] = v[i];
         }
-      l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      // this warpgroup's previous P V must have finished reading the P buffer
-      if (u > 0 && !waited) mbar_wait(o_full + w, (u - 1) & 1);
+      } else {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) store_row32(myP, TILE, row, c * 32, s[c]);
+        for (int i = 0; i < 64; ++i) o[i] = 0.f;
+      }
       tc_fence_before();
-      fence_proxy_async();   // make the generic-proxy smem writes visible to the tensor core
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full + w);
-    }
-    float o[64];
-    float m_run = m_use;
-    if (u > 0) {
-      mbar_wait(o_full + w, (u - 1) & 1);
-      tc_fence_after();
+      if (lane == 0) mbar_arrive(o_empty + w);           // the next item's first P V may overwrite O[w]
+      if (w == 1) {
+        // the exchange area is warpgroup 0's P buffer: its last P V of this item must be complete
+        const int gl0 = g0 + nkv - 1 - ((g0 + nkv - 1) & 1);     // last even global tile of the item
+        if (gl0 >= g0) mbar_wait(o_full + 0, (gl0 >> 1) & 1);
+        sML[row] = m_use;
+        sML[128 + row] = l_run;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float v[32];
-        tmem_ld32(tO + lane_addr + w * HD + c * 32, v);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = v[i];
+        for (int i = 0; i < 64; ++i) xch[i * 128 + row] = o[i];
       }
-    } else {
+      named_bar_sync(1, 256);
+      if (w == 0) {
+        const float m1 = sML[row], l1 = sML[128 + row];
+        const float m = fmaxf(m_use, m1);
+        const float a0 = (m_use == -INFINITY) ? 0.f : fast_exp2(m_use - m), a1 = (m1 == -INFINITY) ? 0.f : fast_exp2(m1 - m);
+        const float l = l_run * a0 + l1 * a1;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) o[i] = 0.f;
-    }
-    // merge the two warpgroups' partial softmax states (all P V reads of smem are complete: every
-    // o_full has fired).  Warpgroup 1 publishes (m, l, O) through the P buffers.
-    float *xch = reinterpret_cast<float *>(sP);     // [128 rows][66 floats] = 33 KB of the 64 KB
-    if (w == 1) {
-      // the exchange area overlaps warpgroup 0's P buffer: wait for its last P V as well
-      mbar_wait(o_full + 0, (((nkv + 1) >> 1) - 1) & 1);
-      float *r = xch + row * 66;
-      r[0] = m_run;
-      r[1] = l_run;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) r[2 + i] = o[i];
-    }
-    named_bar_sync(1, 256);
-    if (w == 0) {
-      const float *r = xch + row * 66;
-      const float m1 = r[0], l1 = r[1];
-      const float m = fmaxf(m_run, m1);
-      const float a0 = fast_exp2(m_run - m), a1 = fast_exp2(m1 - m);
-      const float l = l_run * a0 + l1 * a1;
-#pragma unroll
-      for (int i = 0; i < 64; ++i) o[i] = o[i] * a0 + r[2 + i] * a1;
-      const int t = q0 + row;
-      if (t < p.T) {
-        store_out64(p.out + ((size_t)b * p.T + t) * C + h * HD, o, 1.f / l);
-        p.lse[((size_t)b * p.H + h) * p.T + t] = (m + log2f(l)) * LN2;
+        for (int i = 0; i < 64; ++i) o[i] = o[i] * a0 + xch[i * 128 + row] * a1;
+        const int t = qb * TILE + row;
+        if (t < p.T) {
+          store_out64(p.out + ((size_t)b * p.T + t) * C + h * HD, o, 1.f / l);
+          p.lse[((size_t)b * p.H + h) * p.T + t] = (m + log2f(l)) * LN2;
+        }
+        named_bar_sync(2, 128);                          // every warp of warpgroup 0 is done with the exchange area
       }
     }
   }
@@ -787,8 +816,10 @@ int attention_tc_forward(const void *qkv, void *out, float *lse, int B, int T, i
   p.scale_log2 = p.scale * LOG2E;
   p.out = (bf16 *)out;
   p.lse = lse;
-  dim3 grid((T + TILE - 1) / TILE, H, B);
-  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, st>>>(tq, p);
+  const int nqb = (T + TILE - 1) / TILE;
+  const int num_items = nqb * H * B;
+  const int grid = num_items < sm_count() ? num_items : sm_count();
+  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, st>>>(tq, p, num_items, nqb);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }
