@@ -19,6 +19,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v"]
+if os.environ.get("ASIS_TRACE"):      # debug build with in-kernel event stamps (tools/attn_trace.py)
+    FLAGS = FLAGS + ["-DASIS_TRACE"]
 SOURCES = ["api.cu", "msda.cu", "norm.cu", "gemm_f32.cu", "attention_f32.cu", "misc.cu", "gemm_tc.cu", "attention_tc.cu"]
 
 
