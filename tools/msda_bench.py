@@ -39,7 +39,15 @@ def make(N, Lq, M, D, shapes, P, dtype, dev, seed=0):
     return value, ss, lsi, loc.to(dev), aw.to(dev), gout
 
 
+ONCE = bool(os.environ.get("MSDA_ONCE"))      # one call per case: for ncu captures
+
+
 def timeit(fn, iters, flush):
+    if ONCE:
+        flush.zero_()
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
