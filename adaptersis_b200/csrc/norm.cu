@@ -5,6 +5,8 @@
 // LayerNorm: nn.LayerNorm(eps=1e-6) of the reference (dinov2/models/vision_transformer.py:89;
 // backbones/adapter_blocks.py:114).  Column sums: bias gradients of nn.Linear and the LayerScale
 // gamma gradient (dinov2/layers/layer_scale.py:26-27).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace asis {
@@ -155,6 +157,93 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_bwd_kernel(const DT *__re
   }
 }
 
+// v2: a block owns kLn2Rows rows per iteration and a thread owns 4 columns (C <= 1024 = 256 x 4), so
+// the column partials d gamma / d beta are 8 registers instead of 64, every element is read once
+// (row data stays in registers between the row reduction and the dx pass), and the loads of all
+// kLn2Rows rows are in flight together.  Row sums: warp shuffles, then one shared-memory exchange per
+// iteration (double buffered: one __syncthreads per kLn2Rows rows).
+constexpr int kLn2Rows = 4;
+
+template <typename DT, typename XT>
+__global__ void __launch_bounds__(256, 3) ln_bwd2_kernel(const DT *__restrict__ dy, const XT *__restrict__ x,
+                                                      const float *__restrict__ gamma, const float *__restrict__ mean,
+                                                      const float *__restrict__ rstd, const float *__restrict__ dres,
+                                                      float *__restrict__ dx, float *__restrict__ partial, int R, int C) {
+  __shared__ __align__(16) float red[2][kLn2Rows][2][8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = 4 * threadIdx.x;
+  const bool on = c < C;
+  float g[4] = {0.f, 0.f, 0.f, 0.f}, dg[4] = {0.f, 0.f, 0.f, 0.f}, db[4] = {0.f, 0.f, 0.f, 0.f};
+  if (on) load4(gamma + c, g);
+  const float invC = 1.f / (float)C;
+  int buf = 0;
+  for (int row0 = blockIdx.x * kLn2Rows; row0 < R; row0 += gridDim.x * kLn2Rows, buf ^= 1) {
+    float d[kLn2Rows][4], xh[kLn2Rows][4], rr[kLn2Rows][4], rs[kLn2Rows], mu[kLn2Rows];
+#pragma unroll
+    for (int r = 0; r < kLn2Rows; ++r) {
+      const int row = row0 + r;
+      const bool live = on && row < R;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[r][i] = xh[r][i] = rr[r][i] = 0.f;
+      mu[r] = 0.f;
+      rs[r] = 0.f;
+      if (row < R) {
+        mu[r] = __ldg(mean + row);
+        rs[r] = __ldg(rstd + row);
+      }
+      if (live) {
+        load4(dy + (size_t)row * C + c, d[r]);
+        load4(x + (size_t)row * C + c, xh[r]);
+        if (dres) load4(dres + (size_t)row * C + c, rr[r]);
+      }
+    }
+    float s1[kLn2Rows], s2[kLn2Rows];
+#pragma unroll
+    for (int r = 0; r < kLn2Rows; ++r) {
+      s1[r] = s2[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        xh[r][i] = on ? (xh[r][i] - mu[r]) * rs[r] : 0.f;
+        const float t = d[r][i] * g[i];
+        s1[r] += t;
+        s2[r] += t * xh[r][i];
+      }
+      s1[r] = warp_sum(s1[r]);
+      s2[r] = warp_sum(s2[r]);
+      if (lane == 0) {
+        red[buf][r][0][wid] = s1[r];
+        red[buf][r][1][wid] = s2[r];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kLn2Rows; ++r) {
+      const float4 a0 = *reinterpret_cast<const float4 *>(&red[buf][r][0][0]);
+      const float4 a1 = *reinterpret_cast<const float4 *>(&red[buf][r][0][4]);
+      const float4 b0 = *reinterpret_cast<const float4 *>(&red[buf][r][1][0]);
+      const float4 b1 = *reinterpret_cast<const float4 *>(&red[buf][r][1][4]);
+      const float m1 = (((a0.x + a0.y) + (a0.z + a0.w)) + ((a1.x + a1.y) + (a1.z + a1.w))) * invC;
+      const float m2 = (((b0.x + b0.y) + (b0.z + b0.w)) + ((b1.x + b1.y) + (b1.z + b1.w))) * invC;
+      const int row = row0 + r;
+      if (on && row < R) {
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          dg[i] += d[r][i] * xh[r][i];
+          db[i] += d[r][i];
+          o[i] = rs[r] * (d[r][i] * g[i] - m1 - xh[r][i] * m2) + rr[r][i];
+        }
+        store4(dx + (size_t)row * C + c, o);
+      }
+    }
+  }
+  if (on) {
+    float *pg = partial + (size_t)blockIdx.x * 2 * C;
+    store4(pg + c, dg);
+    store4(pg + C + c, db);
+  }
+}
+
 // out[c] (+)= sum over nparts of partial[p][c], fixed order
 // (columns [n, 2n) go to out2 when it is given: dgamma and dbeta of LayerNorm in one launch)
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const float *__restrict__ partial, int nparts, int stride,
@@ -257,8 +346,8 @@ static int ln_nv(int C) {
 }
 
 static int ln_bwd_blocks(int R) {
-  const int want = (R + kLnWarps - 1) / kLnWarps;
-  return want < 592 ? want : 592;  // 4 x 148 SMs
+  const int want = (R + kLn2Rows - 1) / kLn2Rows;
+  return want < 444 ? want : 444;  // 3 resident blocks x 148 SMs (persistent)
 }
 
 }  // namespace asis
@@ -309,7 +398,12 @@ extern "C" int asis_layernorm_backward(const void *dy, int dy_dtype, const void 
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = ln_bwd_blocks(R);
   float *partial = (float *)workspace;
-  ASIS_DISPATCH_DTYPE(dy_dtype, DT, ASIS_DISPATCH_DTYPE(x_dtype, XT, LN_NV_SWITCH(nv, (ln_bwd_kernel<DT, XT, NV><<<blocks, kLnWarps * 32, 0, st>>>((const DT *)dy, (const XT *)x, gamma, mean, rstd, dres, dx, partial, R, C)))));
+  static const bool use_v1 = getenv("ASIS_LN_BWD_V1") != nullptr;   // A/B switch for tools/one_kernel.py
+  if (use_v1) {
+    ASIS_DISPATCH_DTYPE(dy_dtype, DT, ASIS_DISPATCH_DTYPE(x_dtype, XT, LN_NV_SWITCH(nv, (ln_bwd_kernel<DT, XT, NV><<<blocks, kLnWarps * 32, 0, st>>>((const DT *)dy, (const XT *)x, gamma, mean, rstd, dres, dx, partial, R, C)))));
+  } else {
+    ASIS_DISPATCH_DTYPE(dy_dtype, DT, ASIS_DISPATCH_DTYPE(x_dtype, XT, (ln_bwd2_kernel<DT, XT><<<blocks, 256, 0, st>>>((const DT *)dy, (const XT *)x, gamma, mean, rstd, dres, dx, partial, R, C))));
+  }
   ASIS_LAUNCHED();
   if (dgamma && dbeta) {
     reduce_partials_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(partial, blocks, 2 * C, dgamma, dbeta, C, accumulate);

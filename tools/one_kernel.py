@@ -29,5 +29,25 @@ elif which.startswith("attn"):
         dout = torch.randn_like(out)
         for _ in range(3):
             K.attention_backward(BF16, qkv, out, lse, dout, B, T, H, 64)
+elif which == "ln_bwd":
+    x = torch.randn(R, 1024, device=dev)
+    dy = torch.randn(R, 1024, device=dev).bfloat16()
+    dres = torch.randn(R, 1024, device=dev)
+    w = torch.randn(1024, device=dev)
+    b = torch.randn(1024, device=dev)
+    y, mean, rstd = K.layernorm_forward(x, w, b, 1e-6, torch.bfloat16)
+    for _ in range(3):
+        K.layernorm_backward(dy, x, w, mean, rstd, dres)
+    import time
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        K.layernorm_backward(dy, x, w, mean, rstd, dres)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 20
+    nb = R * 1024 * (2 + 4 + 4 + 4)
+    print(f"ln_bwd {t * 1e3:.1f} us  {nb / t / 1e6:.0f} GB/s")
 torch.cuda.synchronize()
 print("done", which)
