@@ -246,23 +246,35 @@ __global__ void __launch_bounds__(256, 3) ln_bwd2_kernel(const DT *__restrict__ 
 
 // out[c] (+)= sum over nparts of partial[p][c], fixed order
 // (columns [n, 2n) go to out2 when it is given: dgamma and dbeta of LayerNorm in one launch)
-__global__ void __launch_bounds__(128) reduce_partials_kernel(const float *__restrict__ partial, int nparts, int stride,
+// block = 32 columns x 8 part-lanes: part-lane y sums parts y, y+8, ... (coalesced 128-byte rows), the
+// 8 part sums are combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__restrict__ partial, int nparts, int stride,
                                                               float *__restrict__ out, float *__restrict__ out2, int n,
                                                               int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= (out2 ? 2 * n : n)) return;
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  const int ncols = out2 ? 2 * n : n;
   float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
-  int p = 0;
-  for (; p + 3 < nparts; p += 4) {
-    t0 += partial[(size_t)p * stride + c];
-    t1 += partial[(size_t)(p + 1) * stride + c];
-    t2 += partial[(size_t)(p + 2) * stride + c];
-    t3 += partial[(size_t)(p + 3) * stride + c];
+  if (c < ncols) {
+    int p = ty;
+    for (; p + 24 < nparts; p += 32) {
+      t0 += partial[(size_t)p * stride + c];
+      t1 += partial[(size_t)(p + 8) * stride + c];
+      t2 += partial[(size_t)(p + 16) * stride + c];
+      t3 += partial[(size_t)(p + 24) * stride + c];
+    }
+    for (; p < nparts; p += 8) t0 += partial[(size_t)p * stride + c];
   }
-  for (; p < nparts; ++p) t0 += partial[(size_t)p * stride + c];
-  const float t = (t0 + t1) + (t2 + t3);
-  float *dst = c < n ? out + c : out2 + (c - n);
-  *dst = accumulate ? *dst + t : t;
+  red[ty][tx] = (t0 + t1) + (t2 + t3);
+  __syncthreads();
+  if (ty == 0 && c < ncols) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w][tx];
+    float *dst = c < n ? out + c : out2 + (c - n);
+    *dst = accumulate ? *dst + t : t;
+  }
 }
 
 // column sums of X (optionally X*Y): block = 32 lanes x 8 row-lanes, lane owns 4 columns
@@ -406,13 +418,13 @@ extern "C" int asis_layernorm_backward(const void *dy, int dy_dtype, const void 
   }
   ASIS_LAUNCHED();
   if (dgamma && dbeta) {
-    reduce_partials_kernel<<<(2 * C + 127) / 128, 128, 0, st>>>(partial, blocks, 2 * C, dgamma, dbeta, C, accumulate);
+    reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, blocks, 2 * C, dgamma, dbeta, C, accumulate);
     ASIS_LAUNCHED();
   } else if (dgamma) {
-    reduce_partials_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, blocks, 2 * C, dgamma, nullptr, C, accumulate);
+    reduce_partials_kernel<<<(C + 31) / 32, 256, 0, st>>>(partial, blocks, 2 * C, dgamma, nullptr, C, accumulate);
     ASIS_LAUNCHED();
   } else if (dbeta) {
-    reduce_partials_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial + C, blocks, 2 * C, dbeta, nullptr, C, accumulate);
+    reduce_partials_kernel<<<(C + 31) / 32, 256, 0, st>>>(partial + C, blocks, 2 * C, dbeta, nullptr, C, accumulate);
     ASIS_LAUNCHED();
   }
   return ASIS_OK;
@@ -445,7 +457,7 @@ extern "C" int asis_colsum(const void *X, int x_dtype, const void *Y, int y_dtyp
     ASIS_DISPATCH_DTYPE(x_dtype, XT, (colsum_kernel<XT, float, false><<<grid, 256, 0, st>>>((const XT *)X, nullptr, ld, partial, M, N)));
   }
   ASIS_LAUNCHED();
-  reduce_partials_kernel<<<(N + 127) / 128, 128, 0, st>>>(partial, rb, N, out, nullptr, N, accumulate);
+  reduce_partials_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial, rb, N, out, nullptr, N, accumulate);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }

@@ -28,6 +28,17 @@ METRIC = "ViT-L/14-adapter 588^2 train images/s"
 UNIT = "images/s"
 
 
+def ncu_traffic(key):
+    """DRAM bytes of one representative launch of the kernel family `key`, from the committed ncu capture
+    (profiles/ncu_traffic.json); None when there is no capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]
+        return {"dram_bytes_per_launch": t["dram_bytes"], "algorithmic_bytes": t["algorithmic_bytes"],
+                "launch": t["launch"], "source": t["source"]}
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -317,6 +328,11 @@ def run_ours(args, rank, world, local_rank):
 
     peak_tf = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     roof = tensor_roof(["gemm_bf16"], peak_tf) or tensor_roof(["gemm_f32"], peak_tf)
+    if roof is not None and "gemm_bf16" in agg:
+        tr = ncu_traffic("gemm_bf16")
+        if tr is not None:      # bytes of ONE captured launch (dram__bytes_read + write), with its algorithmic bytes beside it
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_detail"] = tr
     table = {k: {"n": v["n"], "ms": round(v["ms"], 3)} for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
     print("[bench] per-op time inside one profiled step (ms):", json.dumps(table), file=sys.stderr)
     print(f"[bench] profiled step {prof_step_ms:.1f} ms; timed step {t_ms / args.steps:.1f} ms", file=sys.stderr)
