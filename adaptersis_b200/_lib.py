@@ -46,6 +46,8 @@ SIGNATURES = {
     "asis_attention_backward_workspace_bytes": (_Z, [_I] * 5),
     "asis_attention_backward": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "asis_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _L, _P]),
+    "asis_upsample2x_bilinear_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "asis_upsample2x_bilinear_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "asis_dwconv3x3_forward": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P]),
     "asis_dwconv3x3_backward_workspace_bytes": (_Z, [_I, _I, _I]),
     "asis_dwconv3x3_backward": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),

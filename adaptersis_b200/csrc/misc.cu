@@ -4,6 +4,8 @@
 //   dwconv   <- DWConv.forward (backbones/adapter_blocks.py:62-80): the reference transposes each
 //               pyramid level to NCHW, runs cuDNN, transposes back; here the conv runs directly
 //               on the [B, tokens, C] layout (channels are the contiguous dimension).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace asis {
@@ -209,6 +211,125 @@ static int dwconv_row_blocks(int64_t rows) {
   return (int)rb;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Bilinear 2x upsampling, align_corners=True, channels-last (the four nn.Upsample layers of
+// FeatureDecoder, backbones/decoders.py:104-127).  HBM-bound: one thread per (output pixel, 16-byte
+// channel vector) forward; the backward is a gather per INPUT pixel over the few output pixels whose
+// footprint contains it (no atomics, fixed order).  Source index = dst * (in-1)/(out-1), as ATen's
+// area_pixel_compute_source_index(align_corners=True).
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Up2Vec;
+template <> struct Up2Vec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float *p, float (&v)[4]) { load4(p, v); }
+  static __device__ __forceinline__ void store(float *p, const float (&v)[4]) { store4(p, v); }
+};
+template <> struct Up2Vec<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16 *p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(bf16 *p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+struct Up2Src {
+  int i0, i1;
+  float l;   // weight of i1; 1 - l of i0
+};
+__device__ __forceinline__ Up2Src up2_src(int o, float scale, int in) {
+  const float s = scale * (float)o;
+  Up2Src r;
+  r.i0 = min((int)s, in - 1);
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l = s - (float)r.i0;
+  return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int B, int H,
+                                                             int W, int C, float sy, float sx) {
+  constexpr int N = Up2Vec<T>::N;
+  const int CV = C / N, OH = 2 * H, OW = 2 * W;
+  const size_t total = (size_t)B * OH * OW * CV;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    size_t r = t / CV;
+    const int ox = (int)(r % OW);
+    r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    const Up2Src ys = up2_src(oy, sy, H), xs = up2_src(ox, sx, W);
+    const T *xb = x + (size_t)b * H * W * C + (size_t)cv * N;
+    float v00[N], v01[N], v10[N], v11[N], o[N];
+    Up2Vec<T>::load(xb + ((size_t)ys.i0 * W + xs.i0) * C, v00);
+    Up2Vec<T>::load(xb + ((size_t)ys.i0 * W + xs.i1) * C, v01);
+    Up2Vec<T>::load(xb + ((size_t)ys.i1 * W + xs.i0) * C, v10);
+    Up2Vec<T>::load(xb + ((size_t)ys.i1 * W + xs.i1) * C, v11);
+    const float w00 = (1.f - ys.l) * (1.f - xs.l), w01 = (1.f - ys.l) * xs.l, w10 = ys.l * (1.f - xs.l), w11 = ys.l * xs.l;
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[i] = w00 * v00[i] + w01 * v01[i] + w10 * v10[i] + w11 * v11[i];
+    Up2Vec<T>::store(y + t * N, o);
+  }
+}
+
+// weights with which output index o reads input index i (0 if it does not)
+__device__ __forceinline__ float up2_weight(int o, int i, float scale, int in) {
+  const Up2Src s = up2_src(o, scale, in);
+  return (s.i0 == i ? 1.f - s.l : 0.f) + (s.i1 == i ? s.l : 0.f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T *__restrict__ gy, T *__restrict__ gx, int B, int H,
+                                                             int W, int C, float sy, float sx) {
+  constexpr int N = Up2Vec<T>::N;
+  const int CV = C / N, OH = 2 * H, OW = 2 * W;
+  const size_t total = (size_t)B * H * W * CV;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    size_t r = t / CV;
+    const int ix = (int)(r % W);
+    r /= W;
+    const int iy = (int)(r % H);
+    const int b = (int)(r / H);
+    // output rows / columns that can touch this input pixel: src in (i - 1, i + 1)  ->  a window of at
+    // most 6 around 2 i (scale is just below 1/2); exact membership is decided by up2_weight
+    const int oy_lo = max(0, 2 * iy - 3), oy_hi = min(OH - 1, 2 * iy + 4);
+    const int ox_lo = max(0, 2 * ix - 3), ox_hi = min(OW - 1, 2 * ix + 4);
+    float acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+    const T *gb = gy + (size_t)b * OH * OW * C + (size_t)cv * N;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const float wy = up2_weight(oy, iy, sy, H);
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const float w = wy * up2_weight(ox, ix, sx, W);
+        if (w == 0.f) continue;
+        float v[N];
+        Up2Vec<T>::load(gb + ((size_t)oy * OW + ox) * C, v);
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+      }
+    }
+    Up2Vec<T>::store(gx + t * N, acc);
+  }
+}
+
 }  // namespace asis
 
 using namespace asis;
@@ -271,6 +392,37 @@ extern "C" int asis_dwconv3x3_backward(const void *dy, const void *pre, const vo
   ASIS_DISPATCH_DTYPE(dtype, T, (dwconv_bwd_kernel<T><<<grid, 256, 0, st>>>((const T *)dy, (const T *)pre, (const T *)x, weight, (T *)dx, partial, B, C, ntok, mp, fuse_gelu)));
   ASIS_LAUNCHED();
   dwconv_reduce_kernel<<<(10 * C + 255) / 256, 256, 0, st>>>(partial, rb, C, dweight, dbias, accumulate);
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+static int up2_check(const void *a, const void *b, int dtype, int B, int H, int W, int C) {
+  ASIS_REQUIRE(a && b, "upsample2x: null pointer");
+  ASIS_REQUIRE(dtype_ok(dtype), "upsample2x: bad dtype");
+  ASIS_REQUIRE(B > 0 && H > 1 && W > 1 && C > 0, "upsample2x: need B > 0, H > 1, W > 1, C > 0");
+  ASIS_REQUIRE(C % (dtype == ASIS_BF16 ? 8 : 4) == 0, "upsample2x: C=%d must be a multiple of %d", C, dtype == ASIS_BF16 ? 8 : 4);
+  ASIS_REQUIRE(aligned16(a) && aligned16(b), "upsample2x: pointers must be 16-byte aligned");
+  return ASIS_OK;
+}
+
+extern "C" int asis_upsample2x_bilinear_forward(const void *x, void *y, int dtype, int B, int H, int W, int C, void *stream) {
+  if (int rc = up2_check(x, y, dtype, B, H, W, C)) return rc;
+  const float sy = (float)(H - 1) / (float)(2 * H - 1), sx = (float)(W - 1) / (float)(2 * W - 1);
+  const size_t total = (size_t)B * 4 * H * W * (C / (dtype == ASIS_BF16 ? 8 : 4));
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(dtype, T, (upsample2x_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)x, (T *)y, B, H, W, C, sy, sx)));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_upsample2x_bilinear_backward(const void *gy, void *gx, int dtype, int B, int H, int W, int C, void *stream) {
+  if (int rc = up2_check(gy, gx, dtype, B, H, W, C)) return rc;
+  const float sy = (float)(H - 1) / (float)(2 * H - 1), sx = (float)(W - 1) / (float)(2 * W - 1);
+  const size_t total = (size_t)B * H * W * (C / (dtype == ASIS_BF16 ? 8 : 4));
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(dtype, T, (upsample2x_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)gy, (T *)gx, B, H, W, C, sy, sx)));
   ASIS_LAUNCHED();
   return ASIS_OK;
 }

@@ -436,3 +436,23 @@ class DWConvFunction(Function):
         maps, fuse_gelu = ctx.meta
         dx, dw, db = K.dwconv3x3_backward(dy, pre, x, weight, maps, fuse_gelu)
         return dx, dw.view(weight.shape).to(weight.dtype), db, None, None
+
+
+class Upsample2xFunction(Function):
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) of FeatureDecoder
+    (backbones/decoders.py:104-127) on an NCHW tensor, computed channels-last by the CUDA kernels."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xh = x.permute(0, 2, 3, 1).contiguous()          # no copy when x is channels_last
+        return K.upsample2x_forward(xh).permute(0, 3, 1, 2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        gh = gy.permute(0, 2, 3, 1).contiguous()
+        return K.upsample2x_backward(gh).permute(0, 3, 1, 2)
+
+
+def upsample2x(x):
+    return Upsample2xFunction.apply(x)

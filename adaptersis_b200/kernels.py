@@ -303,3 +303,27 @@ def dwconv3x3_backward(dy, pre, x, weight, maps, fuse_gelu):
                                       ptr(db), 0, B, C, len(maps), hs, ws_, int(fuse_gelu), ptr(ws), nbytes,
                                       stream()))
     return dx, dw, db
+
+
+# ------------------------------------------------------------------------------------------ decoder
+def upsample2x_forward(x_nhwc):
+    """x [B, H, W, C] contiguous -> [B, 2H, 2W, C]; bilinear, align_corners=True."""
+    need_cuda(x_nhwc)
+    B, H, W, C = x_nhwc.shape
+    y = torch.empty(B, 2 * H, 2 * W, C, dtype=x_nhwc.dtype, device=x_nhwc.device)
+    nb = x_nhwc.element_size() * B * H * W * C * 5
+    with _Span("upsample2x_fwd", nb, "B"):
+        check(_lib.load().asis_upsample2x_bilinear_forward(ptr(x_nhwc), ptr(y), dt(x_nhwc), B, H, W, C, stream()))
+    return y
+
+
+def upsample2x_backward(gy_nhwc):
+    """gy [B, 2H, 2W, C] contiguous -> gx [B, H, W, C]."""
+    need_cuda(gy_nhwc)
+    B, OH, OW, C = gy_nhwc.shape
+    gx = torch.empty(B, OH // 2, OW // 2, C, dtype=gy_nhwc.dtype, device=gy_nhwc.device)
+    nb = gy_nhwc.element_size() * B * (OH // 2) * (OW // 2) * C * 5
+    with _Span("upsample2x_bwd", nb, "B"):
+        check(_lib.load().asis_upsample2x_bilinear_backward(ptr(gy_nhwc), ptr(gx), dt(gy_nhwc), B, OH // 2, OW // 2, C,
+                                                            stream()))
+    return gx

@@ -192,6 +192,15 @@ int asis_dwconv3x3_backward(const void *dy, const void *pre, const void *x, int 
                             const int *ws_host, int fuse_gelu, void *workspace,
                             size_t workspace_bytes, void *stream);
 
+/* Bilinear 2x upsampling with align_corners=True on channels-last tensors: the nn.Upsample layers of
+ * FeatureDecoder (backbones/decoders.py:104-127; SURVEY.md 8f rank 2, the step after the hot path).
+ *   x [B, H, W, C] -> y [B, 2H, 2W, C];  backward: gy [B, 2H, 2W, C] -> gx [B, H, W, C] (gather, no atomics).
+ *   C must be a multiple of 4 (f32) / 8 (bf16). */
+int asis_upsample2x_bilinear_forward(const void *x, void *y, int dtype, int B, int H, int W, int C,
+                                     void *stream);
+int asis_upsample2x_bilinear_backward(const void *gy, void *gx, int dtype, int B, int H, int W, int C,
+                                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -135,3 +135,21 @@ def test_patchify_and_dwconv():
         assert relerr(y, ref) < TOL
         hx, hw, hb = torch.autograd.grad(y, (x2, w2, b2), dy)
         assert relerr(hx, gx) < TOL and relerr(hw, gw) < TOL and relerr(hb, gb) < TOL
+
+
+@pytest.mark.parametrize("B,C,H,W,dtype", [(2, 64, 21, 21, torch.float32), (1, 16, 7, 5, torch.float32),
+                                           (2, 64, 42, 42, torch.bfloat16), (1, 8, 3, 2, torch.bfloat16)])
+def test_upsample2x_matches_torch(B, C, H, W, dtype):
+    # FeatureDecoder's nn.Upsample(scale_factor=2, bilinear, align_corners=True): forward and backward
+    from adaptersis_b200 import functional as Fn
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, C, H, W, generator=g).to(DEV, dtype).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    gy = torch.randn(B, C, 2 * H, 2 * W, generator=g).to(DEV, dtype)
+    y = Fn.upsample2x(x)
+    (gx,) = torch.autograd.grad(y, x, gy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = torch.nn.functional.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True)
+    (gxr,) = torch.autograd.grad(yr, xr, gy.float())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert y.shape == yr.shape and relerr(y.float(), yr) < tol
+    assert relerr(gx.float(), gxr) < tol

@@ -19,14 +19,19 @@ def alg_bytes(N, S, M, D, Lq, L, P, ev, eo):
     return fwd, bwd
 
 
-def make(N, Lq, M, D, shapes, P, dtype, dev, seed=0):
+def make(N, Lq, M, D, shapes, P, dtype, dev, seed=0, qgrids=None):
     g = torch.Generator(device="cpu").manual_seed(seed)
     L = len(shapes)
     S = sum(h * w for h, w in shapes)
     value = torch.randn(N, S, M, D, generator=g).to(dev, dtype)
     side = int(Lq ** 0.5)
     qi = torch.arange(Lq)
-    ref = torch.stack([((qi % side).float() + 0.5) / side, ((qi // side).float().clamp(max=side - 1) + 0.5) / side], -1)
+    if qgrids and sum(h * w for h, w in qgrids) == Lq and len(qgrids) > 1 and qgrids[-1][0] > 1:
+        # queries = several row-major grids over the same image, laid end to end (the extractor's pyramid)
+        ref = torch.cat([torch.stack([((torch.arange(h * w) % w).float() + 0.5) / w,
+                                      ((torch.arange(h * w) // w).float() + 0.5) / h], -1) for h, w in qgrids])
+    else:
+        ref = torch.stack([((qi % side).float() + 0.5) / side, ((qi // side).float().clamp(max=side - 1) + 0.5) / side], -1)
     loc = ref.view(1, Lq, 1, 1, 1, 2).expand(N, Lq, M, L, P, 2).clone()
     for l, (H, W) in enumerate(shapes):
         loc[:, :, :, l] += (torch.rand(N, Lq, M, P, 2, generator=g) * 8 - 4) / torch.tensor([W, H], dtype=torch.float32)
@@ -84,13 +89,16 @@ def main():
         if only and only not in name:
             continue
         for dtype in (torch.float32, torch.bfloat16):
-            v, ss, lsi, loc, aw, gout = make(N, Lq, M, D, shapes, P, dtype, dev)
+            side = int(Lq ** 0.5)
+            qs = [(73, 73), (36, 36), (18, 18)] if name == "extractor_real" else \
+                ([(side, side)] + ([(1, Lq - side * side)] if Lq > side * side else []))
+            v, ss, lsi, loc, aw, gout = make(N, Lq, M, D, shapes, P, dtype, dev, qgrids=qs)
             S = v.shape[1]
             e = 4 if dtype == torch.float32 else 2
             fb, bb = alg_bytes(N, S, M, D, Lq, len(shapes), P, e, e)
             tf = timeit(lambda: K.msda_forward(v, ss, lsi, loc, aw), 10, flush)
             tb = timeit(lambda: K.msda_backward(v, ss, lsi, loc, aw, gout), 10, flush)
-            row = dict(case=name, dtype=str(dtype).split(".")[-1], N=N, Lq=Lq, S=S, M=M, D=D,
+            row = dict(case=name, dtype=str(dtype).split(".")[-1], N=N, Lq=Lq, S=S, M=M, D=D, query_grids=qs,
                        fwd_ms=round(tf, 4), fwd_GBs=round(fb / tf / 1e6, 1), fwd_frac=round(fb / tf / 1e6 / peak, 3),
                        bwd_ms=round(tb, 4), bwd_GBs=round(bb / tb / 1e6, 1), bwd_frac=round(bb / tb / 1e6 / peak, 3))
             rows.append(row)
