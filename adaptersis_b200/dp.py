@@ -78,10 +78,13 @@ class BucketedGradAllReduce:
         else:
             import contextlib
             ctx = contextlib.nullcontext()
+        # NCCL averages inside the collective; other backends (gloo in the CPU tests) sum and divide after
+        avg_in_op = self.average and dev.type == "cuda" and dist.get_backend(self.group) == "nccl"
         with ctx:
-            torch._foreach_copy_(list(flat.split([p.numel() for p in bucket])), [p.grad.reshape(-1).float() for p in bucket])
-            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-        self._works.append((bucket, flat, work))
+            torch._foreach_copy_(list(flat.split([p.numel() for p in bucket])), [p.grad.reshape(-1) for p in bucket])
+            work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg_in_op else dist.ReduceOp.SUM, group=self.group,
+                                   async_op=True)
+        self._works.append((bucket, flat, work, avg_in_op))
 
     def finish(self):
         """Wait for all buckets, write the reduced (averaged) gradients back."""
@@ -91,12 +94,14 @@ class BucketedGradAllReduce:
         for i, left in enumerate(self._pending):
             if left != 0:
                 self._launch(i, partial=True)
-        for bucket, flat, work in self._works:
+        for bucket, flat, work, averaged in self._works:
             work.wait()
-            if self.average:
+            if self.average and not averaged:
                 flat.div_(self.world)
-            for p, chunk in zip(bucket, flat.split([p.numel() for p in bucket])):
-                p.grad.copy_(chunk.view_as(p.grad))
+            # one multi-tensor copy per bucket (a per-parameter loop costs ~420 launches per step)
+            torch._foreach_copy_([p.grad.view(-1) if p.grad.is_contiguous() else p.grad for p in bucket],
+                                 [c.view_as(p.grad) if not p.grad.is_contiguous() else c
+                                  for p, c in zip(bucket, flat.split([p.numel() for p in bucket]))])
         if self._comm_stream is not None:
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         self.reset()
