@@ -48,7 +48,9 @@ class TrainStep(nn.Module):
                 p.requires_grad_(False)
         params = [p for p in self.parameters() if p.requires_grad]
         # reference: SGD(momentum=0.99, weight_decay=3e-5), train.py:178-189
-        self.optimizer = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay, foreach=True)
+        on_cuda = torch.device(device).type == "cuda"
+        self.optimizer = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay,
+                                         **({"fused": True} if on_cuda else {"foreach": True}))
         self.reducer = BucketedGradAllReduce(params, bucket_bytes=bucket_bytes)
         self.device = torch.device(device)
 
