@@ -323,7 +323,10 @@ class BlockFunction(Function):
         x2 = x.reshape(R, C)
         x2 = x2 if x2.dtype == torch.float32 else x2.float()
         hd = C // num_heads
-        save_u = [g1 is not None and g1.requires_grad, g2 is not None and g2.requires_grad]
+        # forward-only calls (the taps pass runs under no_grad: nothing needs a gradient) skip the tensors
+        # that exist only for backward: the GELU pre-activation and the LayerScale branch outputs
+        track = any(ctx.needs_input_grad)
+        save_u = [track and g1 is not None and g1.requires_grad, track and g2 is not None and g2.requires_grad]
         gam1 = _f32(g1) if g1 is not None else _ones(C, dev)
         gam2 = _f32(g2) if g2 is not None else _ones(C, dev)
 
@@ -336,7 +339,7 @@ class BlockFunction(Function):
         y2, mean2, rstd2 = K.layernorm_forward(x1, _f32(n2w), _f32(n2b), eps, cdt)
         Hd = fc1_w.shape[0]
         g, h = K.gemm(comp, y2, MAJOR_K, _operand(fc1_w, cdt), MAJOR_K, R, Hd, C, cdt, epilogue=EPI_GELU,
-                      bias=_f32(fc1_b), want_aux_dtype=cdt)
+                      bias=_f32(fc1_b), want_aux_dtype=cdt if track else None)
         out, u2 = K.gemm(comp, g, MAJOR_K, _operand(fc2_w, cdt), MAJOR_K, R, C, Hd, torch.float32,
                          epilogue=EPI_SCALE_RESIDUAL, bias=_f32(fc2_b), gamma=gam2, residual=x1,
                          want_aux_dtype=cdt if save_u[1] else None)
