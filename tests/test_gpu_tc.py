@@ -166,3 +166,46 @@ def test_attention_run_to_run_identical():
         assert torch.equal(out, out0) and torch.equal(lse, lse0), f"forward differs at repeat {i}"
         if i % 5 == 0:
             assert torch.equal(K.attention_backward(BF16, qkv, out0, lse0, dout, B, T, H, 64), g0), f"backward differs at repeat {i}"
+
+
+def test_full_size_batch_independence():
+    """BASELINE.json's full sizes (ViT-L width, 1765 tokens, 12 images; the injector's MSDA shape): a
+    size-independent property the reference has by construction -- every image is processed on its
+    own -- checked bit for bit: the 12-image call equals two 6-image calls, for the block's outputs
+    and input gradients and for the deformable attention's output and all three gradients."""
+    torch.manual_seed(7)
+    blk = asis.Block(dim=1024, num_heads=16, qkv_bias=True, init_values=1e-5, attn_class=asis.MemEffAttention).to(DEV)
+    with torch.no_grad():
+        blk.ls1.gamma.normal_(0.5, 0.2)
+        blk.ls2.gamma.normal_(0.5, 0.2)
+    x = torch.randn(12, 1765, 1024, device=DEV)
+    gy = torch.randn(12, 1765, 1024, device=DEV)
+    with asis.precision("bf16"):
+        def run(xs, gs):
+            xx = xs.clone().requires_grad_(True)
+            y = blk(xx)
+            (gx,) = torch.autograd.grad(y, xx, gs)
+            return y, gx
+        y12, g12 = run(x, gy)
+        ya, ga = run(x[:6], gy[:6])
+        yb, gb = run(x[6:], gy[6:])
+    assert torch.isfinite(y12).all() and torch.isfinite(g12).all()
+    assert torch.equal(y12, torch.cat([ya, yb])) and torch.equal(g12, torch.cat([ga, gb]))
+
+    shapes = [(73, 73), (36, 36), (18, 18)]
+    g = torch.Generator().manual_seed(8)
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(12, S, 8, 128, generator=g).to(DEV).bfloat16()
+    loc = (torch.rand(12, 1764, 8, 3, 4, 2, generator=g) * 1.1 - 0.05).to(DEV)
+    aw = torch.softmax(torch.randn(12, 1764, 8, 12, generator=g), -1).view(12, 1764, 8, 3, 4).to(DEV)
+    gout = torch.randn(12, 1764, 1024, generator=g).to(DEV).bfloat16()
+    ss = torch.as_tensor(shapes, dtype=torch.long, device=DEV)
+    lsi = torch.cat([ss.new_zeros(1), ss.prod(1).cumsum(0)[:-1]])
+    o12 = K.msda_forward(value, ss, lsi, loc, aw)
+    b12 = K.msda_backward(value, ss, lsi, loc, aw, gout)
+    for sl in (slice(0, 6), slice(6, 12)):
+        o = K.msda_forward(value[sl], ss, lsi, loc[sl], aw[sl])
+        b = K.msda_backward(value[sl], ss, lsi, loc[sl], aw[sl], gout[sl])
+        assert torch.equal(o12[sl], o)
+        for t12, t in zip(b12, b):
+            assert torch.equal(t12[sl], t)
