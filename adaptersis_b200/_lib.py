@@ -38,6 +38,8 @@ SIGNATURES = {
     "asis_gemm": (_I, [_I, _P, _I, _L, _P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _P, _P, _P, _P, _I, _L, _P]),
     "asis_colsum_workspace_bytes": (_Z, [_I, _I]),
     "asis_colsum": (_I, [_P, _I, _P, _I, _L, _P, _I, _I, _I, _P, _Z, _P]),
+    "asis_layerscale_backward_workspace_bytes": (_Z, [_I, _I]),
+    "asis_layerscale_backward": (_I, [_P, _P, _P, _P, _I, _P, _P, _I, _I, _P, _Z, _P]),
     "asis_scale_cols": (_I, [_P, _I, _P, _P, _I, _L, _I, _P]),
     "asis_add": (_I, [_P, _I, _P, _I, _P, _I, _L, _P]),
     "asis_cast": (_I, [_P, _I, _P, _I, _L, _P]),

@@ -312,6 +312,54 @@ __global__ void __launch_bounds__(256) colsum_kernel(const XT *__restrict__ X, c
   }
 }
 
+// LayerScale backward in one pass over the incoming gradient d [M, N] (f32):
+//   du = d * gamma (compute dtype: the gradient of the branch output, next GEMM's operand),
+//   partial column sums of d * u (-> d gamma) and of du as stored (-> bias gradient of the branch's last Linear).
+// Replaces scale_cols + colsum(d, u) + colsum(du): d is read once instead of twice, du is not re-read.
+// block = 32 lanes x 8 row-lanes, lane owns 4 columns; partial[blockIdx.y][2][N].
+template <typename UT>
+__global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float *__restrict__ d, const UT *__restrict__ u,
+                                                             const float *__restrict__ gamma, UT *__restrict__ du,
+                                                             float *__restrict__ partial, int M, int N) {
+  __shared__ float red[8][132];
+  const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + lane * 4;
+  float ag[4] = {0, 0, 0, 0}, ab[4] = {0, 0, 0, 0};
+  if (c < N) {
+    float g[4];
+    load4(gamma + c, g);
+    for (int r = blockIdx.y * 8 + ty; r < M; r += gridDim.y * 8) {
+      float dv[4], o[4];
+      load4(d + (size_t)r * N + c, dv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = to_f(from_f<UT>(dv[i] * g[i]));    // as the next GEMM will see it
+      store4(du + (size_t)r * N + c, o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) ab[i] += o[i];
+      if (u) {
+        float uv[4];
+        load4(u + (size_t)r * N + c, uv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ag[i] += dv[i] * uv[i];
+      }
+    }
+  }
+  float *pg = partial + (size_t)blockIdx.y * 2 * N;
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) red[ty][lane * 4 + i] = pass == 0 ? ag[i] : ab[i];
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+      const int cc = blockIdx.x * 128 + threadIdx.x;
+      if (cc < N) pg[pass * N + cc] = t;
+    }
+  }
+}
+
 template <typename AT, typename OT>
 __global__ void __launch_bounds__(256) scale_cols_kernel(const AT *__restrict__ a, const float *__restrict__ gamma,
                                                          OT *__restrict__ out, int64_t M, int N) {
@@ -459,6 +507,37 @@ extern "C" int asis_colsum(const void *X, int x_dtype, const void *Y, int y_dtyp
   ASIS_LAUNCHED();
   reduce_partials_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial, rb, N, out, nullptr, N, accumulate);
   ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" size_t asis_layerscale_backward_workspace_bytes(int M, int N) { return (size_t)colsum_rb(M) * 2 * N * sizeof(float); }
+
+extern "C" int asis_layerscale_backward(const float *d, const void *u, const float *gamma, void *du, int dtype,
+                                        float *dgamma, float *dbias, int M, int N, void *workspace,
+                                        size_t workspace_bytes, void *stream) {
+  ASIS_REQUIRE(d && gamma && du && workspace, "layerscale_backward: null pointer");
+  ASIS_REQUIRE(dtype_ok(dtype), "layerscale_backward: bad dtype");
+  ASIS_REQUIRE(!dgamma || u, "layerscale_backward: d gamma needs the saved branch output u");
+  ASIS_REQUIRE(M > 0 && N > 0 && N % 4 == 0, "layerscale_backward: N=%d must be a multiple of 4", N);
+  const size_t need = asis_layerscale_backward_workspace_bytes(M, N);
+  if (workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "layerscale_backward: workspace %zu < %zu bytes", workspace_bytes, need);
+  ASIS_REQUIRE(aligned16(d) && aligned16(du) && aligned16(gamma) && (!u || aligned16(u)), "layerscale_backward: pointers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rb = colsum_rb(M);
+  dim3 grid((N + 127) / 128, rb);
+  float *partial = (float *)workspace;
+  ASIS_DISPATCH_DTYPE(dtype, UT, (layerscale_bwd_kernel<UT><<<grid, 256, 0, st>>>(d, dgamma ? (const UT *)u : nullptr, gamma, (UT *)du, partial, M, N)));
+  ASIS_LAUNCHED();
+  if (dgamma && dbias) {
+    reduce_partials_kernel<<<(2 * N + 31) / 32, 256, 0, st>>>(partial, rb, 2 * N, dgamma, dbias, N, 0);
+    ASIS_LAUNCHED();
+  } else if (dgamma) {
+    reduce_partials_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial, rb, 2 * N, dgamma, nullptr, N, 0);
+    ASIS_LAUNCHED();
+  } else if (dbias) {
+    reduce_partials_kernel<<<(N + 31) / 32, 256, 0, st>>>(partial + N, rb, 2 * N, dbias, nullptr, N, 0);
+    ASIS_LAUNCHED();
+  }
   return ASIS_OK;
 }
 

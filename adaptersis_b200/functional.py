@@ -363,15 +363,23 @@ class BlockFunction(Function):
         d2 = d2 if d2.dtype == torch.float32 else d2.float()
 
         # ---- MLP branch
-        dg2 = K.colsum(d2, u2) if (g2 is not None and ni[14]) else None
-        du2 = K.scale_cols(d2, _f32(g2), cdt) if g2 is not None else K.cast(d2, cdt)
-        dh, dfc2_w, dfc2_b = _linear_backward(comp, cdt, du2, g, fc2_w, True, ni[12], hb_fc2 and ni[13], dgelu_aux=h)
+        if g2 is not None:      # LayerScale backward: du, d gamma and the fc2 bias gradient in one pass over d2
+            du2, dg2, dfc2_b = K.layerscale_backward(d2, u2, _f32(g2), cdt, ni[14] and u2 is not None, hb_fc2 and ni[13])
+            dh, dfc2_w, _ = _linear_backward(comp, cdt, du2, g, fc2_w, True, ni[12], False, dgelu_aux=h)
+        else:
+            dg2 = None
+            du2 = K.cast(d2, cdt)
+            dh, dfc2_w, dfc2_b = _linear_backward(comp, cdt, du2, g, fc2_w, True, ni[12], hb_fc2 and ni[13], dgelu_aux=h)
         dy2, dfc1_w, dfc1_b = _linear_backward(comp, cdt, dh, y2, fc1_w, True, ni[10], hb_fc1 and ni[11])
         dx1, dn2w, dn2b = K.layernorm_backward(dy2, x1, _f32(n2w), mean2, rstd2, d2, ni[8] or ni[9])
         # ---- attention branch
-        dg1 = K.colsum(dx1, u1) if (g1 is not None and ni[7]) else None
-        du1 = K.scale_cols(dx1, _f32(g1), cdt) if g1 is not None else K.cast(dx1, cdt)
-        do, dproj_w, dproj_b = _linear_backward(comp, cdt, du1, o.view(R, C), proj_w, True, ni[5], hb_proj and ni[6])
+        if g1 is not None:
+            du1, dg1, dproj_b = K.layerscale_backward(dx1, u1, _f32(g1), cdt, ni[7] and u1 is not None, hb_proj and ni[6])
+            do, dproj_w, _ = _linear_backward(comp, cdt, du1, o.view(R, C), proj_w, True, ni[5], False)
+        else:
+            dg1 = None
+            du1 = K.cast(dx1, cdt)
+            do, dproj_w, dproj_b = _linear_backward(comp, cdt, du1, o.view(R, C), proj_w, True, ni[5], hb_proj and ni[6])
         dqkv = K.attention_backward(comp, qkv.view(B, T, 3 * C), o, lse, do.view(B, T, C), B, T, H, hd).view(R, 3 * C)
         dy1, dqkv_w, dqkv_b = _linear_backward(comp, cdt, dqkv, y1, qkv_w, True, ni[3], hb_qkv and ni[4])
         dx, dn1w, dn1b = K.layernorm_backward(dy1, x2, _f32(n1w), mean1, rstd1, dx1, ni[1] or ni[2])

@@ -210,6 +210,26 @@ def scale_cols(a2d, gamma, out_dtype):
     return out
 
 
+def layerscale_backward(d2d, u2d, gamma, out_dtype, want_dgamma, want_dbias):
+    """d [M, N] f32 -> du = d * gamma (out_dtype), dgamma = colsum(d * u), dbias = colsum(du) (f32 or None)."""
+    M, N = d2d.shape
+    lib = _lib.load()
+    d2d = _c(d2d)
+    dev = d2d.device
+    du = torch.empty(M, N, dtype=out_dtype, device=dev)
+    dgamma = torch.empty(N, dtype=torch.float32, device=dev) if want_dgamma else None
+    dbias = torch.empty(N, dtype=torch.float32, device=dev) if want_dbias else None
+    u = _c(u2d) if (want_dgamma and u2d is not None) else None
+    assert u is None or u.dtype == out_dtype
+    nbytes = lib.asis_layerscale_backward_workspace_bytes(M, N)
+    ws = workspace(nbytes, dev)
+    nb = M * N * (4 + du.element_size() + (u.element_size() if u is not None else 0))
+    with _Span("layerscale_bwd", nb, "B"):
+        check(lib.asis_layerscale_backward(ptr(d2d), ptr(u), ptr(gamma), ptr(du), dt(du), ptr(dgamma), ptr(dbias), M, N,
+                                           ptr(ws), nbytes, stream()))
+    return du, dgamma, dbias
+
+
 def add(a, b, out_dtype):
     a = _c(a)
     b = _c(b)

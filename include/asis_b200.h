@@ -201,6 +201,15 @@ int asis_upsample2x_bilinear_forward(const void *x, void *y, int dtype, int B, i
 int asis_upsample2x_bilinear_backward(const void *gy, void *gx, int dtype, int B, int H, int W, int C,
                                       void *stream);
 
+/* LayerScale backward (dinov2/layers/layer_scale.py:26-27 behind x + ls(branch(x)), block.py:112-113) in
+ * one pass over the incoming gradient d [M, N] f32:  du = d * gamma (dtype, the branch-output gradient),
+ * dgamma = colsum(d * u) (optional, needs the saved branch output u), dbias = colsum(du) (optional: the
+ * bias gradient of the branch's last nn.Linear). */
+size_t asis_layerscale_backward_workspace_bytes(int M, int N);
+int asis_layerscale_backward(const float *d, const void *u, const float *gamma, void *du, int dtype,
+                             float *dgamma, float *dbias, int M, int N, void *workspace,
+                             size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
