@@ -1,7 +1,10 @@
-"""Stress the bf16 attention kernels: repeat on the same input, compare bitwise with the first
-result, look for non-finite values; interleave with GEMMs to vary what runs before/after."""
+"""Stress the bf16 attention kernels: repeat the forward on the same input (interleaved with GEMMs and
+backward launches), checksum every result, and report how many distinct outputs appeared -- 1 means
+bit-identical run to run."""
+import collections
 import os
 import sys
+import time
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,26 +17,34 @@ torch.manual_seed(0)
 qkv = (torch.randn(B, T, 3 * H * 64, device=dev) * 0.5).bfloat16()
 A = torch.randn(B * T, 1024, device=dev).bfloat16()
 W = torch.randn(4096, 1024, device=dev).bfloat16()
-out0, lse0 = K.attention_forward(BF16, qkv, B, T, H, 64)
-dout = torch.randn_like(out0)
-g0 = K.attention_backward(BF16, qkv, out0, lse0, dout, B, T, H, 64)
-torch.cuda.synchronize()
-print("first finite:", bool(torch.isfinite(out0.float()).all()), bool(torch.isfinite(lse0).all()), bool(torch.isfinite(g0.float()).all()))
-bad_f = bad_b = 0
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+wts = torch.randn(B, T, H * 64, device=dev)
+sums = collections.Counter()
+outs = {}
+t0 = time.time()
 for i in range(n):
     if i % 3 == 0:
         K.gemm(BF16, A, MAJOR_K, W, MAJOR_K, B * T, 4096, 1024, torch.bfloat16)
     out, lse = K.attention_forward(BF16, qkv, B, T, H, 64)
-    if i % 2 == 0:
-        g = K.attention_backward(BF16, qkv, out, lse, dout, B, T, H, 64)
-        if not torch.equal(g, g0):
-            bad_b += 1
-    if not (torch.equal(out, out0) and torch.equal(lse, lse0)):
-        bad_f += 1
-        if bad_f <= 3:
-            d = (out.float() - out0.float()).abs()
-            print(f"iter {i}: fwd mismatch max {float(d.max()):.3e} nonfinite {int((~torch.isfinite(out.float())).sum())} "
-                  f"rows {int((d.amax(-1) > 0).sum())}", flush=True)
+    if i % 4 == 0:
+        K.attention_backward(BF16, qkv, out, lse, out, B, T, H, 64)
+    key = (float((out.float() * wts).sum()), float(lse.sum()))
+    sums[key] += 1
+    if key not in outs:
+        outs[key] = out.clone()
 torch.cuda.synchronize()
-print(f"fwd mismatches {bad_f}/{n}  bwd mismatches {bad_b}/{(n + 1) // 2}")
+mode = sums.most_common(1)[0][0]
+print(f"{n} forwards in {time.time() - t0:.1f} s: {len(sums)} distinct outputs; most common seen {sums[mode]} times; "
+      f"finite: {bool(torch.isfinite(outs[mode].float()).all())}")
+for k, o in list(outs.items())[:4]:
+    if k != mode:
+        d = (o.float() - outs[mode].float()).abs()
+        print(f"   variant seen {sums[k]}x: max diff {float(d.max()):.3e}, rows differing {int((d.amax(-1) > 0).sum())}")
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(50):
+    K.attention_forward(BF16, qkv, B, T, H, 64)
+e1.record()
+torch.cuda.synchronize()
+us = e0.elapsed_time(e1) / 50 * 1e3
+print(f"forward {us:.1f} us = {4.0 * B * H * T * T * 64 / us / 1e6:.0f} TFLOP/s (back to back, warm L2)")
