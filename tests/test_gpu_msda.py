@@ -141,6 +141,35 @@ def test_long_bucket_path():
     assert relerr(gv, rgv) < TOL32
 
 
+@pytest.mark.parametrize("name,N,Lq,M,D,shapes,P", [
+    # a level with more pixels than the fill kernel keeps cursors for in shared memory (16-bit cursors:
+    # 81920 pixels) -> processed window by window
+    ("fill_windows", 1, 3000, 2, 8, [(300, 300)], 4),
+    # cursor table capped at 256 MB -> one query chunk of 17000 queries -> a bucket may exceed 65535
+    # entries -> 32-bit cursors (40960 pixels per window) -- both rarely used paths of the backward
+    ("fill_int_cursors", 12, 17000, 16, 8, [(424, 424)], 4),
+])
+def test_backward_large_value_maps(name, N, Lq, M, D, shapes, P):
+    g = torch.Generator().manual_seed(21)
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(N, S, M, D, generator=g).to(DEV)
+    loc = (torch.rand(N, Lq, M, len(shapes), P, 2, generator=g) * 1.04 - 0.02).to(DEV)
+    # half of the samples crowd into one corner of the map: long per-pixel lists
+    loc[:, ::2] = loc[:, ::2] * 0.05
+    aw = torch.softmax(torch.randn(N, Lq, M, len(shapes) * P, generator=g), -1).view(N, Lq, M, len(shapes), P).to(DEV)
+    gout = torch.randn(N, Lq, M * D, generator=g).to(DEV)
+    ss = torch.as_tensor(shapes, dtype=torch.long, device=DEV)
+    vo, lo, ao = value.clone().requires_grad_(True), loc.clone().requires_grad_(True), aw.clone().requires_grad_(True)
+    ref = o_msda.msda_core(vo, shapes, lo, ao)            # the oracle's plain-PyTorch formulation, on the GPU
+    rgv, rgl, rga = torch.autograd.grad(ref, (vo, lo, ao), gout)
+    out = K.msda_forward(value, ss, _lsi(ss), loc, aw)
+    assert relerr(out, ref) < TOL32
+    gv, gl, ga = K.msda_backward(value, ss, _lsi(ss), loc, aw, gout)
+    assert relerr(gv, rgv) < TOL32 and relerr(ga, rga) < TOL32
+    gv2, _, _ = K.msda_backward(value, ss, _lsi(ss), loc, aw, gout)
+    assert torch.equal(gv, gv2)
+
+
 def test_module_golden(golden):
     g = golden("msda_module.pt")
     m = asis.MSDeformAttn(**g["cfg"]).to(DEV)
