@@ -29,6 +29,21 @@ elif which.startswith("attn"):
         dout = torch.randn_like(out)
         for _ in range(3):
             K.attention_backward(BF16, qkv, out, lse, dout, B, T, H, 64)
+elif which == "ln_fwd":
+    x = torch.randn(R, 1024, device=dev)
+    w = torch.randn(1024, device=dev)
+    b = torch.randn(1024, device=dev)
+    for _ in range(3):
+        K.layernorm_forward(x, w, b, 1e-6, torch.bfloat16)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        K.layernorm_forward(x, w, b, 1e-6, torch.bfloat16)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 20
+    print(f"ln_fwd {t * 1e3:.1f} us  {R * 1024 * 6 / t / 1e6:.0f} GB/s")
 elif which == "ln_bwd":
     x = torch.randn(R, 1024, device=dev)
     dy = torch.randn(R, 1024, device=dev).bfloat16()
