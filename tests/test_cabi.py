@@ -41,6 +41,45 @@ def test_argument_validation_without_gpu():
     assert lib.asis_attention_backward_workspace_bytes(0, 1, 10, 2, 16) == 2 * 2 * 100 * 4
 
 
+def test_host_side_validation_and_workspace_sizes():
+    """Host logic of the entry points added in round 1 (no kernel is launched: every call fails its
+    argument check first, or only computes a size)."""
+    import ctypes
+    from adaptersis_b200 import _lib
+    lib = _lib.load()
+    fake = ctypes.c_void_p(256)          # a non-null, 16-byte aligned address that is never dereferenced
+    # decoder resize: channel count must fill 16-byte vectors, H and W > 1
+    rc = lib.asis_upsample2x_bilinear_forward(fake, fake, 1, 2, 8, 8, 12, None)
+    assert rc == -1 and b"multiple of 8" in lib.asis_last_error()
+    rc = lib.asis_upsample2x_bilinear_backward(fake, fake, 0, 2, 1, 8, 16, None)
+    assert rc == -1 and b"H > 1" in lib.asis_last_error()
+    rc = lib.asis_upsample2x_bilinear_forward(None, fake, 0, 2, 8, 8, 16, None)
+    assert rc == -1 and b"null pointer" in lib.asis_last_error()
+    # LayerScale backward: d gamma needs the saved branch output; workspace is checked before launch
+    rc = lib.asis_layerscale_backward(fake, None, fake, fake, 1, fake, None, 64, 128, fake, 1 << 20, None)
+    assert rc == -1 and b"needs the saved branch output" in lib.asis_last_error()
+    need = lib.asis_layerscale_backward_workspace_bytes(21180, 1024)
+    assert need >= 2 * 1024 * 4
+    rc = lib.asis_layerscale_backward(fake, fake, fake, fake, 1, fake, fake, 21180, 1024, fake, need - 1, None)
+    assert rc != 0 and b"workspace" in lib.asis_last_error()
+    # MSDA backward workspace: cursor table (chunks x pixels) + pixel pointers + 8-byte entries; the
+    # table is capped (256 MB) by using fewer, longer query chunks
+    def ws(N, S, M, D, Lq, L, P):
+        return lib.asis_msda_backward_workspace_bytes(N, S, M, D, Lq, L, P)
+    entries = 12 * 8 * 1764 * 3 * 4 * 4 * 8
+    w = ws(12, 6949, 8, 128, 1764, 3, 4)
+    assert entries + 12 * 8 * 6949 * 4 <= w <= entries + 12 * 8 * 6949 * 4 * 8 + (1 << 20)
+    assert ws(12, 6949, 8, 128, 3528, 3, 4) > w                      # more queries: more entries and chunks
+    big = ws(12, 180000, 16, 8, 17000, 1, 4)
+    assert big <= 12 * 16 * 17000 * 4 * 4 * 8 + (256 << 20) + 12 * 16 * 180001 * 4 + (1 << 20)
+    assert ws(0, 10, 1, 8, 10, 1, 1) == 0
+    # MSDA dimension limits are reported, not silently truncated
+    rc = lib.asis_msda_forward(fake, 0, fake, fake, fake, fake, fake, 0, 1, 10, 1, 256, 5, 1, 1, None)
+    assert rc == -1 and b"<= 128" in lib.asis_last_error()
+    rc = lib.asis_msda_forward(fake, 0, fake, fake, fake, fake, fake, 0, 1, 10, 1, 8, 5, 9, 1, None)
+    assert rc == -1 and b"n_levels" in lib.asis_last_error()
+
+
 def test_no_cpu_fallback():
     import adaptersis_b200 as asis
     m = asis.MSDeformAttn(d_model=32, n_levels=1, n_heads=4, n_points=2)
