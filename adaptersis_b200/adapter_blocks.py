@@ -1,5 +1,24 @@
 """Injector / extractor adapter blocks with the reference's names, signatures and state_dict keys
-(backbones/adapter_blocks.py), running on libasis_b200 kernels."""
+(backbones/adapter_blocks.py), running on libasis_b200 kernels.
+
+What differs from the reference underneath the same interface:
+
+* every ``nn.LayerNorm`` call is ``asis_layernorm_forward`` on the token-major tensor (the module
+  objects only hold the parameters); its backward also adds the residual-branch gradient and produces
+  the column partials of d gamma / d beta in the same pass;
+* the residual adds (``query + attn`` in the extractor, ``query + gamma * attn`` in the injector,
+  ``query + ffn`` after the ConvFFN) are the epilogue of the GEMM that produces the branch output
+  (``MSDeformAttn.output_proj``, ``ConvFFN.fc2``), not separate element-wise kernels;
+* ``ConvFFN``: the reference splits the token axis into three images, transposes each to NCHW, runs
+  three cuDNN depth-wise convolutions and transposes back (six layout copies); here one kernel walks
+  the three maps in place on ``[B, tokens, C]`` and applies the exact GELU on the way out, its backward
+  forms ``dy * GELU'(pre)`` once per element and then gathers the 3x3 neighbourhood;
+* ``deform_inputs`` is computed once per (resolution, device) and cached: it is static, the reference
+  rebuilds it (a dozen small kernels and two host syncs) in every training iteration.
+
+``with_cp`` (activation checkpointing) is accepted and ignored: at 180 GB per GPU the saved state of the
+four adapter stages (about 3 GB at batch 12) is not worth recomputing.
+"""
 from functools import partial
 
 import torch
@@ -89,7 +108,11 @@ class ConvFFN(nn.Module):
 
 
 class CACNN(nn.Module):
-    """Extractor (:102-147): c + MSDA(LN c, ref, LN x), then c + ConvFFN(LN c)."""
+    """Extractor (:102-147): c + MSDA(LN c, ref, LN x), then c + ConvFFN(LN c).
+
+    Queries are the 6949 pyramid tokens (73^2 + 36^2 + 18^2 at 588^2), the value map is the single
+    42 x 42 ViT token grid: 4 sampling points per query and head, one level.  Both residual adds ride
+    on GEMM epilogues (see the module docstring); drop_path is the identity at the reference's 0.0."""
 
     def __init__(self, dim, num_heads=6, n_points=4, n_levels=1, deform_ratio=1.0, with_cffn=True, cffn_ratio=0.25,
                  drop=0.0, drop_path=0.0, norm_layer=partial(nn.LayerNorm, eps=1e-6), with_cp=False):
@@ -117,7 +140,13 @@ class CACNN(nn.Module):
 
 
 class CAViT(nn.Module):
-    """Injector (:149-183): q + gamma * MSDA(LN q, ref, LN feat); gamma initialised to 0."""
+    """Injector (:149-183): q + gamma * MSDA(LN q, ref, LN feat); gamma initialised to 0.
+
+    Queries are the 1764 ViT tokens, the value map is the three-level pyramid (6949 tokens): 3 x 4
+    sampling points per query and head.  ``gamma`` (the per-channel gate, zero at initialisation as in
+    the reference, so the injector starts as the identity -- SURVEY F4) is applied together with the
+    residual add in the epilogue of the output projection; its gradient is the column sum of
+    (incoming gradient x branch output), one `asis_colsum` pass."""
 
     def __init__(self, dim, num_heads=6, n_points=4, n_levels=1, deform_ratio=1.0,
                  norm_layer=partial(nn.LayerNorm, eps=1e-6), init_values=0.0, with_cp=False):

@@ -1,5 +1,21 @@
 """DinoVisionTransformer with the reference's constructor, attributes, methods and state_dict keys
-(dinov2/models/vision_transformer.py:44-357), running on libasis_b200 kernels."""
+(dinov2/models/vision_transformer.py:44-357), running on libasis_b200 kernels.
+
+Same object model as the reference so that public DINOv2 checkpoints load key for key and
+``train.py``-style code can keep indexing ``model.blocks[i]`` / calling ``model.patch_embed``; what
+runs underneath is different:
+
+* ``patch_embed`` is a patch gather (``asis_patchify``) plus one tcgen05 GEMM instead of a strided
+  convolution; its backward is the same GEMM with the other operand majors;
+* a block is ONE autograd node (``functional.BlockFunction``): LayerNorm, fused-QKV GEMM, flash-style
+  attention over the 1765 tokens, projection + LayerScale + residual epilogue, LayerNorm, fc1 + GELU
+  epilogue, fc2 + LayerScale + residual epilogue -- seven kernels forward; the residual stream,
+  LayerNorm statistics and LayerScale stay fp32 in both precision modes;
+* the bicubic interpolation of the position embedding (37 x 37 -> 42 x 42 at 588^2) is static per
+  resolution and cached per parameter version instead of being recomputed in every forward;
+* forward-only calls (``get_intermediate_layers`` under ``inference_mode`` -- the taps pass of the
+  training step) skip every tensor that exists only for backward.
+"""
 import math
 from functools import partial
 from typing import Sequence, Tuple, Union
