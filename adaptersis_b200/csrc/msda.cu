@@ -1,9 +1,10 @@
 // msda.cu -- multi-scale deformable attention for sm_100a: bilinear sampling gather (forward),
-// atomic-free deterministic backward, and the fused softmax / sampling-location prep.
+// deterministic backward without floating-point atomics, and the fused softmax / sampling-location prep.
 //
 // Replaces ms_deform_attn_core_pytorch (reference backbones/ops/modules/ms_deform_attn.py:33-54)
-// and the arithmetic of MSDeformAttn.forward :156-171.  HBM-bound integer/float gather work: no
-// tensor cores; the design rules are coalesced 16-byte value loads, per-level spatial shapes in
+// and the arithmetic of MSDeformAttn.forward :156-171.  Bandwidth-bound integer/float gather work (in
+// practice the L1 data pipe and the L2->SM path rather than HBM: DESIGN.md 5.1): no tensor cores; the
+// design rules are coalesced 16-byte value loads, per-level spatial shapes in
 // shared memory, one thread group (16 bytes of channels per lane) per (query, head) so that a bilinear
 // corner is one coalesced segment, and grids laid out (queries fastest, then head, then image) so the
 // value slice of one (image, head) stays L2/L1 resident while it is being gathered.
@@ -17,8 +18,8 @@
 // scatter.  Instead of floating-point atomics the kernels build a CSR index of the contributions by
 // pixel: (1) count per (image, head, query chunk, pixel) [integer counters, inside the grad_loc /
 // grad_attn kernel], (2) scan -> start of every (pixel, chunk) bucket, pixel-major, (3) fill: one warp
-// per (chunk, level, image, head) writes (query, weight) entries to their final positions in the
-// canonical order (query, point, corner) using cursors in shared memory, (4) gather: one thread
+// per (chunk, level, image, head) writes (grad_out row offset, weight) entries to their final positions
+// in a fixed order, using cursors in shared memory that only it advances (integer adds), (4) gather: one thread
 // group per (image, pixel, head) walks the pixel's contiguous entry range and accumulates -> every
 // grad_value element is written exactly once, in a fixed summation order: run-to-run deterministic,
 // no float atomics, no sort.
