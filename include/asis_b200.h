@@ -79,8 +79,9 @@ int asis_msda_forward(const void *value, int value_dtype, const int64_t *spatial
                       int D, int Lq, int L, int P, void *stream);
 
 /* Backward (the reference's Function has none; semantics = autograd through the
- * reference core).  Atomic-free and run-to-run deterministic: contributions to grad_value are
- * bucketed per value pixel (counting sort), ordered, then reduced by one thread group per pixel.
+ * reference core).  No floating-point atomics, run-to-run deterministic: the contributions to
+ * grad_value are indexed per value pixel (integer count -> scan -> ordered fill), then one thread
+ * group per pixel sums its list in a fixed order and writes each element exactly once.
  *   grad_out     [N, Lq, M*D]  gdtype      grad_value  [N, S, M, D]  gdtype (fully overwritten)
  *   grad_loc     [N, Lq, M, L, P, 2] f32   grad_attn   [N, Lq, M, L, P] f32
  */
