@@ -3,8 +3,8 @@ DINOv2 ViT backbone forward/backward, the injector/extractor adapter blocks and 
 deformable attention, behind the reference's own module API.  All compute goes through
 libasis_b200.so (include/asis_b200.h); there is no CPU fallback."""
 from . import _lib  # noqa: F401
-from .functional import (MSDeformAttnFunction, get_precision, ms_deform_attn_core, precision,  # noqa: F401
-                         set_precision)
+from .functional import (MSDeformAttnFunction, get_precision, invalidate_weight_cache,  # noqa: F401
+                         ms_deform_attn_core, precision, set_precision)
 from .ms_deform_attn import MSDeformAttn  # noqa: F401
 from .adapter_blocks import CACNN, CAViT, ConvFFN, DWConv, deform_inputs, get_reference_points  # noqa: F401
 from .layers import (Attention, Block, LayerScale, MemEffAttention, Mlp, NestedTensorBlock,  # noqa: F401

@@ -6,6 +6,8 @@ DistributedDataParallel wrappers, train.py:84,96,112,116).
 Buckets are formed in reverse parameter-registration order (the order backward produces
 gradients); a bucket is reduced as soon as all its gradients have been accumulated
 (post-accumulate-grad hooks).  Works with any torch.distributed backend (gloo on CPU for tests)."""
+import contextlib
+
 import torch
 import torch.distributed as dist
 
@@ -32,11 +34,13 @@ class BucketedGradAllReduce:
         self._flat = [None] * len(self.buckets)
         self._works = []
         self._comm_stream = None
+        self._defer = False
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self.reset()
 
     def reset(self):
         self._pending = [len(b) for b in self.buckets]
+        self._fired = set()
         self._works = []
 
     def _stream(self, device):
@@ -47,10 +51,30 @@ class BucketedGradAllReduce:
         return self._comm_stream
 
     def _on_grad(self, p):
+        if self._defer:
+            return
         i = self._bucket_of[id(p)]
         self._pending[i] -= 1
+        if id(p) in self._fired:
+            raise RuntimeError(
+                "BucketedGradAllReduce: a gradient was accumulated twice before finish() -- a second backward() "
+                "(gradient accumulation) or a parameter used by two graphs.  Run the micro-batches that should not "
+                "be reduced yet under `with reducer.no_sync():`; the last backward (outside it) + finish() reduces "
+                "the accumulated gradients.")
+        self._fired.add(id(p))
         if self._pending[i] == 0:
             self._launch(i)
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Gradient accumulation: backward() calls inside this context only accumulate into p.grad (no bucket is
+        launched); the first backward outside it reduces the accumulated gradients (DDP.no_sync semantics)."""
+        old = self._defer
+        self._defer = True
+        try:
+            yield
+        finally:
+            self._defer = old
 
     def _launch(self, i, partial=False):
         if self.world == 1:
@@ -76,7 +100,6 @@ class BucketedGradAllReduce:
             side.wait_stream(torch.cuda.current_stream(dev))
             ctx = torch.cuda.stream(side)
         else:
-            import contextlib
             ctx = contextlib.nullcontext()
         # NCCL averages inside the collective; other backends (gloo in the CPU tests) sum and divide after
         avg_in_op = self.average and dev.type == "cuda" and dist.get_backend(self.group) == "nccl"

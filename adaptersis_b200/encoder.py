@@ -25,6 +25,9 @@ class AdapterEncoder(nn.Module):
                  n_last_blocks=4, frozen_backbone=False, model=None, injector_init=0.0):
         super().__init__()
         self.model = model if model is not None else build_model_for_eval(arch, patch_size=patch_size)
+        if self.model.chunked_blocks:
+            raise ValueError("AdapterEncoder indexes model.blocks[i] like train.py:300-370: build the backbone with "
+                             "block_chunks=0 (build_model_for_eval does)")
         C = self.model.embed_dim
         self.patch_size = self.model.patch_size
         self.feature_model = ModelWithIntermediateLayers(self.model, n_last_blocks)

@@ -8,6 +8,7 @@ Precision modes (BASELINE.json north_star):
 """
 import contextlib
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -50,21 +51,40 @@ def _cfg(mode=None):
     return (BF16, torch.bfloat16) if mode == "bf16" else (F32, torch.float32)
 
 
-# bf16 copies of fp32 master weights, refreshed when the parameter is updated in place
+# bf16 copies of fp32 master weights.  One entry per live Parameter, keyed by id() and evicted by a
+# weakref finalizer when the Parameter dies (no strong reference is held, rebuilt models do not leak).
+# An entry is valid while (version counter, storage pointer) are unchanged: every in-place update that
+# autograd can see -- optimizer.step(), load_state_dict(), p.copy_()/p.mul_() under no_grad -- bumps
+# the version.  Writes through ``p.data`` do NOT (``.data`` is a detached alias with its own counter):
+# call ``invalidate_weight_cache()`` after such writes, or run with ASIS_CHECK_WEIGHT_CACHE=1, which
+# re-casts on every use and raises if a cached copy went stale.
 _wcache = {}
+_CHECK_WCACHE = bool(int(os.environ.get("ASIS_CHECK_WEIGHT_CACHE", "0")))
+
+
+def invalidate_weight_cache():
+    """Drop every cached low-precision weight copy (needed only after writes through ``param.data``)."""
+    for key in [k for k in _wcache if not isinstance(k, tuple)]:
+        _wcache.pop(key, None)
 
 
 def _operand(t, tdtype):
     """Weight (or any tensor) in the compute dtype; parameters are cached per version."""
     if t.dtype == tdtype:
         return t.detach()
+    if not isinstance(t, torch.nn.Parameter):
+        return K.cast(t.detach(), tdtype)
     key = id(t)
     hit = _wcache.get(key)
-    if hit is not None and hit[0] is t and hit[1] == t._version and hit[2].dtype == tdtype:
+    if hit is not None and hit[0]() is t and hit[1] == (t._version, t.data_ptr()) and hit[2].dtype == tdtype:
+        if _CHECK_WCACHE and not torch.equal(hit[2], K.cast(t.detach(), tdtype)):
+            raise RuntimeError("stale low-precision weight copy: the parameter was modified through .data "
+                               "(no version bump); call adaptersis_b200.invalidate_weight_cache() after such writes")
         return hit[2]
     c = K.cast(t.detach(), tdtype)
-    if isinstance(t, torch.nn.Parameter):
-        _wcache[key] = (t, t._version, c)
+    if hit is None:
+        weakref.finalize(t, _wcache.pop, key, None)
+    _wcache[key] = (weakref.ref(t), (t._version, t.data_ptr()), c)
     return c
 
 
@@ -315,7 +335,7 @@ class BlockFunction(Function):
 
     @staticmethod
     def forward(ctx, x, n1w, n1b, qkv_w, qkv_b, proj_w, proj_b, g1, n2w, n2b, fc1_w, fc1_b, fc2_w, fc2_b, g2,
-                num_heads, eps, mode):
+                num_heads, eps, mode, grad_on=True):
         comp, cdt = _cfg(mode)
         B, T, C = x.shape
         R = B * T
@@ -325,7 +345,9 @@ class BlockFunction(Function):
         hd = C // num_heads
         # forward-only calls (the taps pass runs under no_grad: nothing needs a gradient) skip the tensors
         # that exist only for backward: the GELU pre-activation and the LayerScale branch outputs
-        track = any(ctx.needs_input_grad)
+        # (``grad_on`` is torch.is_grad_enabled() sampled by the caller: inside Function.forward grad mode is
+        # always off, and ctx.needs_input_grad reports the parameters' requires_grad even under no_grad())
+        track = grad_on and any(ctx.needs_input_grad)
         save_u = [track and g1 is not None and g1.requires_grad, track and g2 is not None and g2.requires_grad]
         gam1 = _f32(g1) if g1 is not None else _ones(C, dev)
         gam2 = _f32(g2) if g2 is not None else _ones(C, dev)
@@ -387,7 +409,7 @@ class BlockFunction(Function):
         if xdt != torch.float32:
             dx = dx.to(xdt)
         return (dx if ni[0] else None, dn1w, dn1b, dqkv_w, dqkv_b, dproj_w, dproj_b, dg1, dn2w, dn2b,
-                dfc1_w, dfc1_b, dfc2_w, dfc2_b, dg2, None, None, None)
+                dfc1_w, dfc1_b, dfc2_w, dfc2_b, dg2, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -120,7 +120,7 @@ class Block(nn.Module):
         return Fn.BlockFunction.apply(
             x, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias, g1,
             self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias, g2,
-            a.num_heads, self.norm1.eps, Fn.get_precision())
+            a.num_heads, self.norm1.eps, Fn.get_precision(), torch.is_grad_enabled())
 
 
 class NestedTensorBlock(Block):

@@ -54,9 +54,12 @@ class TrainStep(nn.Module):
         self.reducer = BucketedGradAllReduce(params, bucket_bytes=bucket_bytes)
         self.device = torch.device(device)
 
-    def forward_loss(self, inp, target):
+    def forward_loss(self, inp, target, internals=None):
+        """Loss of one batch.  ``internals`` (optional dict) receives the tensors the parity tests compare with
+        the oracle: encoder state ("x", "c", "feat"), full-resolution "logits", and the "loss" itself."""
         with Fn.precision(self.precision):
-            feat = self.encoder(inp)["feat"]
+            res = self.encoder(inp)
+            feat = res["feat"]
             # the decoder is still library code (SURVEY.md 8f rank 2): in bf16 mode let cuDNN run it in
             # bf16 / channels-last, like the rest of the step
             lowp = self.precision == "bf16"
@@ -66,8 +69,13 @@ class TrainStep(nn.Module):
             out = out.float()
             H, W = target.shape[1], target.shape[2]
             out = F.interpolate(out, size=(H, W), mode="bilinear")
+            if internals is not None:
+                internals.update(x=res["x"], c=res["c"], feat=feat, logits=out)
             out = torch.softmax(out, 1)
-            return dice_loss_after_softmax(out, target, self.num_classes)
+            loss = dice_loss_after_softmax(out, target, self.num_classes)
+            if internals is not None:
+                internals["loss"] = loss
+            return loss
 
     def step_device(self, inp, target):
         """inputs already on the device; returns the loss tensor (no host sync)."""

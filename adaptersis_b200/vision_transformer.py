@@ -28,6 +28,15 @@ from . import functional as Fn
 from .layers import MemEffAttention, Mlp, NestedTensorBlock as Block, PatchEmbed
 
 
+class BlockChunk(nn.ModuleList):
+    """One FSDP wrapping unit of the reference (vision_transformer.py:37-41): runs its members in order."""
+
+    def forward(self, x):
+        for b in self:
+            x = b(x)
+        return x
+
+
 class DinoVisionTransformer(nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0,
                  qkv_bias=True, ffn_bias=True, proj_bias=True, drop_path_rate=0.0, drop_path_uniform=False,
@@ -48,13 +57,20 @@ class DinoVisionTransformer(nn.Module):
             raise NotImplementedError("drop_path_rate > 0 is not on the AdapterSIS hot path")
         if ffn_layer != "mlp":
             raise NotImplementedError("ffn_layer must be 'mlp' (configs/eval/vitl14_pretrain.yaml)")
-        if block_chunks != 0:
-            raise NotImplementedError("block_chunks must be 0: train.py indexes model.blocks[i] directly")
-        self.chunked_blocks = False
-        self.blocks = nn.ModuleList([
-            block_fn(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, proj_bias=proj_bias,
-                     ffn_bias=ffn_bias, drop_path=0.0, norm_layer=norm_layer, act_layer=act_layer, ffn_layer=Mlp,
-                     init_values=init_values) for _ in range(depth)])
+        blocks = [block_fn(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias,
+                           proj_bias=proj_bias, ffn_bias=ffn_bias, drop_path=0.0, norm_layer=norm_layer,
+                           act_layer=act_layer, ffn_layer=Mlp, init_values=init_values) for _ in range(depth)]
+        if block_chunks > 0:
+            # FSDP-style chunk layout (:141-147): chunk c holds blocks [c*size, (c+1)*size) at their GLOBAL
+            # positions (identity placeholders in front), so checkpoints saved with ``blocks.<c>.<i>.`` keys load
+            # key for key.  train.py builds with block_chunks=0 and indexes model.blocks[i] directly.
+            self.chunked_blocks = True
+            size = depth // block_chunks
+            self.blocks = nn.ModuleList([BlockChunk([nn.Identity()] * i + blocks[i:i + size])
+                                         for i in range(0, depth, size)])
+        else:
+            self.chunked_blocks = False
+            self.blocks = nn.ModuleList(blocks)
         self.norm = norm_layer(embed_dim)
         self.head = nn.Identity()
         self.mask_token = nn.Parameter(torch.zeros(1, embed_dim))
@@ -116,21 +132,31 @@ class DinoVisionTransformer(nn.Module):
         if isinstance(x, list):
             return [self.forward_features(xi, mi) for xi, mi in zip(x, masks)]
         x = self.prepare_tokens_with_masks(x, masks)
-        for blk in self.blocks:
+        for blk in self.blocks:          # a Block, or a BlockChunk running its members (identities in front)
             x = blk(x)
         x_norm = self._norm(x)
         return {"x_norm_clstoken": x_norm[:, 0], "x_norm_patchtokens": x_norm[:, 1:], "x_prenorm": x, "masks": masks}
 
+    def _real_blocks(self):
+        """The transformer blocks in execution order, whichever layout ``self.blocks`` has."""
+        if not self.chunked_blocks:
+            return list(self.blocks)
+        return [b for chunk in self.blocks for b in chunk if not isinstance(b, nn.Identity)]
+
     def _get_intermediate_layers_not_chunked(self, x, n=1):
+        # serves both layouts (:237-261): outputs are indexed by global block position
         x = self.prepare_tokens_with_masks(x)
-        output, total_block_len = [], len(self.blocks)
+        blocks = self._real_blocks()
+        output, total_block_len = [], len(blocks)
         blocks_to_take = range(total_block_len - n, total_block_len) if isinstance(n, int) else n
-        for i, blk in enumerate(self.blocks):
+        for i, blk in enumerate(blocks):
             x = blk(x)
             if i in blocks_to_take:
                 output.append(x)
         assert len(output) == len(blocks_to_take), f"only {len(output)} / {len(blocks_to_take)} blocks found"
         return output
+
+    _get_intermediate_layers_chunked = _get_intermediate_layers_not_chunked
 
     def get_intermediate_layers(self, x: torch.Tensor, n: Union[int, Sequence] = 1, reshape: bool = False,
                                 return_class_token: bool = False, norm=True) -> Tuple[Union[torch.Tensor, Tuple[torch.Tensor]]]:

@@ -2,7 +2,7 @@
 """bench.py -- BASELINE.json's headline metric: ViT-L/14-adapter 588x588 train images/s.
 
     python bench.py --gpus N --steps K --warmup W            # our arm (CUDA kernels)
-    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the reference's own modules (oracle/_ref)
     torchrun --nproc-per-node N bench.py --gpus N ...        # N > 1, one rank per GPU over NCCL
 
 One "step" = one training iteration of the reference's train() loop body (train.py:268-441) on one
@@ -185,19 +185,36 @@ def build_cpu_state(arch, seed=0):
     return out, enc.model.num_heads
 
 
+ADAPTER_HEADS = {"vit_small": 6, "vit_base": 12, "vit_large": 8}     # train.py:86-110 uses 8 with ViT-L
+
+
+def make_cpu_step(arch):
+    """The CPU leg's step function: the reference's OWN modules when oracle/make_ref.sh has staged them under
+    oracle/_ref/ (kind "reference"), else the oracle port (kind "port").  Returns (step(img, tgt) -> loss, kind, what)."""
+    from oracle import ref_step
+    if ref_step.available() and not os.environ.get("ASIS_CPU_PORT"):
+        rs = ref_step.ReferenceStep(arch, adapter_heads=ADAPTER_HEADS.get(arch, 8))
+        return rs.step, "reference", ("the reference's own unmodified PyTorch modules (oracle/_ref: MSDeformAttn via "
+                                      "ms_deform_attn_core_pytorch/grid_sample, CAViT, CACNN, DINOv2 blocks with the naive "
+                                      "attention path, FeatureEncoder, FeatureDecoder, DC loss)")
+    sds, heads = build_cpu_state(arch)
+    return (lambda img, tgt: cpu_reference_step(sds, img, tgt, heads)), "port", \
+        "oracle port (pure PyTorch fp32 restatement of the reference modules)"
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     ncores = os.cpu_count() or 1
     torch.set_num_threads(ncores)
-    sds, heads = build_cpu_state(args.arch)
+    step_fn, kind, what = make_cpu_step(args.arch)
     img, tgt = synth_batch(1, args.imsize, 2, 1234)
     budget_s = float(os.environ.get("ASIS_REF_BUDGET_S", "170"))
     t_begin = time.perf_counter()
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        cpu_reference_step(sds, img, tgt, heads)
+        step_fn(img, tgt)
         dt_ = time.perf_counter() - t0
         if i >= min(args.warmup, 1):          # CPU arm: one warm-up is enough (no JIT, no autotune)
             times.append(dt_)
@@ -205,13 +222,13 @@ def run_reference(args, rank):
             break
     ms = 1e3 * sum(times) / len(times)
     val = 1.0 / (ms / 1e3)
-    sample = (f"{len(times)} timed step(s) of 1 image each (of the 12-image batch), full ViT-L/14 + adapters + decoder "
-              f"fwd+bwd, oracle port (pure PyTorch fp32 restatement of the reference modules), {ncores} threads")
+    sample = (f"{len(times)} timed step(s) of 1 image each (of the 12-image batch), full {args.arch} /14 + adapters + decoder "
+              f"fwd+bwd, {what}, {ncores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 5), "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(ms, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, 1, "cpu"),
-            "cpu_baseline": {"value": round(val, 5), "unit": UNIT, "cores": ncores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": round(val, 5), "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
             "e2e": {"value": round(val, 5), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -348,16 +365,34 @@ def run_ours(args, rank, world, local_rank):
         try:
             ncores = os.cpu_count() or 1
             torch.set_num_threads(ncores)
-            sds, heads = build_cpu_state(args.arch)
+            step_fn, kind, what = make_cpu_step(args.arch)
             img, tgt = synth_batch(1, args.imsize, 2, 1234)
-            t0 = time.perf_counter()
-            cpu_reference_step(sds, img, tgt, heads)
-            dt_ = time.perf_counter() - t0
-            cpu = {"value": round(1.0 / dt_, 5), "unit": UNIT, "cores": ncores, "kind": "port",
-                   "sample": "1 image (of the 12-image batch), one un-warmed fwd+bwd of the same step through the oracle "
-                             "port (pure PyTorch fp32 restatement of the reference modules), all host threads"}
+            step_fn(img, tgt)                                   # 1 warm-up
+            ts_ = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                step_fn(img, tgt)
+                ts_.append(time.perf_counter() - t0)
+            cpu = {"value": round(1.0 / min(ts_), 5), "unit": UNIT, "cores": ncores, "kind": kind,
+                   "sample": f"1 image (of the 12-image batch) per step, 1 warm-up + min of 3 fwd+bwd steps "
+                             f"({', '.join(f'{t:.2f}' for t in ts_)} s) through {what}, all host threads"}
         except Exception as ex:  # pragma: no cover
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex!r}"}
+
+    # BASELINE.json's second metric: MSDeformAttn achieved HBM GB/s (fwd and bwd) on algorithmic bytes, at the two real
+    # shapes of the step and two points of the config[4] sweep (M=16, D=64), fp32 and the bf16-value variant
+    msda = None
+    if world == 1 and not args.no_msda:
+        try:
+            from tools.msda_bench import REAL_CASES, run_cases
+            extra = [("sweep_g36_Lq1764", 12, 1764, 16, 64, [(72, 72), (36, 36), (18, 18)], 4),
+                     ("sweep_g36_Lq6949", 12, 6949, 16, 64, [(72, 72), (36, 36), (18, 18)], 4)]
+            rows = run_cases(REAL_CASES + extra, dev, pk["hbm_gbs"], iters=7)
+            msda = {"unit": "GB/s", "peak": pk["hbm_gbs"], "peak_source": pk_src, "bytes": "algorithmic (SURVEY.md 8d), "
+                    "value counted once and only where samples can touch it", "timing": "median of 7, L2 flushed "
+                    "between iterations, CUDA events", "cases": rows}
+        except Exception as ex:  # pragma: no cover
+            msda = {"failed": repr(ex)}
 
     imgs = B * world * args.steps
     h2d = sum(t.numel() * t.element_size() for t in batches[0])
@@ -371,7 +406,7 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
             "roofline_attention": tensor_roof(["attn_fwd", "attn_bwd"], peak_tf),
             "roofline_msda": hbm_roof(["msda_fwd", "msda_bwd"]),
-            "cpu_baseline": cpu, "last_loss": lv}
+            "msda": msda, "cpu_baseline": cpu, "last_loss": lv}
     print(json.dumps(line), flush=True)
 
 
@@ -387,6 +422,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--frozen-backbone", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-msda", action="store_true", help="skip the MSDeformAttn GB/s record")
     ap.add_argument("--detail", action="store_true", help="print the per-shape GEMM breakdown of the profiled step")
     ap.add_argument("--only-timed", action="store_true", help="warm-up + timed loop only (used under ncu)")
     args = ap.parse_args()

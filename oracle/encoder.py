@@ -73,6 +73,9 @@ def adapter_encoder(vit_sd, spm_sd, inj_sd, ext_sd, img, num_heads, patch=14, n_
     C = vit_sd["cls_token"].shape[-1]
     depth = vit.depth_of(vit_sd)
     d1, d2 = adapter.deform_inputs(H, W, patch)
+    # reference points are fp32 cell centres (adapter_blocks.py:9-22); same values on the input's device / dtype
+    d1 = [d1[0].to(img.device, img.dtype), d1[1], d1[2]]
+    d2 = [d2[0].to(img.device, img.dtype), d2[1], d2[2]]
     Hc, Wc = H // 16, W // 16
 
     c1, c2, c3, c4 = spm(spm_sd, img)

@@ -36,8 +36,8 @@ def msda_core(value, spatial_shapes, sampling_locations, attention_weights):
     assert sum(h * w for h, w in shapes) == S
     out = value.new_zeros(N, Lq, M, D)
     start = 0
-    n_idx = torch.arange(N).view(N, 1, 1, 1)
-    m_idx = torch.arange(M).view(1, 1, M, 1)
+    n_idx = torch.arange(N, device=value.device).view(N, 1, 1, 1)
+    m_idx = torch.arange(M, device=value.device).view(1, 1, M, 1)
     for lvl, (H, W) in enumerate(shapes):
         v = value[:, start:start + H * W]                     # [N,HW,M,D]
         loc = sampling_locations[:, :, :, lvl]                # [N,Lq,M,P,2]
@@ -69,6 +69,7 @@ def msda_core(value, spatial_shapes, sampling_locations, attention_weights):
 def msda_locations(reference_points, sampling_offsets, spatial_shapes, n_points):
     """reference_points [N|1,Lq,L|1,2or4], sampling_offsets [N,Lq,M,L,P,2]."""
     shapes = spatial_shapes if torch.is_tensor(spatial_shapes) else torch.as_tensor(spatial_shapes)
+    shapes = shapes.to(sampling_offsets.device)
     if reference_points.shape[-1] == 2:
         norm = torch.stack([shapes[..., 1], shapes[..., 0]], -1).to(sampling_offsets.dtype)  # (W,H)
         return reference_points[:, :, None, :, None, :] + sampling_offsets / norm[None, None, None, :, None, :]

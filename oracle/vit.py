@@ -36,7 +36,7 @@ def interpolate_pos_encoding(pos_embed, n_patch_tokens, w, h, patch):
     N = pos_embed.shape[1] - 1
     if n_patch_tokens == N and w == h:
         return pos_embed
-    pe = pos_embed.float()
+    pe = pos_embed if pos_embed.dtype == torch.float64 else pos_embed.float()   # (:170; fp64 kept for the fp64 oracle runs)
     cls_pe, patch_pe = pe[:, :1], pe[:, 1:]
     dim = pe.shape[-1]
     side = int(math.sqrt(N))

@@ -237,13 +237,22 @@ def gold_adapter():
                             grad_ext={k: g for k, g in zip(ext_p.keys(), grads[2 + n1:])}))
 
 
-def gold_encoder():
-    """train.py:275-406 data flow with the reference's own modules, graph left connected."""
+def sample_idx(numel, n=4096):
+    """Evenly strided sample positions of a flattened tensor (large-gradient fixtures)."""
+    step = max(1, numel // n)
+    return torch.arange(0, numel, step)[:n]
+
+
+def gold_encoder(name="encoder.pt", dim=32, heads=2, depth=5, seed=19, full_grad_numel=4096):
+    """train.py:275-406 data flow with the reference's own modules, graph left connected.
+    ``encoder.pt``: head_dim 16 (fp32 parity mode).  ``encoder_hd64.pt``: head_dim 64 for the backbone AND
+    the adapters (dim 128, 2 heads), the shape class the tcgen05 attention / bf16 MSDA kernels need, so the
+    bf16 performance mode can be compared with the reference end to end."""
     from einops import rearrange
     import torch.nn.functional as F
-    gen = torch.Generator().manual_seed(19)
-    torch.manual_seed(19)
-    dim, heads, depth = 32, 2, 5
+    import numpy as np
+    gen = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
     model = tiny_vit(dim, depth, heads, gen, img_size=70)
     enc = stress_init(sync_bn_to_bn(FeatureEncoder(inplanes=8, embed_dim=dim)), gen)
     inj = stress_init(ref_ab.CAViT(dim=dim, n_levels=3, num_heads=heads, n_points=4, init_values=0.0), gen)
@@ -296,16 +305,24 @@ def gold_encoder():
     for (k, p), g in zip(named.items(), grads):
         if g is None:
             continue
-        gsel[k] = g if g.numel() <= 4096 else dict(norm=g.double().norm(), head=g.flatten()[:256].clone(),
-                                                  sum=g.double().sum())
-    save("encoder.pt", dict(cfg=dict(dim=dim, heads=heads, depth=depth, inplanes=8, dec_features=[dim, 16, 8, 8, 4]),
+        gsel[k] = g if g.numel() <= full_grad_numel else dict(
+            norm=g.double().norm(), head=g.flatten()[:256].clone(), sum=g.double().sum(),
+            sample=g.flatten()[sample_idx(g.numel())].clone(), absmax=g.abs().max())
+    mask = logits.argmax(1).to(torch.uint8).numpy()                      # [1, 588, 588] in {0, 1}
+    save(name, dict(cfg=dict(dim=dim, heads=heads, depth=depth, inplanes=8, dec_features=[dim, 16, 8, 8, 4]),
                             vit_sd=cpu_sd(model), spm_sd=cpu_sd(enc), inj_sd=cpu_sd(inj), ext_sd=cpu_sd(ext),
                             dec_sd=cpu_sd(dec), img_lowres=inp[:, :, ::28, ::28].clone(),
                             img_sum=inp.double().sum(), target_sum=int(target.sum()),
                             feat=feat.detach().clone(), x=x.detach().clone(), c_sum=c.detach().double().sum(),
                             logits_lowres=logits.detach()[:, :, ::12, ::12].clone(),
-                            argmax_sum=int(logits.argmax(1).sum()), loss=loss.detach(), aux=aux.detach(),
-                            grads=gsel))
+                            logits_s4=logits.detach()[:, :, ::4, ::4].clone(),
+                            argmax_sum=int(logits.argmax(1).sum()),
+                            argmax_packed=torch.from_numpy(np.packbits(mask.reshape(-1))), argmax_shape=tuple(mask.shape),
+                            # class-1 minus class-0 logit at every pixel (fp16 is plenty: it only tells the tests which
+                            # pixels are numerical near-ties, where two correct evaluations may legitimately disagree)
+                            margin_f16=(logits.detach()[:, 1] - logits.detach()[:, 0]).half(),
+                            logits_absmax=float(logits.detach().abs().max()),
+                            loss=loss.detach(), aux=aux.detach(), grads=gsel))
 
 
 if __name__ == "__main__":
@@ -315,3 +332,4 @@ if __name__ == "__main__":
     gold_vit()
     gold_adapter()
     gold_encoder()
+    gold_encoder("encoder_hd64.pt", dim=128, heads=2, depth=5, seed=23, full_grad_numel=20000)

@@ -43,9 +43,34 @@ def _worker(rank, world, port, q):
             (tot / world).backward()
             want = torch.cat([p.grad.reshape(-1) for p in ref_net.parameters()])
             assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (rank, step, float((got - want).abs().max()))
+        # gradient accumulation: first micro-batch under no_sync(), second one reduces the accumulated gradients
+        g = torch.Generator().manual_seed(300)
+        data = torch.randn(2, world, 5, 8, generator=g)
+        net.zero_grad(set_to_none=True)
+        with red.no_sync():
+            net(data[0, rank]).square().sum().backward()
+        net(data[1, rank]).square().sum().backward()
+        red.finish()
+        got = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+        ref_net.load_state_dict(net.state_dict())
+        ref_net.zero_grad(set_to_none=True)
+        tot = sum(ref_net(data[mb, r]).square().sum() for mb in range(2) for r in range(world))
+        (tot / world).backward()
+        want = torch.cat([p.grad.reshape(-1) for p in ref_net.parameters()])
+        assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), (rank, "accumulate", float((got - want).abs().max()))
+        # a second backward before finish() without no_sync() must fail loudly, not drop gradients silently
+        net.zero_grad(set_to_none=True)
+        net(data[0, rank]).square().sum().backward()
+        try:
+            net(data[1, rank]).square().sum().backward()
+            raise AssertionError("second backward before finish() did not raise")
+        except RuntimeError as e:
+            assert "no_sync" in str(e)
+        red.finish()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
-        q.put((rank, repr(e)))
+        import traceback
+        q.put((rank, traceback.format_exc()))
     finally:
         dist.destroy_process_group()
 

@@ -6,7 +6,7 @@ are sums over ~1e4-1e6 fp32 terms in a different order than the reference's)."""
 import pytest
 import torch
 
-from conftest import relerr
+from conftest import grad_err, mask_check, relerr
 from synth import adapter_data, encoder_data
 import adaptersis_b200 as asis
 from oracle import encoder as o_enc
@@ -104,22 +104,18 @@ def _build_encoder(g):
     return enc, dec
 
 
-def test_composed_encoder_golden(golden):
-    g = golden("encoder.pt")
+def run_composed(g, mode):
+    """Composed train.py data flow (encoder + decoder + loss) on the CUDA path in `mode`; returns internals and
+    the gradients of loss + aux for every parameter the fixture lists."""
     cfg = g["cfg"]
     img, target, gfeat = [t.to(DEV) for t in encoder_data(1, 588, 3 * cfg["dim"], 42)]
     enc, dec = _build_encoder(g)
-    with asis.precision("fp32"):
+    with asis.precision(mode):
         res = enc(img)
         feat = res["feat"]
-        assert relerr(feat, g["feat"]) < TOL
-        assert relerr(res["x"], g["x"]) < TOL
-        logits = torch.nn.functional.interpolate(dec(feat), size=(588, 588), mode="bilinear")
-        assert relerr(logits[:, :, ::12, ::12], g["logits_lowres"]) < TOL
-        assert int(logits.argmax(1).sum()) == g["argmax_sum"]          # argmax mask identical
+        logits = torch.nn.functional.interpolate(dec(feat.float()), size=(588, 588), mode="bilinear")
         loss = o_enc.dice_loss(torch.softmax(logits, 1), target)
         aux = (feat * gfeat).sum() / feat.numel() ** 0.5
-        assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5
         named = {}
         for tag, mod in (("vit", enc.model), ("spm", enc.backbone_encoder), ("inj", enc.cross_vit),
                          ("ext", enc.cross_cnn), ("dec", dec)):
@@ -127,18 +123,33 @@ def test_composed_encoder_golden(golden):
                 named[f"{tag}.{k}"] = p
         keys = [k for k in g["grads"]]
         grads = torch.autograd.grad(loss + aux, [named[k] for k in keys], allow_unused=True)
+    return dict(feat=feat, x=res["x"], logits=logits, loss=loss, grads=dict(zip(keys, grads)))
+
+
+@pytest.mark.parametrize("fixture", ["encoder.pt", "encoder_hd64.pt"])
+def test_composed_encoder_golden(golden, fixture):
+    g = golden(fixture)
+    r = run_composed(g, "fp32")
+    assert relerr(r["feat"], g["feat"]) < TOL
+    assert relerr(r["x"], g["x"]) < TOL
+    logits = r["logits"]
+    assert relerr(logits[:, :, ::12, ::12], g["logits_lowres"]) < TOL
+    assert relerr(logits[:, :, ::4, ::4], g["logits_s4"]) < TOL
+    # the reference's argmax mask, EVERY pixel: bit-exact wherever the decision is numerically determined
+    flips, near = mask_check(logits, g, TOL)
+    print(f"[{fixture}] fp32 mode vs reference mask: {flips} flips / {logits[:, 0].numel()} pixels ({near} near-ties)")
+    assert flips <= 3
+    assert abs(float(r["loss"].detach()) - float(g["loss"])) < 1e-5
     checked = 0
-    for k, gr in zip(keys, grads):
+    for k, gr in r["grads"].items():
         ref = g["grads"][k]
         assert gr is not None, k
-        if isinstance(ref, dict):
-            scale = float(ref["norm"]) + 1e-12
-            assert abs(float(gr.double().norm()) - float(ref["norm"])) / scale < GTOL, k
-            assert float((gr.flatten()[:256].cpu() - ref["head"]).abs().max()) / (float(ref["head"].abs().max()) + 1e-12) < 5e-3, k
-        elif float(ref.abs().max()) < 1e-8:
-            assert float(gr.abs().max()) < 1e-7, k
+        if not isinstance(ref, dict) and float(ref.abs().max()) < 1e-7:
+            assert float(gr.abs().max()) < 1e-6, k
         else:
-            assert relerr(gr, ref) < 5e-3, k
+            # 5e-3: the reference's own fp32 gradients sit 1e-4..4.6e-3 from an fp64 evaluation of the same
+            # graph (tests/test_oracle_golden.py::test_gradient_tolerance_is_fp32_summation_noise)
+            assert grad_err(gr, ref) < 5e-3, k
         checked += 1
     assert checked > 100
 

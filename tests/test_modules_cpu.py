@@ -64,9 +64,21 @@ def test_deform_inputs_match_reference(golden):
     assert d1[1].tolist() == [[73, 73], [36, 36], [18, 18]] and d1[2].tolist() == [0, 5329, 6625]
 
 
+def test_default_and_chunked_block_layouts_match_reference_keys():
+    """the reference's constructor default is block_chunks=1 (FSDP chunk layout, keys
+    ``blocks.<chunk>.<index>.*``); it must construct, and both layouts must carry the reference's keys."""
+    m = asis.DinoVisionTransformer(img_size=28, patch_size=14, embed_dim=32, depth=4, num_heads=2)   # all defaults
+    assert m.chunked_blocks and "blocks.0.3.norm1.weight" in m.state_dict()
+    m2 = asis.DinoVisionTransformer(img_size=28, patch_size=14, embed_dim=32, depth=4, num_heads=2, block_chunks=2)
+    assert "blocks.1.2.norm1.weight" in m2.state_dict() and "blocks.0.2.norm1.weight" not in m2.state_dict()
+    assert len(m2._real_blocks()) == 4
+    flat = asis.DinoVisionTransformer(img_size=28, patch_size=14, embed_dim=32, depth=4, num_heads=2, block_chunks=0)
+    assert "blocks.3.norm1.weight" in flat.state_dict()
+    with pytest.raises(ValueError, match="block_chunks=0"):
+        asis.AdapterEncoder(model=m2)
+
+
 def test_unsupported_configs_are_rejected():
-    with pytest.raises(NotImplementedError):
-        asis.DinoVisionTransformer(patch_size=14, block_chunks=1)
     with pytest.raises(NotImplementedError):
         asis.DinoVisionTransformer(patch_size=14, block_chunks=0, drop_path_rate=0.1)
     blk = asis.NestedTensorBlock(dim=32, num_heads=2)

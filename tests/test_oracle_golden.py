@@ -3,7 +3,9 @@
 re-association noise between two fp32 formulations of the same mathematics)."""
 import torch
 
-from conftest import relerr
+import pytest
+
+from conftest import as_fixture_entry, grad_err, mask_check, relerr
 from synth import adapter_data, encoder_data
 import oracle
 from oracle import adapter, encoder, layers, msda, vit
@@ -107,48 +109,89 @@ def test_adapter_blocks(golden):
         assert relerr(gr, g["grad_ext"][k]) < 1e-4, k
 
 
-def test_composed_encoder(golden):
-    g = golden("encoder.pt")
+def _oracle_step(g, dtype):
+    """The composed train.py data flow through the oracle in `dtype`: internals + gradients of loss + aux."""
     cfg = g["cfg"]
     img, target, gfeat = encoder_data(1, 588, 3 * cfg["dim"], 42)
-    assert torch.equal(img[:, :, ::28, ::28], g["img_lowres"])
-    assert int(target.sum()) == g["target_sum"]
     sds = {}
     for tag in ("vit", "spm", "inj", "ext", "dec"):
-        sds[tag] = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in g[tag + "_sd"].items()}
-    res = encoder.adapter_encoder(sds["vit"], sds["spm"], sds["inj"], sds["ext"], img, cfg["heads"])
+        sds[tag] = {k: (v.to(dtype).requires_grad_(True) if v.is_floating_point() else v) for k, v in g[tag + "_sd"].items()}
+    res = encoder.adapter_encoder(sds["vit"], sds["spm"], sds["inj"], sds["ext"], img.to(dtype), cfg["heads"])
     feat = res["feat"]
-    assert relerr(feat, g["feat"]) < 5e-5
-    assert relerr(res["x"], g["x"]) < 5e-5
     logits = encoder.feature_decoder(sds["dec"], feat)
     logits = torch.nn.functional.interpolate(logits, size=(588, 588), mode="bilinear")
-    assert relerr(logits[:, :, ::12, ::12], g["logits_lowres"]) < 1e-4
-    assert int(logits.argmax(1).sum()) == g["argmax_sum"]
     loss = encoder.dice_loss(torch.softmax(logits, 1), target)
-    assert abs(float(loss.detach() - g["loss"])) < 1e-6
-    aux = (feat * gfeat).sum() / feat.numel() ** 0.5
-    assert abs(float(aux.detach() - g["aux"])) < 1e-4 * max(1.0, abs(float(g["aux"])))
+    aux = (feat * gfeat.to(dtype)).sum() / feat.numel() ** 0.5
     names, params = [], []
     for key in g["grads"]:
         tag, k = key.split(".", 1)
         names.append(key)
         params.append(sds[tag][k])
     grads = torch.autograd.grad(loss + aux, params, allow_unused=True)
+    return dict(feat=feat.detach(), x=res["x"].detach(), logits=logits.detach(), loss=loss.detach(), aux=aux.detach(),
+                grads=dict(zip(names, grads)), img=img, target=target)
+
+
+@pytest.mark.parametrize("fixture", ["encoder.pt", "encoder_hd64.pt"])
+def test_composed_encoder(golden, fixture):
+    g = golden(fixture)
+    o = _oracle_step(g, torch.float32)
+    assert torch.equal(o["img"][:, :, ::28, ::28], g["img_lowres"])
+    assert int(o["target"].sum()) == g["target_sum"]
+    assert relerr(o["feat"], g["feat"]) < 5e-5
+    assert relerr(o["x"], g["x"]) < 5e-5
+    logits = o["logits"]
+    assert relerr(logits[:, :, ::12, ::12], g["logits_lowres"]) < 1e-4
+    assert relerr(logits[:, :, ::4, ::4], g["logits_s4"]) < 1e-4
+    # the reference's argmax segmentation mask, every pixel (not a checksum): identical wherever the decision is
+    # numerically determined; flips are only tolerated at near-ties (margin < 1e-4 max|logit|) and counted
+    flips, near = mask_check(logits, g, 1e-4)
+    print(f"[{fixture}] oracle fp32 vs reference mask: {flips} flips / {logits[:, 0].numel()} pixels ({near} near-ties)")
+    assert flips <= 3
+    assert abs(float(o["loss"] - g["loss"])) < 1e-6
+    assert abs(float(o["aux"] - g["aux"])) < 1e-4 * max(1.0, abs(float(g["aux"])))
     checked = 0
-    for key, gr in zip(names, grads):
+    for key, gr in o["grads"].items():
         ref = g["grads"][key]
         assert gr is not None, key
-        if isinstance(ref, dict):
-            scale = float(ref["norm"]) + 1e-12
-            assert abs(float(gr.double().norm()) - float(ref["norm"])) / scale < 2e-4, key
-            assert float((gr.flatten()[:256] - ref["head"]).abs().max()) / (float(ref["head"].abs().max()) + 1e-12) < 2e-3, key
-        elif float(ref.abs().max()) < 1e-8:
+        if not isinstance(ref, dict) and float(ref.abs().max()) < 1e-7:
             # analytically zero (a conv bias in front of a BatchNorm): both sides are rounding noise
-            assert float(gr.abs().max()) < 1e-8, key
+            assert float(gr.abs().max()) < 1e-7, key
         else:
-            assert relerr(gr, ref) < 2e-3, key
+            assert grad_err(gr, ref) < 2e-3, key
         checked += 1
     assert checked > 100
+
+
+@pytest.mark.parametrize("fixture", ["encoder.pt", "encoder_hd64.pt"])
+def test_gradient_tolerance_is_fp32_summation_noise(golden, fixture):
+    """Why parameter gradients are held to 2e-3 and not 1e-4: measure the REFERENCE's own fp32 gradients (the
+    fixture) and the fp32 oracle against an fp64 evaluation of the same graph.  Both sit at the same distance
+    from the fp64 truth -- the tolerance is the fp32 summation-order noise of 1e4..1e6-term sums, present in the
+    reference itself, not slack for the implementation."""
+    g = golden(fixture)
+    o64 = _oracle_step(g, torch.float64)
+    o32 = _oracle_step(g, torch.float32)
+    worst_ref = worst_o32 = 0.0
+    table = []
+    for key, g64 in o64["grads"].items():
+        ref = g["grads"][key]
+        if g64 is None or float(g64.abs().max()) < 1e-7:
+            continue
+        e_ref = grad_err(g64, ref)                    # reference fp32 vs fp64 truth (normalised by the reference's max)
+        e_o32 = relerr(o32["grads"][key], g64)
+        worst_ref, worst_o32 = max(worst_ref, e_ref), max(worst_o32, e_o32)
+        table.append((e_ref, e_o32, key))
+        # the fp32 oracle is never further from the truth than a few times the reference itself (+ a 1e-3 floor:
+        # the oracle's composite BatchNorm is a little less accurate in fp32 than ATen's fused one)
+        assert e_o32 < max(1e-3, 6 * e_ref), (key, e_o32, e_ref)
+    print(f"[{fixture}] worst fp32-vs-fp64 gradient error: reference {worst_ref:.2e}, oracle fp32 {worst_o32:.2e}")
+    for e_ref, e_o32, key in sorted(table, reverse=True)[:5]:
+        print(f"    {key}: reference {e_ref:.2e}  oracle fp32 {e_o32:.2e}")
+    assert worst_ref < 1e-2 and worst_o32 < 1e-2
+    # activations: fp32 is within 1e-4 of fp64, and so is the fixture
+    assert relerr(g["feat"], o64["feat"]) < 1e-4 and relerr(o32["feat"], o64["feat"]) < 1e-4
+    assert relerr(g["logits_s4"], o64["logits"][:, :, ::4, ::4]) < 1e-4
 
 
 def test_oracle_is_test_infrastructure_only():

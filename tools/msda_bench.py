@@ -11,11 +11,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from adaptersis_b200 import kernels as K  # noqa: E402
 
 
-def alg_bytes(N, S, M, D, Lq, L, P, ev, eo):
+def alg_bytes(N, shapes, M, D, Lq, P, ev, eo):
+    """Algorithmic (compulsory) bytes, SURVEY.md section 8(d): value once + locations / weights + output (fwd);
+    grad_out + value + loc/aw read, grad_value + grad_loc/grad_aw written (bwd).  A level contributes at most
+    the pixels its samples can touch: min(H*W, 4 corners * Lq * P) per head -- with few queries on a large map
+    (e.g. 1764 queries on a 184^2 level) most of the value tensor is never read and must not be counted (round 1's
+    formula counted all of S there and reported 112 % of the HBM peak)."""
     C = M * D
+    L = len(shapes)
     pts = N * Lq * M * L * P
-    fwd = ev * N * S * C + 4 * pts * 2 + 4 * pts + eo * N * Lq * C
-    bwd = eo * N * Lq * C + ev * N * S * C + 12 * pts + ev * N * S * C + 12 * pts
+    touched = sum(min(h * w, 4 * Lq * P) for h, w in shapes)          # per (image, head)
+    S = sum(h * w for h, w in shapes)
+    fwd = ev * N * touched * C + 4 * pts * 2 + 4 * pts + eo * N * Lq * C
+    # grad_value is written in full (untouched pixels get zeros), value is read where touched
+    bwd = eo * N * Lq * C + ev * N * touched * C + 12 * pts + ev * N * S * C + 12 * pts
     return fwd, bwd
 
 
@@ -69,6 +78,42 @@ def timeit(fn, iters, flush):
     return ts[len(ts) // 2]
 
 
+REAL_CASES = [("injector_real", 12, 1764, 8, 128, [(73, 73), (36, 36), (18, 18)], 4),
+              ("extractor_real", 12, 6949, 8, 128, [(42, 42)], 4)]
+
+
+def sweep_cases():
+    cases = list(REAL_CASES)
+    for Lq in (1024, 1764, 4096, 6949, 16384, 30000):
+        cases.append((f"sweep_g36_Lq{Lq}", 12, Lq, 16, 64, [(72, 72), (36, 36), (18, 18)], 4))
+    for Lq in (1764, 6949, 30000):
+        cases.append((f"sweep_g92_Lq{Lq}", 12, Lq, 16, 64, [(184, 184), (92, 92), (46, 46)], 4))
+    return cases
+
+
+def run_cases(cases, dev, peak, iters=10, dtypes=(torch.float32, torch.bfloat16), emit=None):
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    for name, N, Lq, M, D, shapes, P in cases:
+        for dtype in dtypes:
+            side = int(Lq ** 0.5)
+            qs = [(73, 73), (36, 36), (18, 18)] if name == "extractor_real" else \
+                ([(side, side)] + ([(1, Lq - side * side)] if Lq > side * side else []))
+            v, ss, lsi, loc, aw, gout = make(N, Lq, M, D, shapes, P, dtype, dev, qgrids=qs)
+            S = v.shape[1]
+            e = 4 if dtype == torch.float32 else 2
+            fb, bb = alg_bytes(N, shapes, M, D, Lq, P, e, e)
+            tf = timeit(lambda: K.msda_forward(v, ss, lsi, loc, aw), iters, flush)
+            tb = timeit(lambda: K.msda_backward(v, ss, lsi, loc, aw, gout), iters, flush)
+            row = dict(case=name, dtype=str(dtype).split(".")[-1], N=N, Lq=Lq, S=S, M=M, D=D, query_grids=qs,
+                       fwd_ms=round(tf, 4), fwd_GBs=round(fb / tf / 1e6, 1), fwd_frac=round(fb / tf / 1e6 / peak, 3),
+                       bwd_ms=round(tb, 4), bwd_GBs=round(bb / tb / 1e6, 1), bwd_frac=round(bb / tb / 1e6 / peak, 3))
+            rows.append(row)
+            if emit:
+                emit(row)
+    return rows
+
+
 def main():
     dev = torch.device("cuda:0")
     peak = 6504.1
@@ -76,34 +121,9 @@ def main():
         peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
     except Exception:
         pass
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    cases = [("injector_real", 12, 1764, 8, 128, [(73, 73), (36, 36), (18, 18)], 4),
-             ("extractor_real", 12, 6949, 8, 128, [(42, 42)], 4)]
-    for Lq in (1024, 1764, 4096, 6949, 16384, 30000):
-        cases.append((f"sweep_g36_Lq{Lq}", 12, Lq, 16, 64, [(72, 72), (36, 36), (18, 18)], 4))
-    for Lq in (1764, 6949, 30000):
-        cases.append((f"sweep_g92_Lq{Lq}", 12, Lq, 16, 64, [(184, 184), (92, 92), (46, 46)], 4))
     only = sys.argv[1] if len(sys.argv) > 1 else None
-    rows = []
-    for name, N, Lq, M, D, shapes, P in cases:
-        if only and only not in name:
-            continue
-        for dtype in (torch.float32, torch.bfloat16):
-            side = int(Lq ** 0.5)
-            qs = [(73, 73), (36, 36), (18, 18)] if name == "extractor_real" else \
-                ([(side, side)] + ([(1, Lq - side * side)] if Lq > side * side else []))
-            v, ss, lsi, loc, aw, gout = make(N, Lq, M, D, shapes, P, dtype, dev, qgrids=qs)
-            S = v.shape[1]
-            e = 4 if dtype == torch.float32 else 2
-            fb, bb = alg_bytes(N, S, M, D, Lq, len(shapes), P, e, e)
-            tf = timeit(lambda: K.msda_forward(v, ss, lsi, loc, aw), 10, flush)
-            tb = timeit(lambda: K.msda_backward(v, ss, lsi, loc, aw, gout), 10, flush)
-            row = dict(case=name, dtype=str(dtype).split(".")[-1], N=N, Lq=Lq, S=S, M=M, D=D, query_grids=qs,
-                       fwd_ms=round(tf, 4), fwd_GBs=round(fb / tf / 1e6, 1), fwd_frac=round(fb / tf / 1e6 / peak, 3),
-                       bwd_ms=round(tb, 4), bwd_GBs=round(bb / tb / 1e6, 1), bwd_frac=round(bb / tb / 1e6 / peak, 3))
-            rows.append(row)
-            print(json.dumps(row), flush=True)
-    return rows
+    cases = [c for c in sweep_cases() if not only or only in c[0]]
+    return run_cases(cases, dev, peak, emit=lambda row: print(json.dumps(row), flush=True))
 
 
 if __name__ == "__main__":
