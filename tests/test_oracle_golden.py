@@ -182,9 +182,9 @@ def test_gradient_tolerance_is_fp32_summation_noise(golden, fixture):
         e_o32 = relerr(o32["grads"][key], g64)
         worst_ref, worst_o32 = max(worst_ref, e_ref), max(worst_o32, e_o32)
         table.append((e_ref, e_o32, key))
-        # the fp32 oracle is never further from the truth than a few times the reference itself (+ a 1e-3 floor:
-        # the oracle's composite BatchNorm is a little less accurate in fp32 than ATen's fused one)
-        assert e_o32 < max(1e-3, 6 * e_ref), (key, e_o32, e_ref)
+        # the fp32 oracle is never further from the truth than a few times the reference itself (+ a 2e-3 floor:
+        # the oracle's composite BatchNorm is a little less accurate in fp32 than ATen's fused one, which accumulates in double on the CPU)
+        assert e_o32 < max(2e-3, 6 * e_ref), (key, e_o32, e_ref)
     print(f"[{fixture}] worst fp32-vs-fp64 gradient error: reference {worst_ref:.2e}, oracle fp32 {worst_o32:.2e}")
     for e_ref, e_o32, key in sorted(table, reverse=True)[:5]:
         print(f"    {key}: reference {e_ref:.2e}  oracle fp32 {e_o32:.2e}")
