@@ -490,6 +490,282 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward, version 8: every softmax warpgroup OWNS a query tile
+// ------------------------------------------------------------------------------------------------
+// A timeline of v7b (tools/attn_trace.py; profiles/r2_attn_trace.md) showed two things.  (1) The exponential phase of a
+// key tile takes a warp ~2050 clk = exactly the MUFU throughput when the other warpgroup's warp on the same scheduler
+// is in its own exponential phase (2 x 128 MUFU.EX2 x 8 clk): the kernel is MUFU bound while it runs.  (2) It does not
+// run all the time: the two warpgroups split the KEY tiles of one query tile, so at the end of every item (14 key
+// tiles) they meet, exchange (m, l, O) through shared memory and one of them merges and stores -- 7 k clk per item in
+// which the other warpgroup and the tensor pipe idle: 26 % of the kernel.
+// Here an item is a PAIR of query tiles (256 queries) of one (image, head); warpgroup w keeps (m, l, O) of query tile
+// 2*pair + w over all key tiles and normalises / stores it alone: no exchange, no merge, no cross-warpgroup barrier.
+// K and V tiles are fetched once per pair (half the TMA / L2 traffic), both warpgroups' MMAs read the same stages.
+// TMEM (512 columns): per warpgroup S [128] | P [64] (bf16 pairs) | O [64].  P has its own columns, so S(j+1) may be
+// issued as soon as the softmax warps have pulled S(j) into registers -- one score tile ahead is all that is needed.
+constexpr int F8_STAGES = 4;
+constexpr int F8_SMEM = 2 * 2 * T16K /*Q: 2 warpgroups x 2 buffers*/ + F8_STAGES * 2 * T16K /*K, V rings*/ + 1024 /*align*/ + 512 /*barriers*/;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const int num_items, const int npair) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *sQ = smem;                            // [buffer][warpgroup] tiles
+  uint8_t *sK = sQ + 4 * T16K;
+  uint8_t *sV = sK + F8_STAGES * T16K;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sV + F8_STAGES * T16K);
+  uint64_t *q_full = bars, *q_empty = q_full + 2, *k_full = q_empty + 2, *k_empty = k_full + F8_STAGES,
+           *v_full = k_empty + F8_STAGES, *v_empty = v_full + F8_STAGES, *s_full = v_empty + F8_STAGES, *s_free = s_full + 2,
+           *p_full = s_free + 2, *o_full = p_full + 2, *o_empty = o_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int TMA_WARP = 8, MMA_WARP = 9;      // the SMSP arbiter favours the highest warp id (see v7b)
+  const int C = p.H * HD;
+  const int nkv = (p.T + TILE - 1) / TILE;
+  const int n_my = (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int G = n_my * nkv;
+
+  if (warp == TMA_WARP && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + i, 1);
+      mbar_init(q_empty + i, 1);
+      mbar_init(s_full + i, 1);
+      mbar_init(s_free + i, 4);
+      mbar_init(p_full + i, 4);
+      mbar_init(o_full + i, 1);
+      mbar_init(o_empty + i, 4);
+    }
+    for (int i = 0; i < F8_STAGES; ++i) {
+      mbar_init(k_full + i, 1);
+      mbar_init(k_empty + i, 1);
+      mbar_init(v_full + i, 1);
+      mbar_init(v_empty + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // warpgroup w: S at w*256, P at w*256 + 128, O at w*256 + 192
+  constexpr uint32_t WG_COLS = 256, P_OFF = 128, O_OFF = 192;
+
+  if (warp == TMA_WARP) {
+    // K(i) is requested one tile ahead of V(i-1): the MMA warp issues S(g+1) before P V(g)
+    for (int i = 0; i <= G; ++i) {
+      if (i < G) {
+        const int k = i / nkv, j = i - k * nkv;
+        const int item = (int)blockIdx.x + k * (int)gridDim.x;
+        const int bh = item / npair, pr = item - bh * npair, h = bh % p.H, b = bh / p.H;
+        if (j == 0) {
+          const int qbuf = k & 1;
+          if (k >= 2) mbar_wait_wd(q_empty + qbuf, ((k >> 1) - 1) & 1);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(q_full + qbuf, 2 * T16K);
+            tma_load_3d(&tmQKV, q_full + qbuf, sQ + (qbuf * 2 + 0) * T16K, h * HD, (2 * pr) * TILE, b);
+            tma_load_3d(&tmQKV, q_full + qbuf, sQ + (qbuf * 2 + 1) * T16K, h * HD, (2 * pr + 1) * TILE, b);   // rows >= T: zero fill
+          }
+          __syncwarp();
+        }
+        const int st = i % F8_STAGES, use = i / F8_STAGES;
+        if (use > 0) mbar_wait_wd(k_empty + st, (use - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(k_full + st, T16K);
+          tma_load_3d(&tmQKV, k_full + st, sK + st * T16K, C + h * HD, j * TILE, b);
+        }
+        __syncwarp();
+      }
+      const int g = i - 1;
+      if (g >= 0) {
+        const int k = g / nkv, j = g - k * nkv;
+        const int item = (int)blockIdx.x + k * (int)gridDim.x;
+        const int bh = item / npair, h = bh % p.H, b = bh / p.H;
+        const int st = g % F8_STAGES, use = g / F8_STAGES;
+        if (use > 0) mbar_wait_wd(v_empty + st, (use - 1) & 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(v_full + st, T16K);
+          tma_load_3d(&tmQKV, v_full + st, sV + st * T16K, 2 * C + h * HD, j * TILE, b);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    constexpr uint32_t idesc_s = make_idesc(TILE, TILE, 0, 0);   // S = Q K^T : both K-major
+    constexpr uint32_t idesc_o = make_idesc(TILE, HD, 0, 1);     // O = P V   : V is MN-major
+    const uint64_t dQ = desc_kmajor(smem_u32(sQ), 0), dK = desc_kmajor(smem_u32(sK), 0), dV = desc_mnmajor(smem_u32(sV), 0);
+    constexpr uint32_t STAGE16 = T16K >> 4;
+    // incremental (item, tile, stage, phase) counters of the score stream (one tile ahead) and of the P V stream
+    struct Stream { int g, k, j, st; uint32_t ph; } ss{0, 0, 0, 0, 0}, ps{0, 0, 0, 0, 0};
+    auto step = [&](Stream &x) {
+      ++x.g;
+      if (++x.j == nkv) { x.j = 0; ++x.k; }
+      if (++x.st == F8_STAGES) { x.st = 0; x.ph ^= 1; }
+    };
+    auto issue_s = [&]() {              // S_w(g) = Q_w K(g)^T for both warpgroups
+      const int qbuf = ss.k & 1;
+      if (ss.j == 0) mbar_wait_wd(q_full + qbuf, (ss.k >> 1) & 1);
+      mbar_wait_wd(k_full + ss.st, ss.ph);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        if (ss.g > 0) mbar_wait_wd(s_free + w, (ss.g - 1) & 1);        // the softmax warps hold S_w(g-1) in registers
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a = dQ + (uint32_t)((qbuf * 2 + w) * STAGE16), bdesc = dK + (uint32_t)(ss.st * STAGE16);
+          const uint32_t d = tmem + w * WG_COLS;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(d, a + 2 * kk, bdesc + 2 * kk, idesc_s, kk > 0);
+          umma_commit(s_full + w);
+          if (w == 1) {
+            umma_commit(k_empty + ss.st);
+            if (ss.j == nkv - 1) umma_commit(q_empty + qbuf);      // both Q tiles may be refilled (item k + 2)
+          }
+        }
+        __syncwarp();
+      }
+      step(ss);
+    };
+    if (G > 0) issue_s();
+    for (; ps.g < G; step(ps)) {
+      if (ss.g < G) issue_s();
+      mbar_wait_wd(v_full + ps.st, ps.ph);
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        mbar_wait_wd(p_full + w, ps.g & 1);
+        if (ps.j == 0 && ps.k > 0) mbar_wait_wd(o_empty + w, (ps.k - 1) & 1);   // the previous item's O_w has been read
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t bdesc = dV + (uint32_t)(ps.st * STAGE16);
+          const uint32_t d = tmem + w * WG_COLS + O_OFF, a = tmem + w * WG_COLS + P_OFF;
+          const uint32_t acc0 = ps.j > 0;
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)     // O_w (+)= P_w V, accumulated in TMEM over the item's key tiles
+            umma_bf16_ts(d, a + kk * 8, bdesc + 128 * kk, idesc_o, kk > 0 ? 1u : acc0);
+          umma_commit(o_full + w);
+          if (w == 1) umma_commit(v_empty + ps.st);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int w = warp >> 2;                        // warpgroup = query tile of the pair
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;            // row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tS = tmem + lane_addr + w * WG_COLS, tP = tS + P_OFF, tO = tS + O_OFF;
+    for (int k = 0; k < n_my; ++k) {
+      const int item = (int)blockIdx.x + k * (int)gridDim.x;
+      const int pr = item % npair, bh = item / npair, h = bh % p.H, b = bh / p.H;
+      const int g0 = k * nkv;
+      // running state in the log2 domain; O_w lives in TMEM and is only touched here when the running maximum grows
+      // by more than 2^8 (lazy rescaling, as in v7b)
+      float m_use = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nkv; ++j) {
+        const int g = g0 + j;
+        const int kv0 = j * TILE;
+        mbar_wait_wd(s_full + w, g & 1);
+        tc_fence_after();
+        float s[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32_issue(tS + c * 32, s[c]);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free + w);            // S_w may be overwritten by the next score tile
+        if (kv0 + TILE > p.T) {                            // only the last key block has invalid columns
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (kv0 + c * 32 + i >= p.T) s[c][i] = -INFINITY;
+        }
+        float mx4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          mx4[c] = fmaxf(s[c][0], s[c][1]);
+#pragma unroll
+          for (int i = 2; i < 32; i += 2) mx4[c] = fmaxf(mx4[c], fmaxf(s[c][i], s[c][i + 1]));
+        }
+        const float m_new = fmaxf(m_use, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2);
+        if (j > 0) {
+          // P V(g-1) complete: O_w is consistent and the P columns are free.  Every phase of o_full[w] is observed
+          // in order (here, or at the end of the item), so the parity waits cannot alias (see v7b's post-mortem).
+          mbar_wait_wd(o_full + w, (g - 1) & 1);
+          tc_fence_after();
+        }
+        if (j == 0) {
+          m_use = m_new;
+        } else {
+          const bool grow = m_new - m_use > 8.f;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float alpha = grow ? fast_exp2(m_use - m_new) : 1.f;
+            if (grow) m_use = m_new;
+            l_run *= alpha;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {                // 32 columns at a time: the score row owns the registers
+              float o0[32];
+              tmem_ld32(tO + c * 32, o0);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o0[i] *= alpha;
+              tmem_st32(tO + c * 32, o0);
+            }
+            tmem_st_wait();
+          }
+        }
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t pk[32];                               // keys [64 half, 64 half + 64), two per word
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const float e0 = fast_exp2(fmaf(s[2 * half + c][i], p.scale_log2, -m_use));
+              const float e1 = fast_exp2(fmaf(s[2 * half + c][i + 1], p.scale_log2, -m_use));
+              l4[(i >> 1) & 3] += e0 + e1;
+              __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+              pk[c * 16 + (i >> 1)] = *reinterpret_cast<uint32_t *>(&hh);
+            }
+          tmem_st32u(tP + half * 32, pk);
+        }
+        l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + w);
+      }
+      // ---- item epilogue: this warpgroup's query tile is complete -- normalise and store, nobody to wait for
+      mbar_wait_wd(o_full + w, (g0 + nkv - 1) & 1);
+      tc_fence_after();
+      float o[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float v[32];
+        tmem_ld32(tO + c * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = v[i];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty + w);           // the next item's first P V may overwrite O_w
+      const int t = (2 * pr + w) * TILE + row;
+      if (t < p.T) {
+        store_out64(p.out + ((size_t)b * p.T + t) * C + h * HD, o, 1.f / l_run);
+        p.lse[((size_t)b * p.H + h) * p.T + t] = (m_use + log2f(l_run)) * LN2;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // backward prep: D[b,h,t] = sum_e dO[b,t,h,e] * O[b,t,h,e] and lse * log2(e), both written with a
 // row pitch Tp = ceil(T/64)*64 (zero tail), so that the kernels can bulk-copy 64-entry tiles and
 // never need a bounds check
@@ -902,6 +1178,7 @@ int attention_tc_forward(const void *qkv, void *out, float *lse, int B, int T, i
   static bool configured = false;
   if (!configured) {
     if (int rc = set_smem((const void *)attn_fwd_kernel, FWD_SMEM)) return rc;
+    if (int rc = set_smem((const void *)attn_fwd8_kernel, F8_SMEM)) return rc;
     configured = true;
   }
   AttnParams p{};
@@ -911,9 +1188,22 @@ int attention_tc_forward(const void *qkv, void *out, float *lse, int B, int T, i
   p.out = (bf16 *)out;
   p.lse = lse;
   const int nqb = (T + TILE - 1) / TILE;
-  const int num_items = nqb * H * B;
+  static int version = -1;      // ASIS_ATTN_FWD=7: the v7b kernel (warpgroups split the key tiles), kept for comparison
+  if (version < 0) {
+    const char *e = getenv("ASIS_ATTN_FWD");
+    version = e ? atoi(e) : 8;
+  }
+  if (version == 7) {
+    const int num_items = nqb * H * B;
+    const int grid = num_items < sm_count() ? num_items : sm_count();
+    attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, st>>>(tq, p, num_items, nqb);
+    ASIS_LAUNCHED();
+    return ASIS_OK;
+  }
+  const int npair = (nqb + 1) / 2;
+  const int num_items = npair * H * B;
   const int grid = num_items < sm_count() ? num_items : sm_count();
-  attn_fwd_kernel<<<grid, ATT_THREADS, FWD_SMEM, st>>>(tq, p, num_items, nqb);
+  attn_fwd8_kernel<<<grid, ATT_THREADS, F8_SMEM, st>>>(tq, p, num_items, npair);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }

@@ -236,6 +236,189 @@ __device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, 
   }
 }
 
+// ---- lean slab epilogue (CTA-pair kernel) ------------------------------------------------------------
+// A timeline of the first pair kernel (tools/gemm_trace.py, profiles/r2_gemm_trace.md) showed the epilogue, not the
+// MMA main loop, setting the tile period: 8.0 k clk per 128 x 256 tile for the plain bias epilogue, 12.4 k / 13.9 k for
+// GELU without / with the saved pre-activation, against 8.3-9.6 k clk of MMAs.  Software-pipelining the chunks (TMEM
+// load of chunk c+1 under chunk c, alternating transposition buffers) changed nothing, and the SASS said why: ~25
+// instructions per output element, most of them 64-bit address arithmetic ((size_t)row * ld + col redone for every
+// 4-element group of every operand), run-time dtype selects, per-element bounds predicates and generic-space LD/ST
+// for the transposition buffer -- the epilogue warps were ISSUE bound.  This version keeps the pipelining and
+//   * takes the output dtype as a template parameter and assumes bf16 for the optional aux operand,
+//   * handles only slabs that lie inside N with 16-byte-aligned pitches (everything else, and split-K, goes to
+//     the generic epi_slab), so no column predicates,
+//   * carries one byte pointer per operand per lane and reaches row group `it` with one IMAD.WIDE,
+//   * replaces the per-row M predicate by a per-lane count of valid row groups,
+//   * uses 32-bit shared-window addresses (ld/st.shared) whose swizzle is folded into two per-lane bases.
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ uint2 pack_bf16x4(const float (&v)[4]) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+  return make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
+}
+
+template <int KIND> struct EpiHasBias { static constexpr bool value = KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE; };
+
+// state of one lane for one slab: byte pointers at (its first row, its 4 columns of the current chunk)
+struct EpiLane {
+  char *c;               // output
+  char *aux;             // GELU / SCALE_RESIDUAL: optional bf16 output (null: none)
+  const char *in2;       // SCALE_RESIDUAL: residual f32; DGELU: saved pre-activation bf16; ACCUMULATE: C f32
+  uint32_t cstep, astep, istep;   // bytes between row groups (4 rows)
+  int nit;               // valid row groups of this lane (rows < M)
+};
+
+template <int KIND>
+__device__ __forceinline__ void epi3_prefetch(const EpiLane &L, uint4 (&pre)[8]) {
+  if (!EpiReads<KIND>::value) return;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    if (it < L.nit) {
+      const char *q = L.in2 + (size_t)((uint32_t)it * L.istep);
+      if (KIND == ASIS_EPI_DGELU) {
+        const uint2 t = *reinterpret_cast<const uint2 *>(q);
+        pre[it] = make_uint4(t.x, t.y, 0u, 0u);
+      } else {
+        pre[it] = *reinterpret_cast<const uint4 *>(q);
+      }
+    }
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void epi3_colvec(const GemmTcParams &p, int col, float4 &b4, float4 &g4) {
+  const EpiArgs &e = p.epi;
+  b4 = g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (EpiHasBias<KIND>::value && e.bias) b4 = __ldg(reinterpret_cast<const float4 *>(e.bias + col));
+  if (KIND == ASIS_EPI_SCALE_RESIDUAL) g4 = __ldg(reinterpret_cast<const float4 *>(e.gamma + col));
+}
+
+// one transposed 32 x 32 chunk read back as lane -> (row it*4 + lane/8, 4 columns): fused math, coalesced stores
+template <int KIND, bool CBF16>
+__device__ __forceinline__ void epi3_chunk(const EpiLane &L, uint32_t rd0, uint32_t rd1, const float4 &b4, const float4 &g4,
+                                           const uint4 (&cur)[8]) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    if (it < L.nit) {
+      const float4 t = lds128(((it & 1) ? rd1 : rd0) + it * 512);
+      float w[4] = {t.x, t.y, t.z, t.w};
+      if (EpiHasBias<KIND>::value) { w[0] += b4.x; w[1] += b4.y; w[2] += b4.z; w[3] += b4.w; }
+      if (KIND == ASIS_EPI_GELU || KIND == ASIS_EPI_SCALE_RESIDUAL) {
+        if (L.aux) *reinterpret_cast<uint2 *>(L.aux + (size_t)((uint32_t)it * L.astep)) = pack_bf16x4(w);
+      }
+      if (KIND == ASIS_EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = gelu_fast(w[i]);
+      } else if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
+        w[0] = fmaf(g4.x, w[0], __uint_as_float(cur[it].x)); w[1] = fmaf(g4.y, w[1], __uint_as_float(cur[it].y));
+        w[2] = fmaf(g4.z, w[2], __uint_as_float(cur[it].z)); w[3] = fmaf(g4.w, w[3], __uint_as_float(cur[it].w));
+      } else if (KIND == ASIS_EPI_DGELU) {
+        const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162 *>(&cur[it].x);
+        const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162 *>(&cur[it].y);
+        w[0] *= dgelu_fast(__low2float(ha)); w[1] *= dgelu_fast(__high2float(ha));
+        w[2] *= dgelu_fast(__low2float(hb)); w[3] *= dgelu_fast(__high2float(hb));
+      } else if (KIND == ASIS_EPI_ACCUMULATE) {
+        w[0] += __uint_as_float(cur[it].x); w[1] += __uint_as_float(cur[it].y);
+        w[2] += __uint_as_float(cur[it].z); w[3] += __uint_as_float(cur[it].w);
+      }
+      char *q = L.c + (size_t)((uint32_t)it * L.cstep);
+      if (CBF16) *reinterpret_cast<uint2 *>(q) = pack_bf16x4(w);
+      else *reinterpret_cast<float4 *>(q) = make_float4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// the epilogue of one 32-row x 128-column slab (entirely inside N) owned by one warp; `stage_u32`: two 4 KB buffers
+template <int KIND, bool CBF16>
+__device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr, uint32_t stage_u32, int row0, int col_base,
+                                          int lane, uint64_t *tfull, uint32_t tfull_phase, int tr_idx) {
+  const EpiArgs &e = p.epi;
+  const int cg = lane & 7, r = lane >> 3;
+  (void)tr_idx;
+  constexpr uint32_t CE = CBF16 ? 2 : 4;
+  int col = col_base + cg * 4;
+  EpiLane L;
+  {
+    const size_t eoff = (size_t)(row0 + r) * e.ldc + col;
+    L.c = reinterpret_cast<char *>(e.C) + eoff * CE;
+    L.cstep = (uint32_t)(4 * e.ldc) * CE;
+    const int left = p.M - row0 - r;
+    L.nit = left <= 0 ? 0 : (left + 3 >= 32 ? 8 : (left + 3) >> 2);
+    L.aux = nullptr;
+    L.astep = (uint32_t)(4 * e.ldaux) * 2u;
+    L.in2 = nullptr;
+    L.istep = 0;
+    if ((KIND == ASIS_EPI_GELU || KIND == ASIS_EPI_SCALE_RESIDUAL) && e.aux)
+      L.aux = reinterpret_cast<char *>(e.aux) + ((size_t)(row0 + r) * e.ldaux + col) * 2;
+    if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
+      L.in2 = reinterpret_cast<const char *>(e.residual) + eoff * 4;
+      L.istep = (uint32_t)(4 * e.ldc) * 4u;
+    } else if (KIND == ASIS_EPI_ACCUMULATE) {
+      L.in2 = reinterpret_cast<const char *>(e.C) + eoff * 4;
+      L.istep = (uint32_t)(4 * e.ldc) * 4u;
+    } else if (KIND == ASIS_EPI_DGELU) {
+      L.in2 = reinterpret_cast<const char *>(e.aux) + ((size_t)(row0 + r) * e.ldaux + col) * 2;
+      L.istep = L.astep;
+    }
+  }
+  constexpr uint32_t I2E = KIND == ASIS_EPI_DGELU ? 2 : 4;       // element size of the second operand
+  // transposition buffers: write side (thread = row `lane`), read side (row it*4 + r, 16-byte group cg)
+  const uint32_t wrA = stage_u32 + lane * 128 + ((lane & 7) << 4), wrB = wrA + 4096;
+  const uint32_t rdA0 = stage_u32 + r * 128 + ((cg ^ r) << 4), rdA1 = stage_u32 + r * 128 + ((cg ^ (r + 4)) << 4);
+  uint4 pre[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) pre[i] = make_uint4(0u, 0u, 0u, 0u);
+  float4 b4n, g4n;
+  epi3_colvec<KIND>(p, col, b4n, g4n);                    // chunk 0's columns
+  epi3_prefetch<KIND>(L, pre);                            // in flight while the MMAs of this tile finish
+  if (tr_idx >= 0) GEMM_TRACE(3, tr_idx);
+  mbar_wait(tfull, tfull_phase);
+  tc_fence_after();
+  if (tr_idx >= 0) GEMM_TRACE(4, tr_idx);
+  float va[32], vb[32];
+  tmem_ld32_issue(taddr, va);
+#pragma unroll 1
+  for (int c2 = 0; c2 < 2; ++c2) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {           // h = 0: registers va, buffer A;  h = 1: registers vb, buffer B
+      const bool last = (c2 == 1 && h == 1);
+      tmem_ld_wait();
+      if (!last) {
+        if (h == 0) tmem_ld32_issue(taddr + (2 * c2 + 1) * 32, vb);
+        else tmem_ld32_issue(taddr + 2 * 32, va);
+      }
+      const uint32_t wr = h == 0 ? wrA : wrB;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float *v = h == 0 ? va : vb;
+        sts128(wr ^ (g << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+      }
+      __syncwarp();
+      const float4 b4 = b4n, g4 = g4n;
+      uint4 cur[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) cur[i] = pre[i];
+      if (!last) {                          // next chunk's column vectors and second operand, under this chunk's math
+        epi3_colvec<KIND>(p, col + 32, b4n, g4n);
+        L.in2 += EpiReads<KIND>::value ? 32 * I2E : 0;
+        epi3_prefetch<KIND>(L, pre);
+      }
+      epi3_chunk<KIND, CBF16>(L, (h == 0 ? rdA0 : rdA0 + 4096), (h == 0 ? rdA1 : rdA1 + 4096), b4, g4, cur);
+      L.c += 32 * CE;
+      if (L.aux) L.aux += 32 * 2;
+      col += 32;
+    }
+  }
+  __syncwarp();     // the buffers are rewritten by the next tile's first chunks
+}
+
 template <int A_MN, int B_MN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
@@ -427,16 +610,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // (cluster rank 0) issues every instruction for both tensor cores, which read the other half of B from the peer's
 // shared memory.  Per CTA and k-block that is 32 KB filled + 32 KB read instead of 48 + 48 (with the multicast
 // version every CTA still holds -- and its tensor core still reads -- the whole B tile): the 128 B/clk
-// shared-memory port, not the tensor pipe, was what capped the 1-CTA kernel (TMA fill 96 B/clk + operand reads
-// 96 B/clk at full MMA rate).  The smaller stage also buys a deeper ring: 6 x 32 KB.
+// shared-memory port is what this relieves (TMA fill 96 B/clk + operand reads 96 B/clk at full MMA rate in the
+// 1-CTA kernel).  Ring: 5 x 32 KB.
 // Protocol (as in DeepGEMM's sm_100 kernels): both producers report their TMA bytes to the LEADER's full barrier
 // (cp.async.bulk.tensor.cta_group::2 with a shared::cluster barrier address; arrival count 2 = leader's
 // arrive.expect_tx + the peer's plain arrive); tcgen05.commit.cta_group::2 multicasts "stage free" / "accumulator
 // complete" to both CTAs; the epilogue warps of both CTAs release the accumulator on the leader's barrier.
-constexpr int STAGES2 = 6;
+constexpr int STAGES2 = 5;
 constexpr int B2_BYTES = (BN / 2) * BK * 2;           // 16 KB: this CTA's half of the B tile
 constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;      // 32 KB
-constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int EPI2_STAGE_BYTES = 2 * EPI_STAGE_BYTES; // two transposition buffers per epilogue warp (epi_slab2)
+constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + EPI2_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(GEMM2_SMEM <= 227 * 1024, "pair kernel: shared memory over the 227 KB limit");
 
 template <int A_MN, int B_MN>
@@ -445,7 +629,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float *epi_stage = reinterpret_cast<float *>(smem + STAGES2 * STAGE2_BYTES);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES + EPI_STAGE_BYTES);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES2 * STAGE2_BYTES + EPI2_STAGE_BYTES);
   uint64_t *empty_bar = full_bar + STAGES2;
   uint64_t *tfull_bar = empty_bar + STAGES2;
   uint64_t *tempty_bar = tfull_bar + 2;
@@ -485,10 +669,14 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int m_blk = (tile % p.m_groups) * 2 + crank;
-      const int rest = tile / p.m_groups;
-      const int n_blk = rest % p.n_tiles;
-      const int split = rest / p.n_tiles;
+      // N fastest: the n-tiles of one pair of m-tiles run on neighbouring clusters at the same time, so an A tile
+      // (activations, streamed once) is fetched from HBM once and hit in L2 by the others; the B operand (weights,
+      // a few MB) is L2-resident anyway.  With M fastest a K = 4096, N = 1024 GEMM re-read its 173 MB A operand from
+      // HBM once per n-tile.
+      const int n_blk = tile % p.n_tiles;
+      const int rest = tile / p.n_tiles;
+      const int m_blk = (rest % p.m_groups) * 2 + crank;
+      const int split = rest / p.m_groups;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       const int n0 = n_blk * BN + crank * (BN / 2);            // this CTA's half of the B tile
@@ -531,7 +719,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int split = (tile / p.m_groups) / p.n_tiles;
+        const int split = (tile / p.n_tiles) / p.m_groups;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         GEMM_TRACE(7, tile / num_clusters);
@@ -575,21 +763,41 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.epi.ldc % 4 == 0) && (!p.epi.aux || p.epi.ldaux % 4 == 0);
-    float *stage = epi_stage + ew * EPI_STAGE_FLOATS;
+    float *stage = epi_stage + ew * 2 * EPI_STAGE_FLOATS;
     const uint32_t ltempty0 = mapa_u32(tempty_bar, 0);     // the leader's accumulator-free barriers
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int m_blk = (tile % p.m_groups) * 2 + crank;
-      const int n_blk = (tile / p.m_groups) % p.n_tiles;
+      const int n_blk = tile % p.n_tiles;
+      const int m_blk = ((tile / p.n_tiles) % p.m_groups) * 2 + crank;
       const int row0 = m_blk * BM + quarter * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 128;
       const int col_base = n_blk * BN + half * 128;
       const int tr = ew == 0 ? tile / num_clusters : -1;     // (trace builds: stamps of epilogue warp 0)
-      switch (p.epi.kind) {
-        case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
-        case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
-        case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
-        case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
-        default: epi_slab<ASIS_EPI_NONE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+      // slabs inside N with vectorisable pitches and a bf16 (or no) aux operand take the lean epilogue
+      const bool lean = vec_ok && !p.atomic_out && col_base + 128 <= p.N && (!p.epi.aux || p.epi.aux_dtype == ASIS_BF16);
+      if (lean) {
+        const uint32_t st32 = smem_u32(stage);
+        const bool cb = p.epi.c_dtype == ASIS_BF16;
+#define ASIS_EPI3(K)                                                                                                   \
+  do {                                                                                                                 \
+    if (cb) epi_slab3<K, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr);                  \
+    else epi_slab3<K, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr);                    \
+  } while (0)
+        switch (p.epi.kind) {
+          case ASIS_EPI_GELU: ASIS_EPI3(ASIS_EPI_GELU); break;
+          case ASIS_EPI_SCALE_RESIDUAL: epi_slab3<ASIS_EPI_SCALE_RESIDUAL, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_DGELU: ASIS_EPI3(ASIS_EPI_DGELU); break;
+          case ASIS_EPI_ACCUMULATE: epi_slab3<ASIS_EPI_ACCUMULATE, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr); break;
+          default: ASIS_EPI3(ASIS_EPI_NONE); break;
+        }
+#undef ASIS_EPI3
+      } else {
+        switch (p.epi.kind) {
+          case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+          default: epi_slab<ASIS_EPI_NONE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+        }
       }
       tc_fence_before();
       __syncwarp();

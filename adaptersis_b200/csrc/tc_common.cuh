@@ -48,16 +48,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// ASIS_WATCHDOG (defined by a translation unit before including this header): a wait that has not been satisfied
-// after ~2 s of SM clocks traps, so a protocol bug aborts the launch with an error instead of hanging the GPU.
-// The clock is only read on the slow path (the first try_wait failed).
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-#ifdef ASIS_WATCHDOG
+// mbar_wait_wd: a wait that has not been satisfied after ~2 s of SM clocks traps, so a protocol bug aborts the
+// launch with an error instead of hanging the GPU; the clock is only read on the slow path (the first try_wait
+// failed).  A translation unit that defines ASIS_WATCHDOG before including this header gets it for every mbar_wait.
+__device__ __forceinline__ void mbar_wait_wd(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef ASIS_WATCHDOG
+  mbar_wait_wd(bar, parity);
 #else
   while (!mbar_try_wait(bar, parity)) {
   }
