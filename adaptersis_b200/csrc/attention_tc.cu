@@ -122,6 +122,28 @@ __device__ __forceinline__ void store_row32(uint8_t *tile, int rows, int row, in
   }
 }
 
+// 32 floats -> 16 words of two bf16 each (element 2i in the low half)
+__device__ __forceinline__ void pack32_bf16(const float (&v)[32], uint32_t (&w)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t *>(&h);
+  }
+}
+
+// One row (64 bf16 = 128 bytes) of a K-major, 128B-swizzled smem tile -> 32 TMEM columns of lane `row` (two consecutive
+// K elements per column): the layout tcgen05.mma expects for an A operand in tensor memory.
+__device__ __forceinline__ void row_to_tmem(const uint8_t *tile, int row, uint32_t taddr) {
+  const uint8_t *src = tile + (row >> 3) * 1024 + (row & 7) * 128;
+  uint32_t w[32];
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    const uint4 t = *reinterpret_cast<const uint4 *>(src + ((ch ^ (row & 7)) << 4));
+    w[4 * ch] = t.x; w[4 * ch + 1] = t.y; w[4 * ch + 2] = t.z; w[4 * ch + 3] = t.w;
+  }
+  tmem_st32u(taddr, w);
+}
+
 struct AttnParams {
   int B, T, H;
   float scale_log2;  // hd^-0.5 * log2(e)
@@ -810,7 +832,7 @@ __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16 *__restri
 // backward, dK / dV: one CTA per (128-key block, head, image); loops over 64-query tiles
 // ------------------------------------------------------------------------------------------------
 constexpr int BWD_STAGES = 4;
-constexpr int BWD_SMEM = 2 * T16K /*resident pair*/ + BWD_STAGES * 2 * T8K /*streamed pair*/ + 2 * 2 * T16K /*2 bufs x 2 WGs*/ +
+constexpr int BWD_SMEM = 2 * T16K /*resident pair*/ + BWD_STAGES * 2 * T8K /*streamed pair*/ +
                          BWD_STAGES * 2 * HALF * 4 /*lse, D tiles*/ + 1024 + 256;
 
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -822,16 +844,23 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
   uint8_t *sV = sK + T16K;
   uint8_t *sQ = sV + T16K;                 // BWD_STAGES x 8 KB
   uint8_t *sDO = sQ + BWD_STAGES * T8K;    // BWD_STAGES x 8 KB
-  uint8_t *sPT = sDO + BWD_STAGES * T8K;   // P^T   [128 keys x 64 queries], one per warpgroup
-  uint8_t *sDST = sPT + 2 * T16K;          // dS^T, one per warpgroup
-  float *sLse = reinterpret_cast<float *>(sDST + 2 * T16K);   // [BWD_STAGES][64]  lse * log2e of the stage's queries
+  // P^T and dS^T (bf16) never touch shared memory: each softmax thread writes them back over the first half of the
+  // TMEM columns it has just read (its 32 S^T columns -> 16 columns of packed P^T, its 32 dP^T columns -> 16 columns of
+  // packed dS^T) and the second pair of GEMMs takes them as the A operand straight from TMEM, as the forward does.
+  // With both staged in smem a 64-query tile moved ~150 KB through the 128 B/clk shared-memory port (4 x 24 KB of MMA
+  // operand reads, 32 KB of st.shared, the TMA fills) = ~1170 clk against 512 clk of MMA: the kernel was
+  // shared-memory bound (ncu: tensor pipe 30 %, 61 M shared wavefronts per launch).
+  float *sLse = reinterpret_cast<float *>(sDO + BWD_STAGES * T8K);   // [BWD_STAGES][64]  lse * log2e of the stage's queries
   float *sD = sLse + BWD_STAGES * HALF;                       // [BWD_STAGES][64]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sD + BWD_STAGES * HALF);
   uint64_t *kv_full = bars, *q_full = bars + 1, *q_empty = q_full + BWD_STAGES, *s_full = q_empty + BWD_STAGES,
-           *s_empty = s_full + NSB, *p_full = s_empty + NSB, *pbuf_free = p_full + 2, *acc_full = pbuf_free + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+           *p_full = s_full + NSB, *acc_full = p_full + 2, *op_full = acc_full + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(op_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ASIS_TRACE
+  unsigned long long *tr = (blockIdx.y == 0 && blockIdx.z == 0) ? g_attn_trace : nullptr;   // CTA (0,0,0) only
+#endif
   const int k0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
   const int C = p.H * HD;
   const int nq = (p.T + HALF - 1) / HALF;
@@ -846,15 +875,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
       mbar_init(q_full + i, 1);
       mbar_init(q_empty + i, 1);
     }
-    for (int i = 0; i < NSB; ++i) {
-      mbar_init(s_full + i, 1);
-      mbar_init(s_empty + i, 8);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(p_full + i, 8);
-      mbar_init(pbuf_free + i, 1);
-    }
+    for (int i = 0; i < 2; ++i) mbar_init(s_full + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(p_full + i, 8);
     mbar_init(acc_full, 1);
+    mbar_init(op_full, 16);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -862,8 +886,14 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // score buffer sb (tile i uses i % 3): S^T at sb*128, dP^T at sb*128 + 64; dV at 384, dK at 448
-  const uint32_t tSC = tmem, tDV = tmem + NSB * 2 * HALF, tDK = tDV + HD;
+  // Two score buffers (tile i uses i % 2): S^T at sb*128, dP^T at sb*128 + 64; dV at 256, dK at 320; the CTA's own K and
+  // V tiles as TMEM-RESIDENT A operands at 384 / 416 (32 columns each).  A 128 x 64 x 16 MMA with both operands in shared
+  // memory fetches 4 KB (A) + 2 KB (B) for 32 clk of math = 192 B/clk from a 128 B/clk port: the MMA warp's timeline
+  // (tools/attn_bwd_trace.py) showed ~1150 clk to get 16 such MMAs accepted per 64-query tile, against 512 clk of math --
+  // the kernel was paced by operand fetch.  K and V are the same for every tile of the CTA, so they are copied into
+  // tensor memory once; with P^T / dS^T there as well every MMA of the kernel reads only its 2 KB B operand from smem.
+  constexpr int NSBK = 2;
+  const uint32_t tSC = tmem, tDV = tmem + NSBK * 2 * HALF, tDK = tDV + HD, tKop = tDK + HD, tVop = tKop + HD / 2;
 
   if (warp == 0) {
     const float *lse_b = p.lse2 + ((size_t)b * p.H + h) * Tp;
@@ -890,43 +920,50 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
     {
       constexpr uint32_t idesc_s = make_idesc(TILE, HALF, 0, 0);   // [128 keys] x [64 queries]
       constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);     // [128 keys] x [64 hd], B MN-major
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aDO = smem_u32(sDO),
-                     aPT = smem_u32(sPT), aDST = smem_u32(sDST);
-      mbar_wait(kv_full, 0);
+      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO);
+      mbar_wait(op_full, 0);                // K and V are in tensor memory
+      tc_fence_after();
+      // Score buffer i % 2 is rewritten by tile i + 2; its previous readers are the softmax warps of tile i (done: the
+      // P^T / dS^T of tile i exist) and the second GEMM pair of tile i, which this warp issued before -- tcgen05.mma
+      // executes in issue order, so no barrier is needed.
       auto issue_scores = [&](int i) {      // S^T = K Q_i^T, dP^T = V dO_i^T into score buffer i % 3
-        const int sb = i % NSB, ub = i / NSB, st = i % BWD_STAGES;
+        const int sb = i % NSBK, st = i % BWD_STAGES;
         mbar_wait(q_full + st, (i / BWD_STAGES) & 1);
-        if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tSC + sb * 2 * HALF, desc_kmajor(aK, k), desc_kmajor(aQ + st * T8K, k), idesc_s, k > 0);
+            umma_bf16_ts(tSC + sb * 2 * HALF, tKop + k * 8, desc_kmajor(aQ + st * T8K, k), idesc_s, k > 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tSC + sb * 2 * HALF + HALF, desc_kmajor(aV, k), desc_kmajor(aDO + st * T8K, k), idesc_s, k > 0);
+            umma_bf16_ts(tSC + sb * 2 * HALF + HALF, tVop + k * 8, desc_kmajor(aDO + st * T8K, k), idesc_s, k > 0);
           umma_commit(s_full + sb);
         }
         __syncwarp();
       };
-      for (int i = 0; i < NSB && i < nq; ++i) issue_scores(i);
+      for (int i = 0; i < NSBK && i < nq; ++i) issue_scores(i);
       for (int i = 0; i < nq; ++i) {
         const int w = i & 1, u = i >> 1, st = i % BWD_STAGES;
-        mbar_wait(p_full + w, u & 1);         // P^T and dS^T of tile i are in smem
+        mbar_wait(p_full + w, u & 1);         // P^T and dS^T of tile i are in TMEM
         tc_fence_after();
+        ATTN_TRACE(0, i);
         if (elect_one()) {
+          // A operand from TMEM: 16 queries (one k-step) = 8 columns; queries [0,32) sit at columns [0,16) of the
+          // buffer half, queries [32,64) at columns [32,48) (each thread wrote over the columns it had read)
+          const uint32_t aP = tSC + (i % NSBK) * 2 * HALF, aDS = aP + HALF;
 #pragma unroll
           for (int k = 0; k < 4; ++k)         // dV += P^T dO      (K = 64 queries)
-            umma_bf16(tDV, desc_kmajor(aPT + w * T16K, k), desc_mnmajor(aDO + st * T8K, k), idesc_g, (i > 0 || k > 0));
+            umma_bf16_ts(tDV, aP + (k >> 1) * 32 + (k & 1) * 8, desc_mnmajor(aDO + st * T8K, k), idesc_g, (i > 0 || k > 0));
 #pragma unroll
           for (int k = 0; k < 4; ++k)         // dK += dS^T Q
-            umma_bf16(tDK, desc_kmajor(aDST + w * T16K, k), desc_mnmajor(aQ + st * T8K, k), idesc_g, (i > 0 || k > 0));
+            umma_bf16_ts(tDK, aDS + (k >> 1) * 32 + (k & 1) * 8, desc_mnmajor(aQ + st * T8K, k), idesc_g, (i > 0 || k > 0));
           umma_commit(q_empty + st);          // the Q/dO/lse/D stage may be refilled
-          umma_commit(pbuf_free + w);         // warpgroup w may overwrite its P^T / dS^T buffers
           if (i == nq - 1) umma_commit(acc_full);
         }
         __syncwarp();
-        if (i + NSB < nq) issue_scores(i + NSB);
+        ATTN_TRACE(1, i);
+        if (i + NSBK < nq) issue_scores(i + NSBK);
+        ATTN_TRACE(2, i);
       }
     }
   } else {
@@ -936,14 +973,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;     // key row inside the tile
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    uint8_t *myPT = sPT + w * T16K, *myDST = sDST + w * T16K;
-    int u = 0;
-    for (int i = w; i < nq; i += 2, ++u) {
-      const int sb = i % NSB, st = i % BWD_STAGES;
+    // once per CTA: the 256 softmax threads copy the K tile (column half 0) and the V tile (column half 1), one row each
+    mbar_wait(kv_full, 0);
+    row_to_tmem(c == 0 ? sK : sV, row, (c == 0 ? tKop : tVop) + lane_addr);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(op_full);
+    for (int i = w; i < nq; i += 2) {
+      const int sb = i % NSBK, st = i % BWD_STAGES;
+      if (quarter == 0 && c == 0) ATTN_TRACE(4, i);
       mbar_wait(q_full + st, (i / BWD_STAGES) & 1);   // lse / D tile of this stage (bulk copies) has landed
-      mbar_wait(s_full + sb, (i / NSB) & 1);
+      mbar_wait(s_full + sb, (i / NSBK) & 1);
       tc_fence_after();
-      if (u > 0) mbar_wait(pbuf_free + w, (u - 1) & 1);
+      if (quarter == 0 && c == 0) ATTN_TRACE(5, i);
       const float *myLse = sLse + st * HALF, *myD = sD + st * HALF;
       // No masking is needed here: query columns >= T have zero Q / dO rows (TMA zero fill) and
       // lse = D = 0, so their P^T multiplies zero dO rows and their dS^T is exactly 0; key rows >= T
@@ -953,6 +996,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
         tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + c * 32, st_);
         tmem_ld32_issue(tSC + lane_addr + sb * 2 * HALF + HALF + c * 32, dp);
         tmem_ld_wait();
+        if (quarter == 0 && c == 0) ATTN_TRACE(6, i);
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const float4 L = reinterpret_cast<const float4 *>(myLse)[c * 8 + q4];
@@ -966,16 +1010,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV, const __grid_cons
             dp[q] = pr * (dp[q] - ds[k]);
           }
         }
-        store_row32(myPT, TILE, row, c * 32, st_);
-        store_row32(myDST, TILE, row, c * 32, dp);
+        uint32_t pk[16];
+        pack32_bf16(st_, pk);
+        tmem_st16u(tSC + lane_addr + sb * 2 * HALF + c * 32, pk);             // P^T over the S^T columns just read
+        pack32_bf16(dp, pk);
+        tmem_st16u(tSC + lane_addr + sb * 2 * HALF + HALF + c * 32, pk);      // dS^T over the dP^T columns just read
       }
+      if (quarter == 0 && c == 0) ATTN_TRACE(9, i);
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty + sb);
-        mbar_arrive(p_full + w);
-      }
+      if (lane == 0) mbar_arrive(p_full + w);
+      if (quarter == 0 && c == 0) ATTN_TRACE(10, i);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -1006,11 +1052,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint8_t *sDO = sQ + T16K;
   uint8_t *sK = sDO + T16K;                // BWD_STAGES x 8 KB
   uint8_t *sV = sK + BWD_STAGES * T8K;     // BWD_STAGES x 8 KB
-  uint8_t *sDS = sV + BWD_STAGES * T8K;    // dS [128 queries x 64 keys], one per warpgroup
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sDS + 4 * T16K + BWD_STAGES * 2 * HALF * 4);
+  // dS (bf16) is written back over the dP columns in TMEM and consumed from there (see the dK/dV kernel)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sV + BWD_STAGES * T8K);
   uint64_t *q_full = bars, *kv_full = bars + 1, *kv_empty = kv_full + BWD_STAGES, *s_full = kv_empty + BWD_STAGES,
-           *s_empty = s_full + NSB, *p_full = s_empty + NSB, *pbuf_free = p_full + 2, *acc_full = pbuf_free + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+           *p_full = s_full + NSB, *acc_full = p_full + 2, *op_full = acc_full + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(op_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * TILE, h = blockIdx.y, b = blockIdx.z;
@@ -1027,15 +1073,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_init(kv_full + i, 1);
       mbar_init(kv_empty + i, 1);
     }
-    for (int i = 0; i < NSB; ++i) {
-      mbar_init(s_full + i, 1);
-      mbar_init(s_empty + i, 8);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(p_full + i, 8);
-      mbar_init(pbuf_free + i, 1);
-    }
+    for (int i = 0; i < NSB; ++i) mbar_init(s_full + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(p_full + i, 8);
     mbar_init(acc_full, 1);
+    mbar_init(op_full, 16);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -1043,7 +1084,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tSC = tmem, tDQ = tmem + NSB * 2 * HALF;   // S at sb*128, dP at sb*128 + 64; dQ at 384
+  // S at sb*128, dP at sb*128 + 64 (3 buffers); dQ at 384; the CTA's own Q and dO tiles as TMEM-resident A operands at
+  // 448 / 480 (see the dK/dV kernel: every MMA then reads only its 2 KB B operand from shared memory)
+  const uint32_t tSC = tmem, tDQ = tmem + NSB * 2 * HALF, tQop = tDQ + HD, tDOop = tQop + HD / 2;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -1066,20 +1109,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     {
       constexpr uint32_t idesc_s = make_idesc(TILE, HALF, 0, 0);
       constexpr uint32_t idesc_g = make_idesc(TILE, HD, 0, 1);
-      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO), aK = smem_u32(sK), aV = smem_u32(sV), aDS = smem_u32(sDS);
-      mbar_wait(q_full, 0);
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      mbar_wait(op_full, 0);                // Q and dO are in tensor memory
+      tc_fence_after();
       auto issue_scores = [&](int j) {      // S = Q K_j^T, dP = dO V_j^T into score buffer j % 3
-        const int sb = j % NSB, ub = j / NSB, st = j % BWD_STAGES;
+        const int sb = j % NSB, st = j % BWD_STAGES;    // (buffer reuse is ordered by the issue order of this warp's MMAs)
         mbar_wait(kv_full + st, (j / BWD_STAGES) & 1);
-        if (ub > 0) mbar_wait(s_empty + sb, (ub - 1) & 1);
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tSC + sb * 2 * HALF, desc_kmajor(aQ, k), desc_kmajor(aK + st * T8K, k), idesc_s, k > 0);
+            umma_bf16_ts(tSC + sb * 2 * HALF, tQop + k * 8, desc_kmajor(aK + st * T8K, k), idesc_s, k > 0);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tSC + sb * 2 * HALF + HALF, desc_kmajor(aDO, k), desc_kmajor(aV + st * T8K, k), idesc_s, k > 0);
+            umma_bf16_ts(tSC + sb * 2 * HALF + HALF, tDOop + k * 8, desc_kmajor(aV + st * T8K, k), idesc_s, k > 0);
           umma_commit(s_full + sb);
         }
         __syncwarp();
@@ -1090,11 +1133,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(p_full + w, u & 1);
         tc_fence_after();
         if (elect_one()) {
+          const uint32_t aDS = tSC + (j % NSB) * 2 * HALF + HALF;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)         // dQ += dS K      (K = 64 keys)
-            umma_bf16(tDQ, desc_kmajor(aDS + w * T16K, k), desc_mnmajor(aK + st * T8K, k), idesc_g, (j > 0 || k > 0));
+          for (int k = 0; k < 4; ++k)         // dQ += dS K      (K = 64 keys), dS from TMEM
+            umma_bf16_ts(tDQ, aDS + (k >> 1) * 32 + (k & 1) * 8, desc_mnmajor(aK + st * T8K, k), idesc_g, (j > 0 || k > 0));
           umma_commit(kv_empty + st);
-          umma_commit(pbuf_free + w);
           if (j == nkv - 1) umma_commit(acc_full);
         }
         __syncwarp();
@@ -1111,13 +1154,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const bool row_ok = t < p.T;
     const float lse2 = t < Tp ? p.lse2[((size_t)b * p.H + h) * Tp + t] : 0.f;
     const float dsum = t < Tp ? p.dvec[((size_t)b * p.H + h) * Tp + t] : 0.f;
-    uint8_t *myDS = sDS + w * T16K;
-    int u = 0;
-    for (int j = w; j < nkv; j += 2, ++u) {
+    // once per CTA: Q rows by column half 0, dO rows by column half 1
+    mbar_wait(q_full, 0);
+    row_to_tmem(c == 0 ? sQ : sDO, row, (c == 0 ? tQop : tDOop) + lane_addr);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(op_full);
+    for (int j = w; j < nkv; j += 2) {
       const int sb = j % NSB;
       mbar_wait(s_full + sb, (j / NSB) & 1);
       tc_fence_after();
-      if (u > 0) mbar_wait(pbuf_free + w, (u - 1) & 1);
       // No masking: key columns >= T multiply zero K rows in dQ += dS K; query rows >= T only
       // pollute their own (never stored) dQ rows.
       {
@@ -1127,15 +1174,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 32; ++q) dp[q] = fast_exp2(fmaf(sv[q], p.scale_log2, -lse2)) * (dp[q] - dsum);
-        store_row32(myDS, TILE, row, c * 32, dp);
+        uint32_t pk[16];
+        pack32_bf16(dp, pk);
+        tmem_st16u(tSC + lane_addr + sb * 2 * HALF + HALF + c * 32, pk);      // dS over the dP columns just read
       }
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty + sb);
-        mbar_arrive(p_full + w);
-      }
+      if (lane == 0) mbar_arrive(p_full + w);
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
