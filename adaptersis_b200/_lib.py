@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("ASIS_LIB") or os.path.join(_HERE, "libasis_b200.so") 
 
 F32, BF16 = 0, 1
 MAJOR_K, MAJOR_MN = 0, 1
-EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL, EPI_DGELU, EPI_ACCUMULATE = 0, 1, 2, 3, 4
+EPI_NONE, EPI_GELU, EPI_SCALE_RESIDUAL, EPI_DGELU, EPI_ACCUMULATE, EPI_GELU_GRAD, EPI_MUL_AUX = 0, 1, 2, 3, 4, 5, 6
 
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 

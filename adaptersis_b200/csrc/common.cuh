@@ -123,6 +123,13 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float h = gelu_half_erfc(x, e);
   return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
+// activation and derivative from ONE erfc / exp evaluation (GELU_GRAD epilogue)
+__device__ __forceinline__ float gelu_and_grad_fast(float x, float &grad) {
+  float e;
+  const float h = gelu_half_erfc(x, e);
+  grad = fmaf(x * e, 0.3989422804014327f, 0.5f + copysignf(0.5f - h, x));
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float dgelu_fast(float x) {
   float e;
   const float h = gelu_half_erfc(x, e);

@@ -51,6 +51,14 @@ __device__ __forceinline__ void epi_scalar(const EpiArgs &e, int m, int n, float
     case ASIS_EPI_ACCUMULATE:
       out = reinterpret_cast<float *>(e.C)[ci] + acc;
       break;
+    case ASIS_EPI_GELU_GRAD: {
+      const float h = acc + b;
+      st_any(e.aux, e.aux_dtype, (size_t)m * e.ldaux + n, dgelu_erf(h));
+      out = gelu_erf(h);
+    } break;
+    case ASIS_EPI_MUL_AUX:
+      out = acc * ld_any(e.aux, e.aux_dtype, (size_t)m * e.ldaux + n);
+      break;
     default:
       out = acc + b;
   }
@@ -59,9 +67,10 @@ __device__ __forceinline__ void epi_scalar(const EpiArgs &e, int m, int n, float
 
 static inline int check_epilogue(int epilogue, const float *gamma, const float *residual, void *aux, int aux_dtype,
                                  int c_dtype) {
-  ASIS_REQUIRE(epilogue >= ASIS_EPI_NONE && epilogue <= ASIS_EPI_ACCUMULATE, "gemm: unknown epilogue %d", epilogue);
+  ASIS_REQUIRE(epilogue >= ASIS_EPI_NONE && epilogue <= ASIS_EPI_MUL_AUX, "gemm: unknown epilogue %d", epilogue);
   if (epilogue == ASIS_EPI_SCALE_RESIDUAL) ASIS_REQUIRE(gamma && residual, "gemm: SCALE_RESIDUAL needs gamma and residual");
   if (epilogue == ASIS_EPI_DGELU) ASIS_REQUIRE(aux, "gemm: DGELU needs aux (the saved pre-activation)");
+  if (epilogue == ASIS_EPI_GELU_GRAD || epilogue == ASIS_EPI_MUL_AUX) ASIS_REQUIRE(aux, "gemm: GELU_GRAD / MUL_AUX need aux (the GELU derivative)");
   if (epilogue == ASIS_EPI_ACCUMULATE) ASIS_REQUIRE(c_dtype == ASIS_F32, "gemm: ACCUMULATE needs an f32 C");
   if (aux) ASIS_REQUIRE(dtype_ok(aux_dtype), "gemm: bad aux dtype");
   return ASIS_OK;

@@ -88,7 +88,7 @@ __device__ __forceinline__ void decode4(const uint4 &r, int dtype, float (&v)[4]
 }
 
 // which epilogues read a second [M, N] operand (the residual, the saved pre-activation, or C itself)
-template <int KIND> struct EpiReads { static constexpr bool value = KIND == ASIS_EPI_SCALE_RESIDUAL || KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_ACCUMULATE; };
+template <int KIND> struct EpiReads { static constexpr bool value = KIND == ASIS_EPI_SCALE_RESIDUAL || KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_ACCUMULATE || KIND == ASIS_EPI_MUL_AUX; };
 
 // the 4-column group of one row in the coalesced layout, vector path (col + 4 <= N, 16-byte aligned
 // pitches, no split-K); KIND is a compile-time constant; `pre` is the prefetched second operand
@@ -97,11 +97,21 @@ __device__ __forceinline__ void epi_group4(const EpiArgs &e, int row, int col, f
                                            const float (&g4)[4], const uint4 &pre) {
   const size_t ci = (size_t)row * e.ldc + col;
   const size_t ai = (size_t)row * e.ldaux + col;
-  if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE) {
+  if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE && KIND != ASIS_EPI_MUL_AUX) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] += b4[i];
   }
-  if (KIND == ASIS_EPI_GELU) {
+  if (KIND == ASIS_EPI_GELU_GRAD) {
+    float d[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = gelu_and_grad_fast(v[i], d[i]);
+    store4_any(e.aux, e.aux_dtype, ai, d);
+  } else if (KIND == ASIS_EPI_MUL_AUX) {
+    float h[4];
+    decode4(pre, e.aux_dtype, h);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] *= h[i];
+  } else if (KIND == ASIS_EPI_GELU) {
     if (e.aux) store4_any(e.aux, e.aux_dtype, ai, v);
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = gelu_fast(v[i]);
@@ -158,7 +168,7 @@ __device__ __forceinline__ void epi_prefetch(const GemmTcParams &p, int row0, in
     const int row = row0 + it * 4 + r;
     if (row < p.M) {
       if (KIND == ASIS_EPI_SCALE_RESIDUAL) pre[it] = ldraw4(e.residual, ASIS_F32, (size_t)row * e.ldc + col);
-      else if (KIND == ASIS_EPI_DGELU) pre[it] = ldraw4(e.aux, e.aux_dtype, (size_t)row * e.ldaux + col);
+      else if (KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_MUL_AUX) pre[it] = ldraw4(e.aux, e.aux_dtype, (size_t)row * e.ldaux + col);
       else pre[it] = ldraw4(e.C, ASIS_F32, (size_t)row * e.ldc + col);
     }
   }
@@ -206,7 +216,7 @@ __device__ __forceinline__ void epi_slab(const GemmTcParams &p, uint32_t taddr, 
     if (c + 1 < 4) epi_prefetch<KIND>(p, row0, col + 32, r, vec_ok, pre);
     if (col < p.N) {
       float b4[4] = {0.f, 0.f, 0.f, 0.f}, g4[4] = {0.f, 0.f, 0.f, 0.f};
-      if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE && e.bias) {
+      if (KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE && KIND != ASIS_EPI_MUL_AUX && e.bias) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) b4[i] = (col + i < p.N) ? __ldg(e.bias + col + i) : 0.f;
       }
@@ -264,7 +274,7 @@ __device__ __forceinline__ uint2 pack_bf16x4(const float (&v)[4]) {
   return make_uint2(*reinterpret_cast<uint32_t *>(&a), *reinterpret_cast<uint32_t *>(&b));
 }
 
-template <int KIND> struct EpiHasBias { static constexpr bool value = KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE; };
+template <int KIND> struct EpiHasBias { static constexpr bool value = KIND != ASIS_EPI_DGELU && KIND != ASIS_EPI_ACCUMULATE && KIND != ASIS_EPI_MUL_AUX; };
 
 // state of one lane for one slab: byte pointers at (its first row, its 4 columns of the current chunk)
 struct EpiLane {
@@ -282,7 +292,7 @@ __device__ __forceinline__ void epi3_prefetch(const EpiLane &L, uint4 (&pre)[8])
   for (int it = 0; it < 8; ++it) {
     if (it < L.nit) {
       const char *q = L.in2 + (size_t)((uint32_t)it * L.istep);
-      if (KIND == ASIS_EPI_DGELU) {
+      if (KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_MUL_AUX) {
         const uint2 t = *reinterpret_cast<const uint2 *>(q);
         pre[it] = make_uint4(t.x, t.y, 0u, 0u);
       } else {
@@ -316,6 +326,15 @@ __device__ __forceinline__ void epi3_chunk(const EpiLane &L, uint32_t rd0, uint3
       if (KIND == ASIS_EPI_GELU) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] = gelu_fast(w[i]);
+      } else if (KIND == ASIS_EPI_GELU_GRAD) {
+        float d[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = gelu_and_grad_fast(w[i], d[i]);
+        *reinterpret_cast<uint2 *>(L.aux + (size_t)((uint32_t)it * L.astep)) = pack_bf16x4(d);
+      } else if (KIND == ASIS_EPI_MUL_AUX) {
+        const __nv_bfloat162 ha = *reinterpret_cast<const __nv_bfloat162 *>(&cur[it].x);
+        const __nv_bfloat162 hb = *reinterpret_cast<const __nv_bfloat162 *>(&cur[it].y);
+        w[0] *= __low2float(ha); w[1] *= __high2float(ha); w[2] *= __low2float(hb); w[3] *= __high2float(hb);
       } else if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
         w[0] = fmaf(g4.x, w[0], __uint_as_float(cur[it].x)); w[1] = fmaf(g4.y, w[1], __uint_as_float(cur[it].y));
         w[2] = fmaf(g4.z, w[2], __uint_as_float(cur[it].z)); w[3] = fmaf(g4.w, w[3], __uint_as_float(cur[it].w));
@@ -335,7 +354,7 @@ __device__ __forceinline__ void epi3_chunk(const EpiLane &L, uint32_t rd0, uint3
   }
 }
 
-// the epilogue of one 32-row x 128-column slab (entirely inside N) owned by one warp; `stage_u32`: two 4 KB buffers
+// the epilogue of one 32-row x 128-column slab (entirely inside N) owned by one warp; `stage_u32`: its 4 KB buffer
 template <int KIND, bool CBF16>
 __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr, uint32_t stage_u32, int row0, int col_base,
                                           int lane, uint64_t *tfull, uint32_t tfull_phase, int tr_idx) {
@@ -355,7 +374,7 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
     L.astep = (uint32_t)(4 * e.ldaux) * 2u;
     L.in2 = nullptr;
     L.istep = 0;
-    if ((KIND == ASIS_EPI_GELU || KIND == ASIS_EPI_SCALE_RESIDUAL) && e.aux)
+    if ((KIND == ASIS_EPI_GELU || KIND == ASIS_EPI_SCALE_RESIDUAL || KIND == ASIS_EPI_GELU_GRAD) && e.aux)
       L.aux = reinterpret_cast<char *>(e.aux) + ((size_t)(row0 + r) * e.ldaux + col) * 2;
     if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
       L.in2 = reinterpret_cast<const char *>(e.residual) + eoff * 4;
@@ -363,14 +382,14 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
     } else if (KIND == ASIS_EPI_ACCUMULATE) {
       L.in2 = reinterpret_cast<const char *>(e.C) + eoff * 4;
       L.istep = (uint32_t)(4 * e.ldc) * 4u;
-    } else if (KIND == ASIS_EPI_DGELU) {
+    } else if (KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_MUL_AUX) {
       L.in2 = reinterpret_cast<const char *>(e.aux) + ((size_t)(row0 + r) * e.ldaux + col) * 2;
       L.istep = L.astep;
     }
   }
-  constexpr uint32_t I2E = KIND == ASIS_EPI_DGELU ? 2 : 4;       // element size of the second operand
+  constexpr uint32_t I2E = (KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_MUL_AUX) ? 2 : 4;       // element size of the second operand
   // transposition buffers: write side (thread = row `lane`), read side (row it*4 + r, 16-byte group cg)
-  const uint32_t wrA = stage_u32 + lane * 128 + ((lane & 7) << 4), wrB = wrA + 4096;
+  const uint32_t wrA = stage_u32 + lane * 128 + ((lane & 7) << 4);
   const uint32_t rdA0 = stage_u32 + r * 128 + ((cg ^ r) << 4), rdA1 = stage_u32 + r * 128 + ((cg ^ (r + 4)) << 4);
   uint4 pre[8];
 #pragma unroll
@@ -387,18 +406,17 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
 #pragma unroll 1
   for (int c2 = 0; c2 < 2; ++c2) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {           // h = 0: registers va, buffer A;  h = 1: registers vb, buffer B
+    for (int h = 0; h < 2; ++h) {           // h = 0: registers va;  h = 1: registers vb
       const bool last = (c2 == 1 && h == 1);
       tmem_ld_wait();
       if (!last) {
         if (h == 0) tmem_ld32_issue(taddr + (2 * c2 + 1) * 32, vb);
         else tmem_ld32_issue(taddr + 2 * 32, va);
       }
-      const uint32_t wr = h == 0 ? wrA : wrB;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
         const float *v = h == 0 ? va : vb;
-        sts128(wr ^ (g << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+        sts128(wrA ^ (g << 4), v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
       }
       __syncwarp();
       const float4 b4 = b4n, g4 = g4n;
@@ -410,13 +428,13 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
         L.in2 += EpiReads<KIND>::value ? 32 * I2E : 0;
         epi3_prefetch<KIND>(L, pre);
       }
-      epi3_chunk<KIND, CBF16>(L, (h == 0 ? rdA0 : rdA0 + 4096), (h == 0 ? rdA1 : rdA1 + 4096), b4, g4, cur);
+      epi3_chunk<KIND, CBF16>(L, rdA0, rdA1, b4, g4, cur);
+      __syncwarp();                         // the buffer is rewritten by the next chunk
       L.c += 32 * CE;
       if (L.aux) L.aux += 32 * 2;
       col += 32;
     }
   }
-  __syncwarp();     // the buffers are rewritten by the next tile's first chunks
 }
 
 template <int A_MN, int B_MN, int CL>
@@ -583,6 +601,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
         case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
         case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
+        case ASIS_EPI_GELU_GRAD: epi_slab<ASIS_EPI_GELU_GRAD>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
+        case ASIS_EPI_MUL_AUX: epi_slab<ASIS_EPI_MUL_AUX>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
         default: epi_slab<ASIS_EPI_NONE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase); break;
       }
       tc_fence_before();
@@ -611,15 +631,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // shared memory.  Per CTA and k-block that is 32 KB filled + 32 KB read instead of 48 + 48 (with the multicast
 // version every CTA still holds -- and its tensor core still reads -- the whole B tile): the 128 B/clk
 // shared-memory port is what this relieves (TMA fill 96 B/clk + operand reads 96 B/clk at full MMA rate in the
-// 1-CTA kernel).  Ring: 5 x 32 KB.
+// 1-CTA kernel).  Ring: 6 x 32 KB (the timeline showed the producer only ~2 k clk ahead of the MMAs with 5 stages,
+// about one L2 round trip: the first k-block of a tile arrived late).
 // Protocol (as in DeepGEMM's sm_100 kernels): both producers report their TMA bytes to the LEADER's full barrier
 // (cp.async.bulk.tensor.cta_group::2 with a shared::cluster barrier address; arrival count 2 = leader's
 // arrive.expect_tx + the peer's plain arrive); tcgen05.commit.cta_group::2 multicasts "stage free" / "accumulator
 // complete" to both CTAs; the epilogue warps of both CTAs release the accumulator on the leader's barrier.
-constexpr int STAGES2 = 5;
+constexpr int STAGES2 = 6;
 constexpr int B2_BYTES = (BN / 2) * BK * 2;           // 16 KB: this CTA's half of the B tile
 constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;      // 32 KB
-constexpr int EPI2_STAGE_BYTES = 2 * EPI_STAGE_BYTES; // two transposition buffers per epilogue warp (epi_slab2)
+constexpr int EPI2_STAGE_BYTES = EPI_STAGE_BYTES;     // one 4 KB transposition buffer per epilogue warp
 constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + EPI2_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(GEMM2_SMEM <= 227 * 1024, "pair kernel: shared memory over the 227 KB limit");
 
@@ -763,7 +784,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     const bool vec_ok = (p.epi.ldc % 4 == 0) && (!p.epi.aux || p.epi.ldaux % 4 == 0);
-    float *stage = epi_stage + ew * 2 * EPI_STAGE_FLOATS;
+    float *stage = epi_stage + ew * EPI_STAGE_FLOATS;
     const uint32_t ltempty0 = mapa_u32(tempty_bar, 0);     // the leader's accumulator-free barriers
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int n_blk = tile % p.n_tiles;
@@ -787,6 +808,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           case ASIS_EPI_SCALE_RESIDUAL: epi_slab3<ASIS_EPI_SCALE_RESIDUAL, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr); break;
           case ASIS_EPI_DGELU: ASIS_EPI3(ASIS_EPI_DGELU); break;
           case ASIS_EPI_ACCUMULATE: epi_slab3<ASIS_EPI_ACCUMULATE, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_GELU_GRAD: ASIS_EPI3(ASIS_EPI_GELU_GRAD); break;
+          case ASIS_EPI_MUL_AUX: ASIS_EPI3(ASIS_EPI_MUL_AUX); break;
           default: ASIS_EPI3(ASIS_EPI_NONE); break;
         }
 #undef ASIS_EPI3
@@ -796,6 +819,8 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
           case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
           case ASIS_EPI_ACCUMULATE: epi_slab<ASIS_EPI_ACCUMULATE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_GELU_GRAD: epi_slab<ASIS_EPI_GELU_GRAD>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_MUL_AUX: epi_slab<ASIS_EPI_MUL_AUX>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
           default: epi_slab<ASIS_EPI_NONE>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
         }
       }

@@ -15,7 +15,8 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import kernels as K
-from ._lib import (BF16, EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_SCALE_RESIDUAL, F32, MAJOR_K, MAJOR_MN)
+from ._lib import (BF16, EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_GELU_GRAD, EPI_MUL_AUX, EPI_NONE, EPI_SCALE_RESIDUAL, F32,
+                   MAJOR_K, MAJOR_MN)
 
 _MODE = [os.environ.get("ASIS_PRECISION", "fp32")]
 
@@ -182,13 +183,15 @@ def layer_norm(x, weight, bias, eps=1e-6, out_dtype=None):
 # ------------------------------------------------------------------------------------------------
 def _linear_backward(comp, cdt, dy2, x2, weight, need_dx, need_dw, need_db, dx_dtype=None, dgelu_aux=None):
     """dy2 [R, N] compute dtype; x2 [R, K] compute dtype; weight [N, K].
-    returns dx [R, K] (dx_dtype), dW [N, K] f32, db [N] f32."""
+    returns dx [R, K] (dx_dtype), dW [N, K] f32, db [N] f32.
+    ``dgelu_aux``: the GELU derivative saved by the forward's GELU_GRAD epilogue -- the input gradient is multiplied
+    by it in the epilogue of the dgrad GEMM."""
     R, N = dy2.shape
     Kd = x2.shape[1] if x2 is not None else weight.shape[1]
     dx = dw = db = None
     if need_dx:
         w = _operand(weight, cdt)
-        epi = EPI_DGELU if dgelu_aux is not None else EPI_NONE
+        epi = EPI_MUL_AUX if dgelu_aux is not None else EPI_NONE
         dx, _ = K.gemm(comp, dy2, MAJOR_K, w, MAJOR_MN, R, Kd, N, dx_dtype or cdt, epilogue=epi, aux=dgelu_aux)
     if need_dw:
         dw, _ = K.gemm(comp, dy2, MAJOR_MN, x2, MAJOR_MN, N, Kd, R, torch.float32)
@@ -298,8 +301,8 @@ class MlpFunction(Function):
         x2 = K.cast(x.reshape(-1, shp[-1]), cdt) if x.dtype != cdt else x.reshape(-1, shp[-1])
         R, Cin = x2.shape
         Hd, Co = w1.shape[0], w2.shape[0]
-        g, h = K.gemm(comp, x2, MAJOR_K, _operand(w1, cdt), MAJOR_K, R, Hd, Cin, cdt, epilogue=EPI_GELU,
-                      bias=_f32(b1), want_aux_dtype=cdt)
+        g, h = K.gemm(comp, x2, MAJOR_K, _operand(w1, cdt), MAJOR_K, R, Hd, Cin, cdt, epilogue=EPI_GELU_GRAD,
+                      bias=_f32(b1), want_aux_dtype=cdt)        # h = GELU'(pre-activation), for the backward
         y, _ = K.gemm(comp, g, MAJOR_K, _operand(w2, cdt), MAJOR_K, R, Co, Hd, cdt, bias=_f32(b2))
         ctx.save_for_backward(x2, w1, w2, h, g)
         ctx.meta = (shp, mode, b1 is not None, b2 is not None)
@@ -360,8 +363,10 @@ class BlockFunction(Function):
                         want_aux_dtype=cdt if save_u[0] else None)
         y2, mean2, rstd2 = K.layernorm_forward(x1, _f32(n2w), _f32(n2b), eps, cdt)
         Hd = fc1_w.shape[0]
-        g, h = K.gemm(comp, y2, MAJOR_K, _operand(fc1_w, cdt), MAJOR_K, R, Hd, C, cdt, epilogue=EPI_GELU,
-                      bias=_f32(fc1_b), want_aux_dtype=cdt if track else None)
+        # with a backward to come the epilogue also saves GELU'(pre-activation) (`h`): it shares the erfc / exp
+        # evaluation with the activation, and fc2's input-gradient GEMM then only multiplies by it
+        g, h = K.gemm(comp, y2, MAJOR_K, _operand(fc1_w, cdt), MAJOR_K, R, Hd, C, cdt,
+                      epilogue=EPI_GELU_GRAD if track else EPI_GELU, bias=_f32(fc1_b), want_aux_dtype=cdt if track else None)
         out, u2 = K.gemm(comp, g, MAJOR_K, _operand(fc2_w, cdt), MAJOR_K, R, C, Hd, torch.float32,
                          epilogue=EPI_SCALE_RESIDUAL, bias=_f32(fc2_b), gamma=gam2, residual=x1,
                          want_aux_dtype=cdt if save_u[1] else None)

@@ -6,8 +6,8 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (BF16, EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_NONE, EPI_SCALE_RESIDUAL, F32, MAJOR_K,
-                   MAJOR_MN, check, dt, need_cuda, ptr, stream, workspace)
+from ._lib import (BF16, EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_GELU_GRAD, EPI_MUL_AUX, EPI_NONE, EPI_SCALE_RESIDUAL,
+                   F32, MAJOR_K, MAJOR_MN, check, dt, need_cuda, ptr, stream, workspace)
 
 TORCH_DT = {F32: torch.float32, BF16: torch.bfloat16}
 
@@ -166,7 +166,7 @@ def gemm(compute, A, a_major, B, b_major, M, N, K, out_dtype, epilogue=EPI_NONE,
     dev = A.device
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=dev)
-    if epilogue in (EPI_GELU, EPI_SCALE_RESIDUAL) and aux is None and want_aux_dtype is not None:
+    if epilogue in (EPI_GELU, EPI_SCALE_RESIDUAL, EPI_GELU_GRAD) and aux is None and want_aux_dtype is not None:
         aux = torch.empty(M, N, dtype=want_aux_dtype, device=dev)
     if residual is not None:
         residual = _c(residual)

@@ -90,6 +90,10 @@ class TrainStep(nn.Module):
         from . import _lib
         if self._graph is not None:
             raise RuntimeError("TrainStep.capture: already captured")
+        try:        # warm-up runs on a side stream while the AccumulateGrad nodes were created on the default one: expected here
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         side = torch.cuda.Stream(self.device)
         side.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(side):               # warm-up on a side stream, as torch.cuda.graph asks

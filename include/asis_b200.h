@@ -50,7 +50,11 @@ enum {
   ASIS_EPI_GELU = 1,          /* aux = acc + bias (pre-activation, optional); C = gelu_erf(aux) */
   ASIS_EPI_SCALE_RESIDUAL = 2,/* aux = acc + bias (optional); C = residual + gamma[n] * aux     */
   ASIS_EPI_DGELU = 3,         /* C = acc * gelu_erf'(aux_in)      (aux is an INPUT here)        */
-  ASIS_EPI_ACCUMULATE = 4     /* C += acc   (fp32 C only; weight-gradient accumulation)       */
+  ASIS_EPI_ACCUMULATE = 4,    /* C += acc   (fp32 C only; weight-gradient accumulation)       */
+  ASIS_EPI_GELU_GRAD = 5,     /* h = acc + bias; C = gelu_erf(h); aux = gelu_erf'(h)  (aux required): the forward
+                                 saves the derivative -- it shares the erfc / exp evaluation with the activation --
+                                 so that the backward epilogue below is a multiply                               */
+  ASIS_EPI_MUL_AUX = 6        /* C = acc * aux_in   (aux is an INPUT: the derivative saved by GELU_GRAD)          */
 };
 
 int asis_abi_version(void);

@@ -8,7 +8,8 @@ from conftest import grad_err, mask_check, relerr
 from synth import encoder_data
 import adaptersis_b200 as asis
 from adaptersis_b200 import kernels as K
-from adaptersis_b200._lib import (BF16, EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_SCALE_RESIDUAL, MAJOR_K, MAJOR_MN)
+from adaptersis_b200._lib import (BF16, EPI_ACCUMULATE, EPI_DGELU, EPI_GELU, EPI_GELU_GRAD, EPI_MUL_AUX, EPI_SCALE_RESIDUAL,
+                                  MAJOR_K, MAJOR_MN)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -77,6 +78,21 @@ def test_gemm_tc_epilogues():
     (dg,) = torch.autograd.grad(torch.nn.functional.gelu(hh), hh, torch.ones_like(hh))
     c, _ = K.gemm(BF16, A, MAJOR_K, B, MAJOR_K, M, N, K_, torch.float32, epilogue=EPI_DGELU, aux=h)
     assert relerr(c, ref * dg) < GEMM_TOL
+    # GELU with the derivative saved for the backward, and the backward epilogue that multiplies by it
+    pre = (ref + bias).requires_grad_(True)
+    (dpre,) = torch.autograd.grad(torch.nn.functional.gelu(pre), pre, torch.ones_like(pre))
+    c, aux = K.gemm(BF16, A, MAJOR_K, B, MAJOR_K, M, N, K_, torch.bfloat16, epilogue=EPI_GELU_GRAD, bias=bias,
+                    want_aux_dtype=torch.bfloat16)
+    assert relerr(c.float(), torch.nn.functional.gelu(ref + bias)) < TOL and relerr(aux.float(), dpre) < TOL
+    c, _ = K.gemm(BF16, A, MAJOR_K, B, MAJOR_K, M, N, K_, torch.bfloat16, epilogue=EPI_MUL_AUX, aux=aux)
+    assert relerr(c.float(), ref * aux.float()) < TOL
+    # the same two on a shape with M / N tails (generic epilogue path)
+    Mt, Nt = 333, 200
+    c, aux = K.gemm(BF16, A[:Mt], MAJOR_K, B[:Nt], MAJOR_K, Mt, Nt, K_, torch.bfloat16, epilogue=EPI_GELU_GRAD, bias=bias[:Nt],
+                    want_aux_dtype=torch.bfloat16)
+    assert relerr(c.float(), torch.nn.functional.gelu(ref[:Mt, :Nt] + bias[:Nt])) < TOL and relerr(aux.float(), dpre[:Mt, :Nt]) < TOL
+    c, _ = K.gemm(BF16, A[:Mt], MAJOR_K, B[:Nt], MAJOR_K, Mt, Nt, K_, torch.float32, epilogue=EPI_MUL_AUX, aux=aux)
+    assert relerr(c, ref[:Mt, :Nt] * aux.float()) < GEMM_TOL
 
 
 @pytest.mark.parametrize("B,T,H", [(1, 128, 1), (2, 300, 3), (1, 1765, 16), (3, 1764, 2)])
