@@ -23,7 +23,7 @@ if os.environ.get("ASIS_TRACE"):      # debug build with in-kernel event stamps 
     FLAGS = FLAGS + ["-DASIS_TRACE"]  # a separate library, loaded with ASIS_LIB=<path>; the product library is untouched
     OUT = os.path.join(HERE, "libasis_b200_trace.so")
     BUILD = os.path.join(CSRC, "build_trace")
-SOURCES = ["api.cu", "msda.cu", "norm.cu", "gemm_f32.cu", "attention_f32.cu", "misc.cu", "gemm_tc.cu", "attention_tc.cu"]
+SOURCES = ["api.cu", "msda.cu", "norm.cu", "gemm_f32.cu", "attention_f32.cu", "misc.cu", "conv.cu", "gemm_tc.cu", "attention_tc.cu"]
 
 
 def _deps_mtime():

@@ -1,0 +1,771 @@
+// conv.cu -- the convolutional stages either side of the hot path, channels-last (token-major) throughout:
+//   * spatial prior module  FeatureEncoder  (backbones/encoders.py:4-74):  3x3 convolutions (+ SyncBatchNorm + ReLU),
+//     3x3 / stride-2 max pooling;
+//   * FeatureDecoder (backbones/decoders.py:92-164): 3x3 convolutions + BatchNorm + ReLU, the final 64 -> n_classes
+//     3x3 convolution.
+// A convolution is  im2col (here)  +  asis_gemm  (tcgen05 in bf16 mode):  rows = output pixels, K = (ky, kx, c) with the
+// channel fastest, so a tap of a pixel is one contiguous C-vector and the GEMM consumes the matrix K-major with the
+// weight viewed as [Cout, ky, kx, Cin].  The input gradient is the transposed GEMM followed by a gather over the taps
+// that touch an input pixel (col2im without atomics); the weight gradient is the MN-major GEMM over the same matrix.
+// BatchNorm in training mode is two kernels each way: per-channel shifted sums (fixed-order partials, no atomics) and a
+// fused normalise (+ReLU) / gradient pass.  Everything here is HBM-bound and written as 16-byte vector passes.
+//
+// A map is stored as [B, H + 2*sp, W + 2*sp, C] with the logical H x W image at offset (sp, sp) ("storage padding";
+// sp = 0 is the plain layout).  Writers fill the storage border with zeros.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace asis {
+
+template <typename T> struct CVec;
+template <> struct CVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float *p, float (&v)[4]) { load4(p, v); }
+  static __device__ __forceinline__ void store(float *p, const float (&v)[4]) { store4(p, v); }
+};
+template <> struct CVec<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16 *p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  static __device__ __forceinline__ void store(bf16 *p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t *>(&h);
+    }
+    *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+struct ConvGeom {
+  int B, H, W, C, sp;        // input map (logical size, channels, storage padding)
+  int k, stride, pad;        // square kernel
+  int Ho, Wo;
+  int64_t ldk;               // row pitch of the column matrix (elements), >= k*k*C
+};
+
+// ---- im2col ------------------------------------------------------------------------------------------
+// vector path: C % N == 0 (one thread per (output pixel, tap, channel vector))
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) im2col_vec_kernel(const TI *__restrict__ x, TO *__restrict__ cols, const ConvGeom g) {
+  constexpr int N = CVec<TO>::N;          // output vector width; the input is read with the same element count
+  const int CV = g.C / N, taps = g.k * g.k;
+  const size_t total = (size_t)g.B * g.Ho * g.Wo * taps * CV;
+  const int Hs = g.H + 2 * g.sp, Ws = g.W + 2 * g.sp;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    size_t r = t / CV;
+    const int tap = (int)(r % taps);
+    r /= taps;                                  // output pixel index (b, oy, ox)
+    const int ox = (int)(r % g.Wo);
+    const size_t r2 = r / g.Wo;
+    const int oy = (int)(r2 % g.Ho);
+    const int b = (int)(r2 / g.Ho);
+    const int iy = oy * g.stride - g.pad + tap / g.k, ix = ox * g.stride - g.pad + tap % g.k;
+    float v[N];
+    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) {
+      const TI *src = x + (((size_t)b * Hs + iy + g.sp) * Ws + ix + g.sp) * g.C + (size_t)cv * N;
+      if (sizeof(TI) == sizeof(TO)) {
+        CVec<TO>::load(reinterpret_cast<const TO *>(src), v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = to_f(src[i]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = 0.f;
+    }
+    CVec<TO>::store(cols + r * g.ldk + (size_t)tap * g.C + (size_t)cv * N, v);
+  }
+}
+
+// scalar path (C = 3: the image); also zero-fills the K padding columns [k*k*C, ldk)
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) im2col_scalar_kernel(const TI *__restrict__ x, TO *__restrict__ cols, const ConvGeom g) {
+  const int taps = g.k * g.k;
+  const size_t total = (size_t)g.B * g.Ho * g.Wo * g.ldk;
+  const int Hs = g.H + 2 * g.sp, Ws = g.W + 2 * g.sp;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int kk = (int)(t % g.ldk);
+    const size_t r = t / g.ldk;
+    float v = 0.f;
+    if (kk < taps * g.C) {
+      const int tap = kk / g.C, c = kk % g.C;
+      const int ox = (int)(r % g.Wo);
+      const size_t r2 = r / g.Wo;
+      const int oy = (int)(r2 % g.Ho);
+      const int b = (int)(r2 / g.Ho);
+      const int iy = oy * g.stride - g.pad + tap / g.k, ix = ox * g.stride - g.pad + tap % g.k;
+      if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) v = to_f(x[(((size_t)b * Hs + iy + g.sp) * Ws + ix + g.sp) * g.C + c]);
+    }
+    cols[t] = from_f<TO>(v);
+  }
+}
+
+// ---- col2im: dx[b, iy, ix, :] = sum over the (ky, kx) whose output pixel exists of dcols[(b, oy, ox), (ky, kx), :] -----
+template <typename T>
+__global__ void __launch_bounds__(256) col2im_kernel(const T *__restrict__ dcols, T *__restrict__ dx, const ConvGeom g) {
+  constexpr int N = CVec<T>::N;
+  const int CV = g.C / N;
+  const int Hs = g.H + 2 * g.sp, Ws = g.W + 2 * g.sp;
+  const size_t total = (size_t)g.B * Hs * Ws * CV;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    size_t r = t / CV;
+    const int sx = (int)(r % Ws);
+    r /= Ws;
+    const int sy = (int)(r % Hs);
+    const int b = (int)(r / Hs);
+    const int iy = sy - g.sp, ix = sx - g.sp;
+    float acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+    if (iy >= 0 && iy < g.H && ix >= 0 && ix < g.W) {
+      for (int ky = 0; ky < g.k; ++ky) {
+        const int ny = iy + g.pad - ky;
+        if (ny < 0 || ny % g.stride) continue;
+        const int oy = ny / g.stride;
+        if (oy >= g.Ho) continue;
+        for (int kx = 0; kx < g.k; ++kx) {
+          const int nx = ix + g.pad - kx;
+          if (nx < 0 || nx % g.stride) continue;
+          const int ox = nx / g.stride;
+          if (ox >= g.Wo) continue;
+          float v[N];
+          CVec<T>::load(dcols + (((size_t)b * g.Ho + oy) * g.Wo + ox) * g.ldk + (size_t)(ky * g.k + kx) * g.C + (size_t)cv * N, v);
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[i] += v[i];
+        }
+      }
+    }
+    CVec<T>::store(dx + t * N, acc);          // border of a padded map: zeros
+  }
+}
+
+// ---- per-channel statistics -------------------------------------------------------------------------
+// block (by) owns a strip of pixels; thread (tx) owns one channel vector and strides over the strip's pixels with
+// ty: partial[(by*TY + ty), 0:C] = sum (x - shift), partial[.., C:2C] = sum (x - shift)^2 over the logical pixels.
+// mode 1 (backward): sums of dz and dz * xhat with dz = dy * relu'(a x + b), xhat = (x - mean) * rstd.
+struct StatArgs {
+  int B, H, W, C, sp;
+  const float *shift;                     // mode 0
+  const float *a, *b, *mean, *rstd;       // mode 1 (a, b: the forward's per-channel scale / offset)
+  int relu;
+};
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) chan_stats_kernel(const T *__restrict__ x, const T *__restrict__ dy, float *__restrict__ partial,
+                                                         const StatArgs s, int pix_per_block) {
+  constexpr int N = CVec<T>::N;
+  const int CV = s.C / N;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // 32 channel vectors x 8 pixel lanes
+  const int Hs = s.H + 2 * s.sp, Ws = s.W + 2 * s.sp;
+  const size_t npix = (size_t)s.B * s.H * s.W;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+  for (int cv = blockIdx.y * 32 + tx; cv < CV; cv += gridDim.y * 32) {
+    float k0[N], k1[N], k2[N], k3[N], s1[N], s2[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { s1[i] = s2[i] = 0.f; }
+    if (MODE == 0) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) k0[i] = s.shift[cv * N + i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        k0[i] = s.a[cv * N + i]; k1[i] = s.b[cv * N + i]; k2[i] = s.mean[cv * N + i]; k3[i] = s.rstd[cv * N + i];
+      }
+    }
+    for (size_t p = p0 + ty; p < p1; p += 8) {
+      const int ix = (int)(p % s.W);
+      const size_t q = p / s.W;
+      const int iy = (int)(q % s.H);
+      const size_t b = q / s.H;
+      const size_t off = ((b * Hs + iy + s.sp) * Ws + ix + s.sp) * s.C + (size_t)cv * N;
+      float v[N];
+      CVec<T>::load(x + off, v);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float d = v[i] - k0[i];
+          s1[i] += d;
+          s2[i] = fmaf(d, d, s2[i]);
+        }
+      } else {
+        float g[N];
+        CVec<T>::load(dy + off, g);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float dz = (s.relu && fmaf(k0[i], v[i], k1[i]) <= 0.f) ? 0.f : g[i];
+          s1[i] += dz;
+          s2[i] = fmaf(dz, (v[i] - k2[i]) * k3[i], s2[i]);
+        }
+      }
+    }
+    float *dst = partial + ((size_t)blockIdx.x * 8 + ty) * 2 * s.C + (size_t)cv * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      dst[i] = s1[i];
+      dst[s.C + i] = s2[i];
+    }
+  }
+}
+
+// fixed-order reduction of the partial rows (same scheme as norm.cu's reduce_partials_kernel)
+__global__ void __launch_bounds__(256) conv_reduce_partials_kernel(const float *__restrict__ partial, int nparts, int ncols,
+                                                                   float *__restrict__ out) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float t = 0.f;
+  if (c < ncols)
+    for (int p = ty; p < nparts; p += 8) t += partial[(size_t)p * ncols + c];
+  red[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && c < ncols) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][tx];
+    out[c] = a;
+  }
+}
+
+// ---- BatchNorm apply (+ReLU) and its gradient --------------------------------------------------------
+// forward:  y = act(a[c] * x + b[c])        (a = weight * rstd, b = bias - mean * a); y may have another storage
+//           padding than x; its border is written with zeros
+// backward: dx = a[c] * (dz - c1[c] - xhat * c2[c]),  dz = dy * relu'(a x + b),  c1 = mean(dz), c2 = mean(dz * xhat)
+struct ApplyArgs {
+  int B, H, W, C, sp_in, sp_out;
+  const float *a, *b, *mean, *rstd, *c1, *c2;
+  int relu;
+};
+
+template <typename TI, typename TO, int MODE>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const TI *__restrict__ x, const TI *__restrict__ dy, TO *__restrict__ out,
+                                                       const ApplyArgs s) {
+  constexpr int N = CVec<TO>::N;
+  const int CV = s.C / N;
+  const int Hi = s.H + 2 * s.sp_in, Wi = s.W + 2 * s.sp_in, Ho = s.H + 2 * s.sp_out, Wo = s.W + 2 * s.sp_out;
+  const size_t total = (size_t)s.B * Ho * Wo * CV;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    size_t r = t / CV;
+    const int sx = (int)(r % Wo);
+    r /= Wo;
+    const int sy = (int)(r % Ho);
+    const size_t b = r / Ho;
+    const int iy = sy - s.sp_out, ix = sx - s.sp_out;
+    float o[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[i] = 0.f;
+    if (iy >= 0 && iy < s.H && ix >= 0 && ix < s.W) {
+      const size_t off = ((b * Hi + iy + s.sp_in) * Wi + ix + s.sp_in) * s.C + (size_t)cv * N;
+      float v[N];
+      if (sizeof(TI) == sizeof(TO)) {
+        CVec<TO>::load(reinterpret_cast<const TO *>(x + off), v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = to_f(x[off + i]);
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float y = fmaf(s.a[cv * N + i], v[i], s.b[cv * N + i]);
+          o[i] = s.relu ? fmaxf(y, 0.f) : y;
+        }
+      } else {
+        float g[N];
+        if (sizeof(TI) == sizeof(TO)) {
+          CVec<TO>::load(reinterpret_cast<const TO *>(dy + off), g);
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) g[i] = to_f(dy[off + i]);
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const int c = cv * N + i;
+          const float a = s.a[c];
+          const float dz = (s.relu && fmaf(a, v[i], s.b[c]) <= 0.f) ? 0.f : g[i];
+          const float xhat = (v[i] - s.mean[c]) * s.rstd[c];
+          o[i] = a * (dz - s.c1[c] - xhat * s.c2[c]);
+        }
+      }
+    }
+    CVec<TO>::store(out + t * N, o);
+  }
+}
+
+// ---- 3x3 / stride-2 / pad-1 max pooling (encoders.py:20) ----------------------------------------------
+// forward stores, per output element, which of the 9 taps won (first maximum in row-major window order, as ATen);
+// backward gathers: an input pixel collects the gradient of the <= 4 windows that selected it.
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, uint8_t *__restrict__ idx,
+                                                          int B, int H, int W, int C, int sp_in, int Ho, int Wo, int sp_out) {
+  constexpr int N = CVec<T>::N;
+  const int CV = C / N;
+  const int Hi = H + 2 * sp_in, Wi = W + 2 * sp_in, Hs = Ho + 2 * sp_out, Ws = Wo + 2 * sp_out;
+  const size_t total = (size_t)B * Hs * Ws * CV;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    size_t r = t / CV;
+    const int sx = (int)(r % Ws);
+    r /= Ws;
+    const int sy = (int)(r % Hs);
+    const size_t b = r / Hs;
+    const int oy = sy - sp_out, ox = sx - sp_out;
+    float best[N];
+    uint8_t bi[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) { best[i] = 0.f; bi[i] = 255; }
+    if (oy >= 0 && oy < Ho && ox >= 0 && ox < Wo) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) best[i] = -INFINITY;
+      for (int tap = 0; tap < 9; ++tap) {
+        const int iy = oy * 2 - 1 + tap / 3, ix = ox * 2 - 1 + tap % 3;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        float v[N];
+        CVec<T>::load(x + ((b * Hi + iy + sp_in) * Wi + ix + sp_in) * C + (size_t)cv * N, v);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+          if (v[i] > best[i] || v[i] != v[i]) { best[i] = v[i]; bi[i] = (uint8_t)tap; }
+      }
+    }
+    CVec<T>::store(y + t * N, best);
+#pragma unroll
+    for (int i = 0; i < N; ++i) idx[t * N + i] = bi[i];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T *__restrict__ gy, const uint8_t *__restrict__ idx, T *__restrict__ gx,
+                                                          int B, int H, int W, int C, int sp_in, int Ho, int Wo, int sp_out) {
+  constexpr int N = CVec<T>::N;
+  const int CV = C / N;
+  const int Hi = H + 2 * sp_in, Wi = W + 2 * sp_in, Hs = Ho + 2 * sp_out, Ws = Wo + 2 * sp_out;
+  const size_t total = (size_t)B * Hi * Wi * CV;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(t % CV);
+    size_t r = t / CV;
+    const int sx = (int)(r % Wi);
+    r /= Wi;
+    const int sy = (int)(r % Hi);
+    const size_t b = r / Hi;
+    const int iy = sy - sp_in, ix = sx - sp_in;
+    float acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      for (int ky = 0; ky < 3; ++ky) {
+        const int ny = iy + 1 - ky;
+        if (ny < 0 || (ny & 1)) continue;
+        const int oy = ny >> 1;
+        if (oy >= Ho) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+          const int nx = ix + 1 - kx;
+          if (nx < 0 || (nx & 1)) continue;
+          const int ox = nx >> 1;
+          if (ox >= Wo) continue;
+          const size_t o = (((b * Hs + oy + sp_out) * Ws + ox + sp_out) * C) + (size_t)cv * N;
+          float v[N];
+          CVec<T>::load(gy + o, v);
+          const uint8_t tap = (uint8_t)(ky * 3 + kx);
+#pragma unroll
+          for (int i = 0; i < N; ++i)
+            if (idx[o + i] == tap) acc[i] += v[i];
+        }
+      }
+    }
+    CVec<T>::store(gx + t * N, acc);
+  }
+}
+
+// ---- 3x3 / stride-1 / pad-1 convolution with a handful of output channels (decoders.py:129: 64 -> n_classes) ------
+// The column matrix of this layer would be 12 x 672^2 x 576 elements; with <= 4 outputs a direct kernel is the natural
+// form: a warp owns one output pixel, its lanes split the channel vectors, the 9 x CO weights of a lane's channels stay
+// in registers, a shuffle tree finishes the dot products.  x: [B, H, W, C] plain; y: [B, H, W, CO] (f32).
+template <typename T, int CO>
+__global__ void __launch_bounds__(256) smallconv_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w /*[CO,3,3,C]*/,
+                                                            const float *__restrict__ bias, float *__restrict__ y, int B, int H, int W, int C) {
+  constexpr int N = CVec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int CV = C / N;                 // <= 32 handled (C <= 128 f32 / 256 bf16)
+  const size_t npix = (size_t)B * H * W;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  float wr[CO][9][N];
+  if (lane < CV) {
+#pragma unroll
+    for (int co = 0; co < CO; ++co)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int i = 0; i < N; ++i) wr[co][tap][i] = w[((size_t)co * 9 + tap) * C + lane * N + i];
+  }
+  for (size_t p = warp0; p < npix; p += nwarps) {
+    const int ix = (int)(p % W);
+    const size_t q = p / W;
+    const int iy = (int)(q % H);
+    const size_t b = q / H;
+    float acc[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[co] = 0.f;
+    if (lane < CV) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = iy - 1 + tap / 3, xx = ix - 1 + tap % 3;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        float v[N];
+        CVec<T>::load(x + ((b * H + yy) * W + xx) * C + (size_t)lane * N, v);
+#pragma unroll
+        for (int co = 0; co < CO; ++co)
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[co] = fmaf(v[i], wr[co][tap][i], acc[co]);
+      }
+    }
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[co] = warp_sum(acc[co]);
+    if (lane == 0) {
+#pragma unroll
+      for (int co = 0; co < CO; ++co) y[p * CO + co] = acc[co] + (bias ? bias[co] : 0.f);
+    }
+  }
+}
+
+// input gradient: dx[b, y, x, c] = sum_{tap, co} dy[b, y - dy(tap), x - dx(tap), co] * w[co, tap, c]
+template <typename T, int CO>
+__global__ void __launch_bounds__(256) smallconv_dgrad_kernel(const float *__restrict__ gy, const float *__restrict__ w, T *__restrict__ gx,
+                                                              int B, int H, int W, int C) {
+  constexpr int N = CVec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int CV = C / N;
+  const size_t npix = (size_t)B * H * W;
+  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  float wr[CO][9][N];
+  if (lane < CV) {
+#pragma unroll
+    for (int co = 0; co < CO; ++co)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int i = 0; i < N; ++i) wr[co][tap][i] = w[((size_t)co * 9 + tap) * C + lane * N + i];
+  }
+  for (size_t p = warp0; p < npix; p += nwarps) {
+    const int ix = (int)(p % W);
+    const size_t q = p / W;
+    const int iy = (int)(q % H);
+    const size_t b = q / H;
+    float acc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      // output pixel (oy, ox) read input (oy - 1 + ky, ox - 1 + kx): this input pixel is its tap (ky, kx) when oy = iy + 1 - ky
+      const int oy = iy + 1 - tap / 3, ox = ix + 1 - tap % 3;
+      if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
+      const float *g = gy + ((b * H + oy) * W + ox) * CO;
+#pragma unroll
+      for (int co = 0; co < CO; ++co) {
+        const float d = g[co];
+        if (lane < CV) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[i] = fmaf(d, wr[co][tap][i], acc[i]);
+        }
+      }
+    }
+    if (lane < CV) CVec<T>::store(gx + p * C + (size_t)lane * N, acc);
+  }
+}
+
+// weight gradient partials: block strip of pixels -> partial[block, CO*9*C]; lanes own channel vectors as above, the
+// 8 warps of a block are combined through shared memory, blocks by conv_reduce_partials_kernel
+template <typename T, int CO>
+__global__ void __launch_bounds__(256) smallconv_wgrad_kernel(const T *__restrict__ x, const float *__restrict__ gy, float *__restrict__ partial,
+                                                              int B, int H, int W, int C, int pix_per_block) {
+  constexpr int N = CVec<T>::N;
+  extern __shared__ float sh[];          // [8 warps][CO*9*C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int CV = C / N;
+  const size_t npix = (size_t)B * H * W;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
+  float acc[CO][9][N];
+#pragma unroll
+  for (int co = 0; co < CO; ++co)
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int i = 0; i < N; ++i) acc[co][tap][i] = 0.f;
+  for (size_t p = p0 + warp; p < p1; p += 8) {
+    const int ix = (int)(p % W);
+    const size_t q = p / W;
+    const int iy = (int)(q % H);
+    const size_t b = q / H;
+    float d[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) d[co] = gy[p * CO + co];
+    if (lane < CV) {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int yy = iy - 1 + tap / 3, xx = ix - 1 + tap % 3;
+        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+        float v[N];
+        CVec<T>::load(x + ((b * H + yy) * W + xx) * C + (size_t)lane * N, v);
+#pragma unroll
+        for (int co = 0; co < CO; ++co)
+#pragma unroll
+          for (int i = 0; i < N; ++i) acc[co][tap][i] = fmaf(d[co], v[i], acc[co][tap][i]);
+      }
+    }
+  }
+  const int per = CO * 9 * C;
+  if (lane < CV) {
+#pragma unroll
+    for (int co = 0; co < CO; ++co)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int i = 0; i < N; ++i) sh[(size_t)warp * per + (co * 9 + tap) * C + lane * N + i] = acc[co][tap][i];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < per; e += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += sh[(size_t)wv * per + e];
+    partial[(size_t)blockIdx.x * per + e] = t;
+  }
+}
+
+static unsigned grid_for(size_t total) { return (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 32); }
+
+}  // namespace asis
+
+using namespace asis;
+
+static int conv_geom(ConvGeom &g, int B, int H, int W, int C, int sp, int k, int stride, int pad, int64_t ldk) {
+  ASIS_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && sp >= 0 && k >= 1 && k <= 7 && stride >= 1 && pad >= 0, "conv: bad geometry");
+  g.B = B; g.H = H; g.W = W; g.C = C; g.sp = sp; g.k = k; g.stride = stride; g.pad = pad;
+  g.Ho = (H + 2 * pad - k) / stride + 1;
+  g.Wo = (W + 2 * pad - k) / stride + 1;
+  g.ldk = ldk;
+  ASIS_REQUIRE(g.Ho > 0 && g.Wo > 0, "conv: empty output");
+  ASIS_REQUIRE(ldk >= (int64_t)k * k * C, "conv: ldk=%lld < k*k*C", (long long)ldk);
+  return ASIS_OK;
+}
+
+extern "C" int asis_im2col(const void *x, int x_dtype, void *cols, int cols_dtype, int B, int H, int W, int C, int storage_pad,
+                           int k, int stride, int pad, int64_t ldk, void *stream) {
+  ASIS_REQUIRE(x && cols, "im2col: null pointer");
+  ASIS_REQUIRE(dtype_ok(x_dtype) && dtype_ok(cols_dtype), "im2col: bad dtype");
+  ConvGeom g;
+  if (int rc = conv_geom(g, B, H, W, C, storage_pad, k, stride, pad, ldk)) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int NV = cols_dtype == ASIS_BF16 ? 8 : 4;
+  const bool vec = C % NV == 0 && ldk % NV == 0 && ldk == (int64_t)k * k * C && aligned16(x) && aligned16(cols) &&
+                   !(x_dtype == ASIS_BF16 && cols_dtype == ASIS_F32);
+  if (vec) {
+    const size_t total = (size_t)B * g.Ho * g.Wo * k * k * (C / NV);
+    ASIS_DISPATCH_DTYPE(x_dtype, TI, ASIS_DISPATCH_DTYPE(cols_dtype, TO, (im2col_vec_kernel<TI, TO><<<grid_for(total), 256, 0, st>>>((const TI *)x, (TO *)cols, g))));
+  } else {
+    const size_t total = (size_t)B * g.Ho * g.Wo * ldk;
+    ASIS_DISPATCH_DTYPE(x_dtype, TI, ASIS_DISPATCH_DTYPE(cols_dtype, TO, (im2col_scalar_kernel<TI, TO><<<grid_for(total), 256, 0, st>>>((const TI *)x, (TO *)cols, g))));
+  }
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_col2im(const void *dcols, void *dx, int dtype, int B, int H, int W, int C, int storage_pad, int k, int stride,
+                           int pad, int64_t ldk, void *stream) {
+  ASIS_REQUIRE(dcols && dx, "col2im: null pointer");
+  ASIS_REQUIRE(dtype_ok(dtype), "col2im: bad dtype");
+  ConvGeom g;
+  if (int rc = conv_geom(g, B, H, W, C, storage_pad, k, stride, pad, ldk)) return rc;
+  const int NV = dtype == ASIS_BF16 ? 8 : 4;
+  ASIS_REQUIRE(C % NV == 0 && ldk % NV == 0 && aligned16(dcols) && aligned16(dx), "col2im: C=%d and ldk must be multiples of %d", C, NV);
+  const size_t total = (size_t)B * (H + 2 * storage_pad) * (W + 2 * storage_pad) * (C / NV);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(dtype, T, (col2im_kernel<T><<<grid_for(total), 256, 0, st>>>((const T *)dcols, (T *)dx, g)));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+static int stat_blocks(size_t npix, int &ppb) {
+  int nb = (int)std::min<size_t>((npix + 255) / 256, 592);
+  if (nb < 1) nb = 1;
+  ppb = (int)((npix + nb - 1) / nb);
+  return nb;
+}
+
+extern "C" size_t asis_chan_stats_workspace_bytes(int B, int H, int W, int C) {
+  int ppb;
+  const int nb = stat_blocks((size_t)B * H * W, ppb);
+  return (size_t)nb * 8 * 2 * C * sizeof(float);
+}
+
+// mode 0: s1 = sum (x - shift), s2 = sum (x - shift)^2.   mode 1: s1 = sum dz, s2 = sum dz * xhat (see StatArgs).
+extern "C" int asis_chan_stats(int mode, const void *x, const void *dy, int dtype, int B, int H, int W, int C, int storage_pad,
+                               const float *shift, const float *a, const float *b, const float *mean, const float *rstd, int relu,
+                               float *s1, float *s2, void *workspace, size_t workspace_bytes, void *stream) {
+  ASIS_REQUIRE(x && s1 && s2 && workspace, "chan_stats: null pointer");
+  ASIS_REQUIRE(dtype_ok(dtype), "chan_stats: bad dtype");
+  ASIS_REQUIRE(mode == 0 ? shift != nullptr : (dy && a && b && mean && rstd), "chan_stats: missing per-channel vectors for mode %d", mode);
+  const int NV = dtype == ASIS_BF16 ? 8 : 4;
+  ASIS_REQUIRE(C % NV == 0 && aligned16(x), "chan_stats: C=%d must be a multiple of %d", C, NV);
+  ASIS_REQUIRE(s2 == s1 + C, "chan_stats: s2 must follow s1 (one [2C] buffer)");
+  const size_t need = asis_chan_stats_workspace_bytes(B, H, W, C);
+  if (workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "chan_stats: workspace %zu < %zu bytes", workspace_bytes, need);
+  int ppb;
+  const int nb = stat_blocks((size_t)B * H * W, ppb);
+  StatArgs s{B, H, W, C, storage_pad, shift, a, b, mean, rstd, relu};
+  const int CV = C / NV;
+  dim3 grid(nb, (CV + 31) / 32 > 8 ? 8 : (CV + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  float *partial = (float *)workspace;
+  if (mode == 0) {
+    ASIS_DISPATCH_DTYPE(dtype, T, (chan_stats_kernel<T, 0><<<grid, 256, 0, st>>>((const T *)x, nullptr, partial, s, ppb)));
+  } else {
+    ASIS_DISPATCH_DTYPE(dtype, T, (chan_stats_kernel<T, 1><<<grid, 256, 0, st>>>((const T *)x, (const T *)dy, partial, s, ppb)));
+  }
+  ASIS_LAUNCHED();
+  conv_reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nb * 8, 2 * C, s1);
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+// mode 0: y = act(a x + b).  mode 1: dx = a (dz - c1 - xhat c2).
+extern "C" int asis_bn_apply(int mode, const void *x, const void *dy, int in_dtype, void *out, int out_dtype, int B, int H, int W, int C,
+                             int pad_in, int pad_out, const float *a, const float *b, const float *mean, const float *rstd,
+                             const float *c1, const float *c2, int relu, void *stream) {
+  ASIS_REQUIRE(x && out && a && b, "bn_apply: null pointer");
+  ASIS_REQUIRE(dtype_ok(in_dtype) && dtype_ok(out_dtype), "bn_apply: bad dtype");
+  ASIS_REQUIRE(mode == 0 || (dy && mean && rstd && c1 && c2), "bn_apply: backward needs dy, mean, rstd, c1, c2");
+  const int NV = out_dtype == ASIS_BF16 ? 8 : 4;
+  ASIS_REQUIRE(C % NV == 0 && aligned16(x) && aligned16(out), "bn_apply: C=%d must be a multiple of %d", C, NV);
+  ASIS_REQUIRE(!(in_dtype == ASIS_BF16 && out_dtype == ASIS_F32), "bn_apply: bf16 -> f32 is not provided");
+  ApplyArgs s{B, H, W, C, pad_in, pad_out, a, b, mean, rstd, c1, c2, relu};
+  const size_t total = (size_t)B * (H + 2 * pad_out) * (W + 2 * pad_out) * (C / NV);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 0) {
+    ASIS_DISPATCH_DTYPE(in_dtype, TI, ASIS_DISPATCH_DTYPE(out_dtype, TO, (bn_apply_kernel<TI, TO, 0><<<grid_for(total), 256, 0, st>>>((const TI *)x, nullptr, (TO *)out, s))));
+  } else {
+    ASIS_DISPATCH_DTYPE(in_dtype, TI, ASIS_DISPATCH_DTYPE(out_dtype, TO, (bn_apply_kernel<TI, TO, 1><<<grid_for(total), 256, 0, st>>>((const TI *)x, (const TI *)dy, (TO *)out, s))));
+  }
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_maxpool3x3s2_forward(const void *x, void *y, uint8_t *idx, int dtype, int B, int H, int W, int C, int pad_in,
+                                         int pad_out, void *stream) {
+  ASIS_REQUIRE(x && y && idx && dtype_ok(dtype), "maxpool: bad arguments");
+  const int NV = dtype == ASIS_BF16 ? 8 : 4;
+  ASIS_REQUIRE(C % NV == 0 && aligned16(x) && aligned16(y), "maxpool: C=%d must be a multiple of %d", C, NV);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * (Ho + 2 * pad_out) * (Wo + 2 * pad_out) * (C / NV);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(dtype, T, (maxpool_fwd_kernel<T><<<grid_for(total), 256, 0, st>>>((const T *)x, (T *)y, idx, B, H, W, C, pad_in, Ho, Wo, pad_out)));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_maxpool3x3s2_backward(const void *gy, const uint8_t *idx, void *gx, int dtype, int B, int H, int W, int C, int pad_in,
+                                          int pad_out, void *stream) {
+  ASIS_REQUIRE(gy && gx && idx && dtype_ok(dtype), "maxpool: bad arguments");
+  const int NV = dtype == ASIS_BF16 ? 8 : 4;
+  ASIS_REQUIRE(C % NV == 0 && aligned16(gy) && aligned16(gx), "maxpool: C=%d must be a multiple of %d", C, NV);
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)B * (H + 2 * pad_in) * (W + 2 * pad_in) * (C / NV);
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(dtype, T, (maxpool_bwd_kernel<T><<<grid_for(total), 256, 0, st>>>((const T *)gy, idx, (T *)gx, B, H, W, C, pad_in, Ho, Wo, pad_out)));
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+template <typename T, int CO>
+static int smallconv_launch(int what, const void *x, const float *w, const float *bias, float *y, const float *gy, void *gx,
+                            float *partial, int nb, int ppb, int B, int H, int W, int C, cudaStream_t st) {
+  const size_t npix = (size_t)B * H * W;
+  const unsigned blocks = (unsigned)std::min<size_t>((npix + 7) / 8, (size_t)148 * 16);
+  if (what == 0) smallconv_fwd_kernel<T, CO><<<blocks, 256, 0, st>>>((const T *)x, w, bias, y, B, H, W, C);
+  else if (what == 1) smallconv_dgrad_kernel<T, CO><<<blocks, 256, 0, st>>>(gy, w, (T *)gx, B, H, W, C);
+  else {
+    const size_t shb = (size_t)8 * CO * 9 * C * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      ASIS_CUDA(cudaFuncSetAttribute(smallconv_wgrad_kernel<T, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    smallconv_wgrad_kernel<T, CO><<<nb, 256, shb, st>>>((const T *)x, gy, partial, B, H, W, C, ppb);
+  }
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+static int smallconv_check(int dtype, int C, int CO) {
+  ASIS_REQUIRE(dtype_ok(dtype), "smallconv: bad dtype");
+  const int NV = dtype == ASIS_BF16 ? 8 : 4;
+  ASIS_REQUIRE(C % NV == 0 && C / NV <= 32, "smallconv: C=%d must be a multiple of %d and at most %d", C, NV, 32 * NV);
+  ASIS_REQUIRE(CO >= 1 && CO <= 4, "smallconv: 1..4 output channels (got %d); wider layers go through im2col + gemm", CO);
+  ASIS_REQUIRE((size_t)8 * CO * 9 * C * sizeof(float) <= 200 * 1024, "smallconv: C * CO too large");
+  return ASIS_OK;
+}
+
+#define ASIS_SMALLCONV(T, CO, ...)                                   \
+  do {                                                               \
+    switch (CO) {                                                    \
+      case 1: rc = smallconv_launch<T, 1>(__VA_ARGS__); break;       \
+      case 2: rc = smallconv_launch<T, 2>(__VA_ARGS__); break;       \
+      case 3: rc = smallconv_launch<T, 3>(__VA_ARGS__); break;       \
+      default: rc = smallconv_launch<T, 4>(__VA_ARGS__); break;      \
+    }                                                                \
+  } while (0)
+
+extern "C" int asis_smallconv3x3_forward(const void *x, int dtype, const float *w, const float *bias, float *y, int B, int H, int W,
+                                         int C, int CO, void *stream) {
+  ASIS_REQUIRE(x && w && y, "smallconv: null pointer");
+  if (int rc = smallconv_check(dtype, C, CO)) return rc;
+  int rc = ASIS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(dtype, T, ASIS_SMALLCONV(T, CO, 0, x, w, bias, y, nullptr, nullptr, nullptr, 0, 0, B, H, W, C, st));
+  return rc;
+}
+
+static int smallconv_wgrad_blocks(size_t npix, int &ppb) {
+  int nb = (int)std::min<size_t>((npix + 2047) / 2048, 296);
+  if (nb < 1) nb = 1;
+  ppb = (int)((npix + nb - 1) / nb);
+  return nb;
+}
+
+extern "C" size_t asis_smallconv3x3_backward_workspace_bytes(int B, int H, int W, int C, int CO) {
+  int ppb;
+  return (size_t)smallconv_wgrad_blocks((size_t)B * H * W, ppb) * CO * 9 * C * sizeof(float);
+}
+
+// gx (dtype, may be null), gw [CO,3,3,C] f32 (may be null); the bias gradient is the column sum of gy (asis_colsum)
+extern "C" int asis_smallconv3x3_backward(const void *x, int dtype, const float *w, const float *gy, void *gx, float *gw, int B, int H,
+                                          int W, int C, int CO, void *workspace, size_t workspace_bytes, void *stream) {
+  ASIS_REQUIRE(x && w && gy, "smallconv: null pointer");
+  if (int rc = smallconv_check(dtype, C, CO)) return rc;
+  int rc = ASIS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (gx) {
+    ASIS_DISPATCH_DTYPE(dtype, T, ASIS_SMALLCONV(T, CO, 1, x, w, nullptr, nullptr, gy, gx, nullptr, 0, 0, B, H, W, C, st));
+    if (rc) return rc;
+  }
+  if (gw) {
+    const size_t need = asis_smallconv3x3_backward_workspace_bytes(B, H, W, C, CO);
+    if (!workspace || workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "smallconv: workspace %zu < %zu bytes", workspace_bytes, need);
+    int ppb;
+    const int nb = smallconv_wgrad_blocks((size_t)B * H * W, ppb);
+    ASIS_DISPATCH_DTYPE(dtype, T, ASIS_SMALLCONV(T, CO, 2, x, w, nullptr, nullptr, gy, nullptr, (float *)workspace, nb, ppb, B, H, W, C, st));
+    if (rc) return rc;
+    conv_reduce_partials_kernel<<<(CO * 9 * C + 31) / 32, 256, 0, st>>>((const float *)workspace, nb, CO * 9 * C, gw);
+    ASIS_LAUNCHED();
+  }
+  return rc;
+}

@@ -1,10 +1,18 @@
-"""FeatureDecoder (backbones/decoders.py:92-164) -- same layer layout and state_dict keys.
-SURVEY.md section 8(f) rank 2: *next*, runs on PyTorch library convolutions for now."""
+"""FeatureDecoder (backbones/decoders.py:92-164) -- same layer layout, constructor arguments and state_dict keys,
+running on libasis_b200 kernels (adaptersis_b200/conv.py), channels-last:
+
+  decoder_1..4   3x3 conv (pad 1, bias) + BatchNorm2d + ReLU + bilinear x2 (align_corners=True)    42 -> 84 -> 168 -> 336 -> 672
+  final_out      3x3 conv 64 -> num_classes
+
+The four wide convolutions are asis_im2col + tcgen05 GEMM (the first one, 3 x embed_dim -> 512 at 42 x 42, is a
+K = 27648 GEMM); BatchNorm + ReLU is one statistics pass + one fused normalise pass; the resize is the channels-last
+kernel pair of csrc/misc.cu; the head is a direct kernel.  Plain BatchNorm2d: per-GPU statistics under data
+parallelism, as in the reference."""
 import torch
 import torch.nn as nn
 
+from . import conv as Cv
 from . import functional as Fn
-from .functional import get_precision
 
 
 class FeatureDecoder(nn.Module):
@@ -23,18 +31,15 @@ class FeatureDecoder(nn.Module):
         self.final_out = nn.Conv2d(features[4], num_classes, 3, padding=1)
 
     def forward(self, x):
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=get_precision() != "fp32"):
-            return self._forward(x)
-
-    def _forward(self, x):
-        lowp = get_precision() == "bf16" and x.is_cuda
+        """x [B, 3*embed_dim, h, w] (any memory format; channels-last is free) -> logits [B, num_classes, 16h, 16w] f32."""
+        x = x.permute(0, 2, 3, 1).contiguous()          # (asis_im2col converts to the compute dtype on the way)
         for k in range(1, 5):
-            conv, bn, relu, up = getattr(self, f"decoder_{k}")
-            x = relu(bn(conv(x)))
-            if lowp and x.shape[1] % 8 == 0:
-                # bf16 mode: the 2x bilinear resize is our channels-last kernel (ATen's NHWC kernel runs at
-                # ~100 GB/s here and autocast would run it in fp32: 13 ms of a 165 ms step)
-                x = Fn.upsample2x(x.to(torch.bfloat16))
-            else:
-                x = up(x)
-        return self.final_out(x)
+            conv, bn, _, _ = getattr(self, f"decoder_{k}")
+            x = Cv.conv2d(x, conv.weight, conv.bias, 1, 1)
+            x = Cv.batch_norm(x, bn, relu=True)
+            x = Fn.upsample2x_nhwc(x)
+        if self.num_classes <= 4:
+            y = Cv.smallconv3x3(x, self.final_out.weight, self.final_out.bias)
+        else:
+            y = Cv.conv2d(x, self.final_out.weight, self.final_out.bias, 1, 1, out_dtype=torch.float32)
+        return y.permute(0, 3, 1, 2)

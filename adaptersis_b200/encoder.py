@@ -62,11 +62,12 @@ class AdapterEncoder(nn.Module):
         gh, gw = H // self.patch_size, W // self.patch_size
         C = x.shape[-1]
         with guard():
-            out_last = x.transpose(1, 2).reshape(B, C, gh, gw)
-            out_vit = taps[3].transpose(1, 2).reshape(B, C, gh, gw)
+            # train.py:389-406 -- rearrange "b (h w) c -> b c h w", pad c4 18 -> 42, cat along the channels.  The token
+            # tensors ARE the channels-last maps, so the concatenation is built channels-last ([B, gh, gw, 3C]) and
+            # handed on as the NCHW tensor the reference produces: same logical values, no transposes; the decoder's
+            # permute back to channels-last is a view.
             s4 = H // 32
-            c4m = c4.transpose(1, 2).reshape(B, C, s4, s4)
             dy, dx = gh - s4, gw - s4
-            c4m = F.pad(c4m, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
-            feat = torch.cat((out_last, c4m, out_vit), dim=1)
+            c4m = F.pad(c4.reshape(B, s4, s4, C), [0, 0, dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
+            feat = torch.cat((x.reshape(B, gh, gw, C), c4m, taps[3].reshape(B, gh, gw, C)), dim=3).permute(0, 3, 1, 2)
         return {"x": x, "c": c, "feat": feat}

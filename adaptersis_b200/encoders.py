@@ -1,16 +1,31 @@
-"""Spatial prior module ("FeatureEncoder", backbones/encoders.py:4-74) -- same layer layout and
-state_dict keys.  SURVEY.md section 8(f) rank 1: this component is *next*, not yet on the
-hand-written path; it runs on PyTorch library convolutions (cuDNN) + SyncBatchNorm for now and is
-excluded from every "our kernels" claim."""
+"""Spatial prior module ("FeatureEncoder", backbones/encoders.py:4-74) -- same layer layout, constructor
+arguments and state_dict keys (nn.Conv2d / nn.SyncBatchNorm hold the parameters and running statistics), running
+on libasis_b200 kernels (adaptersis_b200/conv.py, csrc/conv.cu), channels-last from the first convolution on:
+
+  stem   3x3/s2 conv (3 -> p) + SyncBN + ReLU, 2 x [3x3 conv + SyncBN + ReLU], 3x3/s2 max pool       588 -> 294 -> 147
+  conv2..4   3x3/s2 conv + SyncBN + ReLU (padding 0, 0, 1: only 588 lines the pyramid up)     73, 36, 18
+  fc1..4     1x1 convolutions to embed_dim = one GEMM each on the token-major maps: the reference's
+             ``c.view(bs, dim, -1).transpose(1, 2)`` is the identity here (the maps already are [B, H*W, C])
+
+Every convolution is asis_im2col + the tcgen05 GEMM (bf16 mode) or the FFMA GEMM (fp32 parity mode); every
+SyncBatchNorm exchanges one small tensor per direction (global-batch statistics, the reference's semantics).
+``with_cp`` (activation checkpointing; the reference's own implementation of it is broken, encoders.py:71) is
+accepted and ignored."""
 import torch
 import torch.nn as nn
 
-from .functional import get_precision
+from . import conv as Cv
+from . import functional as Fn
 
 
 def _cbr(cin, cout, stride, padding):
     return [nn.Conv2d(cin, cout, kernel_size=3, stride=stride, padding=padding, bias=False),
             nn.SyncBatchNorm(cout), nn.ReLU(inplace=True)]
+
+
+def _conv_bn_relu(x, conv, bn):
+    y = Cv.conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])
+    return Cv.batch_norm(y, bn, relu=True)
 
 
 class FeatureEncoder(nn.Module):
@@ -28,21 +43,23 @@ class FeatureEncoder(nn.Module):
         self.fc3 = nn.Conv2d(4 * p, embed_dim, kernel_size=1, bias=True)
         self.fc4 = nn.Conv2d(8 * p, embed_dim, kernel_size=1, bias=True)
 
-    def forward(self, x, need_c1=True):
-        # fp32 parity mode: keep the library convolutions out of TF32
-        lowp = get_precision() == "bf16" and x.is_cuda
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=get_precision() != "fp32"), \
-                torch.autocast("cuda", dtype=torch.bfloat16, enabled=lowp):
-            if lowp:
-                x = x.contiguous(memory_format=torch.channels_last)
-            return self._forward(x, need_c1)
+    @staticmethod
+    def _project(fc, c):
+        """1x1 convolution of a channels-last map = nn.Linear over its pixels -> tokens [B, H*W, embed_dim] (f32)."""
+        B, H, W, C = c.shape
+        return Fn.linear(c.reshape(B, H * W, C), fc.weight.view(fc.out_channels, C), fc.bias, out_dtype=torch.float32)
 
-    def _forward(self, x, need_c1):
-        c1 = self.stem(x)
-        c2 = self.conv2(c1)
-        c3 = self.conv3(c2)
-        c4 = self.conv4(c3)
-        # fc1(c1) feeds nothing downstream in train.py (:279, then unused); need_c1=False skips it
-        o1 = self.fc1(c1) if need_c1 else None
-        toks = [f(c).flatten(2).transpose(1, 2) for f, c in ((self.fc2, c2), (self.fc3, c3), (self.fc4, c4))]
-        return o1, toks[0], toks[1], toks[2]
+    def forward(self, x, need_c1=True):
+        """x [B, 3, H, W] (as the reference) -> (c1 [B, D, H/4, W/4] or None, c2, c3, c4 tokens [B, n, D])."""
+        x = x.permute(0, 2, 3, 1).contiguous().float()                   # channels-last image
+        for i in (0, 3, 6):
+            x = _conv_bn_relu(x, self.stem[i], self.stem[i + 1])
+        c1 = Cv.maxpool3x3s2(x)
+        c2 = _conv_bn_relu(c1, self.conv2[0], self.conv2[1])
+        c3 = _conv_bn_relu(c2, self.conv3[0], self.conv3[1])
+        c4 = _conv_bn_relu(c3, self.conv4[0], self.conv4[1])
+        o1 = None
+        if need_c1:        # fc1(c1) feeds nothing downstream in train.py (:279, then unused); need_c1=False skips it
+            B, H, W, _ = c1.shape
+            o1 = self._project(self.fc1, c1).view(B, H, W, -1).permute(0, 3, 1, 2)
+        return o1, self._project(self.fc2, c2), self._project(self.fc3, c3), self._project(self.fc4, c4)

@@ -29,8 +29,8 @@ def set_precision(mode):
     if mode not in ("fp32", "bf16"):
         raise ValueError("precision must be 'fp32' or 'bf16'")
     _MODE[0] = mode
-    # the not-yet-native parts (spatial prior module / decoder convolutions) run on
-    # cuDNN: keep them out of TF32 in parity mode, forward and backward
+    # (no library convolution is left on the path; kept so that user code mixing in cuDNN layers stays out of TF32
+    # in parity mode)
     torch.backends.cudnn.allow_tf32 = mode != "fp32"
 
 
@@ -65,7 +65,7 @@ _CHECK_WCACHE = bool(int(os.environ.get("ASIS_CHECK_WEIGHT_CACHE", "0")))
 
 def invalidate_weight_cache():
     """Drop every cached low-precision weight copy (needed only after writes through ``param.data``)."""
-    for key in [k for k in _wcache if not isinstance(k, tuple)]:
+    for key in [k for k in _wcache if not (isinstance(k, tuple) and k[0] == "ones")]:
         _wcache.pop(key, None)
 
 
@@ -494,3 +494,20 @@ class Upsample2xFunction(Function):
 
 def upsample2x(x):
     return Upsample2xFunction.apply(x)
+
+
+class Upsample2xNHWCFunction(Function):
+    """the same resize on a channels-last map [B, H, W, C] -> [B, 2H, 2W, C] (adaptersis_b200/decoders.py)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.upsample2x_forward(x.contiguous())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        return K.upsample2x_backward(gy.contiguous())
+
+
+def upsample2x_nhwc(x):
+    return Upsample2xNHWCFunction.apply(x)

@@ -347,3 +347,140 @@ def upsample2x_backward(gy_nhwc):
         check(_lib.load().asis_upsample2x_bilinear_backward(ptr(gy_nhwc), ptr(gx), dt(gy_nhwc), B, OH // 2, OW // 2, C,
                                                             stream()))
     return gx
+
+
+# ------------------------------------------------------------------- convolutional stages (SPM, decoder)
+def conv_out_size(n, k, stride, pad):
+    return (n + 2 * pad - k) // stride + 1
+
+
+def im2col(x, k, stride, pad, out_dtype, storage_pad=0):
+    """x [B, H+2sp, W+2sp, C] channels-last -> cols [B*Ho*Wo, ldk], K = (ky, kx, c), ldk = k*k*C rounded up to 8."""
+    need_cuda(x)
+    B, Hs, Ws, C = x.shape
+    H, W = Hs - 2 * storage_pad, Ws - 2 * storage_pad
+    Ho, Wo = conv_out_size(H, k, stride, pad), conv_out_size(W, k, stride, pad)
+    Kd = k * k * C
+    ldk = (Kd + 7) // 8 * 8
+    x = _c(x)
+    cols = torch.empty(B * Ho * Wo, ldk, dtype=out_dtype, device=x.device)
+    nb = cols.numel() * cols.element_size() + B * H * W * C * x.element_size()
+    with _Span("im2col", nb, "B"):
+        check(_lib.load().asis_im2col(ptr(x), dt(x), ptr(cols), dt(cols), B, H, W, C, storage_pad, k, stride, pad, ldk,
+                                      stream()))
+    return cols, (Ho, Wo)
+
+
+def col2im(dcols, B, H, W, C, k, stride, pad, storage_pad=0):
+    """dcols [B*Ho*Wo, ldk] -> dx [B, H+2sp, W+2sp, C] (gather over the taps that touch an input pixel)."""
+    need_cuda(dcols)
+    dcols = _c(dcols)
+    dx = torch.empty(B, H + 2 * storage_pad, W + 2 * storage_pad, C, dtype=dcols.dtype, device=dcols.device)
+    nb = (dcols.numel() + dx.numel()) * dcols.element_size()
+    with _Span("col2im", nb, "B"):
+        check(_lib.load().asis_col2im(ptr(dcols), ptr(dx), dt(dx), B, H, W, C, storage_pad, k, stride, pad,
+                                      dcols.stride(0), stream()))
+    return dx
+
+
+def chan_stats(x, shift, storage_pad=0):
+    """x [B, Hs, Ws, C] -> s [2, C] f32: sum (x - shift), sum (x - shift)^2 over the logical pixels."""
+    need_cuda(x, shift)
+    lib = _lib.load()
+    B, Hs, Ws, C = x.shape
+    H, W = Hs - 2 * storage_pad, Ws - 2 * storage_pad
+    x = _c(x)
+    s = torch.empty(2, C, dtype=torch.float32, device=x.device)
+    nbytes = lib.asis_chan_stats_workspace_bytes(B, H, W, C)
+    ws = workspace(nbytes, x.device)
+    with _Span("bn_stats", x.numel() * x.element_size(), "B"):
+        check(lib.asis_chan_stats(0, ptr(x), None, dt(x), B, H, W, C, storage_pad, ptr(shift), None, None, None, None, 0,
+                                  ptr(s), ptr(s[1]), ptr(ws), nbytes, stream()))
+    return s
+
+
+def chan_stats_backward(x, dy, a, b, mean, rstd, relu, storage_pad=0):
+    """-> s [2, C] f32: sum dz, sum dz * xhat  (dz = dy * relu'(a x + b))."""
+    lib = _lib.load()
+    B, Hs, Ws, C = x.shape
+    H, W = Hs - 2 * storage_pad, Ws - 2 * storage_pad
+    x, dy = _c(x), _c(dy)
+    assert dy.dtype == x.dtype and dy.shape == x.shape
+    s = torch.empty(2, C, dtype=torch.float32, device=x.device)
+    nbytes = lib.asis_chan_stats_workspace_bytes(B, H, W, C)
+    ws = workspace(nbytes, x.device)
+    with _Span("bn_bwd_stats", 2 * x.numel() * x.element_size(), "B"):
+        check(lib.asis_chan_stats(1, ptr(x), ptr(dy), dt(x), B, H, W, C, storage_pad, None, ptr(a), ptr(b), ptr(mean),
+                                  ptr(rstd), int(relu), ptr(s), ptr(s[1]), ptr(ws), nbytes, stream()))
+    return s
+
+
+def bn_apply(x, a, b, relu, out_dtype, pad_in=0, pad_out=0):
+    """y = act(a[c] x + b[c]) on a channels-last map (optionally re-padding the storage)."""
+    need_cuda(x, a, b)
+    B, Hs, Ws, C = x.shape
+    H, W = Hs - 2 * pad_in, Ws - 2 * pad_in
+    x = _c(x)
+    y = torch.empty(B, H + 2 * pad_out, W + 2 * pad_out, C, dtype=out_dtype, device=x.device)
+    with _Span("bn_apply", x.numel() * x.element_size() + y.numel() * y.element_size(), "B"):
+        check(_lib.load().asis_bn_apply(0, ptr(x), None, dt(x), ptr(y), dt(y), B, H, W, C, pad_in, pad_out, ptr(a), ptr(b),
+                                        None, None, None, None, int(relu), stream()))
+    return y
+
+
+def bn_apply_backward(x, dy, a, b, mean, rstd, c1, c2, relu, pad=0):
+    """dx = a * (dz - c1 - xhat * c2), same storage as x."""
+    B, Hs, Ws, C = x.shape
+    H, W = Hs - 2 * pad, Ws - 2 * pad
+    x, dy = _c(x), _c(dy)
+    dx = torch.empty_like(x)
+    with _Span("bn_bwd_apply", 3 * x.numel() * x.element_size(), "B"):
+        check(_lib.load().asis_bn_apply(1, ptr(x), ptr(dy), dt(x), ptr(dx), dt(dx), B, H, W, C, pad, pad, ptr(a), ptr(b),
+                                        ptr(mean), ptr(rstd), ptr(c1), ptr(c2), int(relu), stream()))
+    return dx
+
+
+def maxpool3x3s2_forward(x):
+    need_cuda(x)
+    B, H, W, C = x.shape
+    x = _c(x)
+    Ho, Wo = conv_out_size(H, 3, 2, 1), conv_out_size(W, 3, 2, 1)
+    y = torch.empty(B, Ho, Wo, C, dtype=x.dtype, device=x.device)
+    idx = torch.empty(B, Ho, Wo, C, dtype=torch.uint8, device=x.device)
+    check(_lib.load().asis_maxpool3x3s2_forward(ptr(x), ptr(y), ptr(idx), dt(x), B, H, W, C, 0, 0, stream()))
+    return y, idx
+
+
+def maxpool3x3s2_backward(gy, idx, H, W):
+    B, Ho, Wo, C = gy.shape
+    gy = _c(gy)
+    gx = torch.empty(B, H, W, C, dtype=gy.dtype, device=gy.device)
+    check(_lib.load().asis_maxpool3x3s2_backward(ptr(gy), ptr(idx), ptr(gx), dt(gy), B, H, W, C, 0, 0, stream()))
+    return gx
+
+
+def smallconv3x3_forward(x, w, bias):
+    """x [B,H,W,C] channels-last, w [CO,3,3,C] f32 -> y [B,H,W,CO] f32."""
+    need_cuda(x, w)
+    B, H, W, C = x.shape
+    CO = w.shape[0]
+    x = _c(x)
+    y = torch.empty(B, H, W, CO, dtype=torch.float32, device=x.device)
+    with _Span("smallconv_fwd", x.numel() * x.element_size() + y.numel() * 4, "B"):
+        check(_lib.load().asis_smallconv3x3_forward(ptr(x), dt(x), ptr(w), ptr(bias), ptr(y), B, H, W, C, CO, stream()))
+    return y
+
+
+def smallconv3x3_backward(x, w, gy, need_gx, need_gw):
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    CO = w.shape[0]
+    x, gy = _c(x), _c(gy.float())
+    gx = torch.empty_like(x) if need_gx else None
+    gw = torch.empty(CO, 3, 3, C, dtype=torch.float32, device=x.device) if need_gw else None
+    nbytes = lib.asis_smallconv3x3_backward_workspace_bytes(B, H, W, C, CO)
+    ws = workspace(nbytes, x.device)
+    with _Span("smallconv_bwd", 2 * x.numel() * x.element_size() + gy.numel() * 4, "B"):
+        check(lib.asis_smallconv3x3_backward(ptr(x), dt(x), ptr(w), ptr(gy), ptr(gx), ptr(gw), B, H, W, C, CO, ptr(ws), nbytes,
+                                             stream()))
+    return gx, gw

@@ -39,9 +39,6 @@ class TrainStep(nn.Module):
         self.seg_decoder = FeatureDecoder(embed_dim=C, num_classes=num_classes, features=feats)
         self.num_classes = num_classes
         self.to(device)
-        if precision == "bf16":
-            self.seg_decoder.to(memory_format=torch.channels_last)
-            self.encoder.backbone_encoder.to(memory_format=torch.channels_last)
         self.encoder.model.eval()
         if not train_backbone:
             for p in self.encoder.model.parameters():
@@ -62,13 +59,7 @@ class TrainStep(nn.Module):
         with Fn.precision(self.precision):
             res = self.encoder(inp)
             feat = res["feat"]
-            # the decoder is still library code: in bf16 mode let cuDNN run it in
-            # bf16 / channels-last, like the rest of the step
-            lowp = self.precision == "bf16"
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=lowp):
-                x = feat.contiguous(memory_format=torch.channels_last) if lowp else feat.float()
-                out = self.seg_decoder(x)
-            out = out.float()
+            out = self.seg_decoder(feat)          # [B, n_cls, 672, 672] f32 (channels-last memory)
             H, W = target.shape[1], target.shape[2]
             out = F.interpolate(out, size=(H, W), mode="bilinear")
             if internals is not None:

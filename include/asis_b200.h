@@ -215,6 +215,55 @@ int asis_layerscale_backward(const float *d, const void *u, const float *gamma, 
                              float *dgamma, float *dbias, int M, int N, void *workspace,
                              size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Convolutional stages either side of the hot path, channels-last:
+ * the spatial prior module  FeatureEncoder  (backbones/encoders.py:4-74) and  FeatureDecoder
+ * (backbones/decoders.py:92-164).  A map is stored as [B, H + 2*sp, W + 2*sp, C] ("storage padding"
+ * sp >= 0, zeros in the border; sp = 0 is the plain layout).  A convolution is asis_im2col + asis_gemm:
+ * rows = output pixels (b, oy, ox), K = (ky, kx, c) with c fastest, weight viewed as [Cout, ky, kx, Cin];
+ * its input gradient is the transposed GEMM + asis_col2im (a gather over the taps that touch an input
+ * pixel: no atomics), its weight gradient the MN-major GEMM over the same column matrix.
+ * ------------------------------------------------------------------------------------------ */
+int asis_im2col(const void *x, int x_dtype, void *cols, int cols_dtype, int B, int H, int W, int C,
+                int storage_pad, int k, int stride, int pad, int64_t ldk, void *stream);
+int asis_col2im(const void *dcols, void *dx, int dtype, int B, int H, int W, int C, int storage_pad,
+                int k, int stride, int pad, int64_t ldk, void *stream);
+
+/* BatchNorm in training mode (nn.SyncBatchNorm encoders.py:12-40, nn.BatchNorm2d decoders.py:100-125), two
+ * kernels each way.  Statistics: per-channel sums over the logical pixels, fixed-order partials (no atomics):
+ *   mode 0: s1 = sum (x - shift[c]),  s2 = sum (x - shift[c])^2        (shifted: no cancellation)
+ *   mode 1: s1 = sum dz,  s2 = sum dz * xhat,   dz = dy * relu'(a x + b),  xhat = (x - mean) * rstd
+ * s1, s2 are the two halves of ONE [2C] f32 buffer; the cross-rank exchange of SyncBatchNorm acts on it.
+ * Apply:  mode 0: y = act(a[c] x + b[c])   (a = weight * rstd, b = bias - mean * a; y may use another storage
+ *                                             padding; its border is zero-filled)
+ *         mode 1: dx = a[c] * (dz - c1[c] - xhat * c2[c])            (c1 = mean dz, c2 = mean dz * xhat)   */
+size_t asis_chan_stats_workspace_bytes(int B, int H, int W, int C);
+int asis_chan_stats(int mode, const void *x, const void *dy, int dtype, int B, int H, int W, int C,
+                    int storage_pad, const float *shift, const float *a, const float *b,
+                    const float *mean, const float *rstd, int relu, float *s1, float *s2,
+                    void *workspace, size_t workspace_bytes, void *stream);
+int asis_bn_apply(int mode, const void *x, const void *dy, int in_dtype, void *out, int out_dtype,
+                  int B, int H, int W, int C, int pad_in, int pad_out, const float *a, const float *b,
+                  const float *mean, const float *rstd, const float *c1, const float *c2, int relu,
+                  void *stream);
+
+/* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (encoders.py:20): idx [same shape as y] u8 = winning tap
+ * (first maximum in window order, as ATen); the backward is a gather over the <= 4 windows of an input pixel. */
+int asis_maxpool3x3s2_forward(const void *x, void *y, uint8_t *idx, int dtype, int B, int H, int W, int C,
+                              int pad_in, int pad_out, void *stream);
+int asis_maxpool3x3s2_backward(const void *gy, const uint8_t *idx, void *gx, int dtype, int B, int H,
+                               int W, int C, int pad_in, int pad_out, void *stream);
+
+/* 3x3 / stride 1 / pad 1 convolution with 1..4 output channels (final_out, decoders.py:129: its column
+ * matrix would be 12 x 672^2 x 576 elements): direct kernels.  x [B,H,W,C] plain, w [CO,3,3,C] f32,
+ * y / gy [B,H,W,CO] f32; backward: gx (x's dtype, optional), gw [CO,3,3,C] f32 (optional). */
+int asis_smallconv3x3_forward(const void *x, int dtype, const float *w, const float *bias, float *y,
+                              int B, int H, int W, int C, int CO, void *stream);
+size_t asis_smallconv3x3_backward_workspace_bytes(int B, int H, int W, int C, int CO);
+int asis_smallconv3x3_backward(const void *x, int dtype, const float *w, const float *gy, void *gx,
+                               float *gw, int B, int H, int W, int C, int CO, void *workspace,
+                               size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

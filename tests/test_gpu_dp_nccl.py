@@ -49,7 +49,14 @@ def _make(precision, dev):
 def _grads(ts, img, tgt):
     for p in ts.parameters():
         p.grad = None
-    loss = ts.forward_loss(img, tgt)
+    internals = {}
+    loss = ts.forward_loss(img, tgt, internals)
+    # the dice loss of a freshly initialised 2-class head is almost flat (gradients at fp32-noise level), so a second
+    # term drives the encoder graph directly, as in the golden fixtures; it is a per-image mean, like the loss
+    feat = internals["feat"]
+    g = torch.Generator().manual_seed(5)
+    probe = torch.randn(feat.shape[1:], generator=g).to(feat.device)
+    loss = loss + (feat * probe).sum() / (feat.shape[0] * feat[0].numel() ** 0.5)
     loss.backward()
     ts.reducer.finish()
     torch.cuda.synchronize()
@@ -101,13 +108,16 @@ def test_two_gpu_gradients_equal_one_gpu(precision, tol):
     g1, loss1 = _grads(ts, img.to(dev), tgt.to(dev))
     assert abs(loss1 - loss2) < (1e-5 if precision == "fp32" else 2e-3), (loss1, loss2)
     assert set(g1) == set(g2)
-    worst = (0.0, None)
+    worst, errs = (0.0, None), []
     for k in g1:
         scale = float(g1[k].abs().max())
         if scale < 1e-12:
             continue
         e = float((g1[k] - g2[k]).abs().max()) / scale
+        errs.append((e, k))
         worst = max(worst, (e, k))
+    errs.sort(reverse=True)
+    print(f"[dp nccl {precision}] largest: " + "; ".join(f"{k} {e:.1e}" for e, k in errs[:6]) + f"; median {errs[len(errs) // 2][0]:.1e}")
     print(f"[dp nccl {precision}] {len(g1)} gradients, worst 2-GPU vs 1-GPU error {worst[0]:.2e} ({worst[1]})")
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
