@@ -50,16 +50,19 @@ SIGNATURES = {
     "asis_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _L, _P]),
     "asis_upsample2x_bilinear_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "asis_upsample2x_bilinear_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "asis_upsample2x_bilinear_forward_padded": (_I, [_P, _P] + [_I] * 7 + [_P]),
+    "asis_upsample2x_bilinear_backward_padded": (_I, [_P, _P] + [_I] * 7 + [_P]),
     "asis_im2col": (_I, [_P, _I, _P, _I] + [_I] * 8 + [_L, _P]),
     "asis_col2im": (_I, [_P, _P, _I] + [_I] * 8 + [_L, _P]),
+    "asis_conv3x3s1_gemm": (_I, [_I, _P, _P, _P, _I, _P] + [_I] * 5 + [_P]),
     "asis_chan_stats_workspace_bytes": (_Z, [_I] * 4),
-    "asis_chan_stats": (_I, [_I, _P, _P, _I] + [_I] * 5 + [_P] * 5 + [_I, _P, _P, _P, _Z, _P]),
-    "asis_bn_apply": (_I, [_I, _P, _P, _I, _P, _I] + [_I] * 6 + [_P] * 6 + [_I, _P]),
+    "asis_chan_stats": (_I, [_I, _P, _P, _I] + [_I] * 6 + [_P] * 5 + [_I, _P, _P, _P, _Z, _P]),
+    "asis_bn_apply": (_I, [_I, _P, _P, _I, _P, _I] + [_I] * 7 + [_P] * 6 + [_I, _P]),
     "asis_maxpool3x3s2_forward": (_I, [_P, _P, _P, _I] + [_I] * 6 + [_P]),
     "asis_maxpool3x3s2_backward": (_I, [_P, _P, _P, _I] + [_I] * 6 + [_P]),
-    "asis_smallconv3x3_forward": (_I, [_P, _I, _P, _P, _P] + [_I] * 5 + [_P]),
-    "asis_smallconv3x3_backward_workspace_bytes": (_Z, [_I] * 5),
-    "asis_smallconv3x3_backward": (_I, [_P, _I, _P, _P, _P, _P] + [_I] * 5 + [_P, _Z, _P]),
+    "asis_seg_head_workspace_bytes": (_Z, [_I] * 5),
+    "asis_seg_head_forward": (_I, [_P, _I, _P, _P, _P] + [_I] * 5 + [_P, _Z, _P]),
+    "asis_seg_head_backward": (_I, [_P, _I, _P, _P, _P, _P] + [_I] * 5 + [_P, _Z, _P]),
     "asis_dwconv3x3_forward": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P]),
     "asis_dwconv3x3_backward_workspace_bytes": (_Z, [_I, _I, _I]),
     "asis_dwconv3x3_backward": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _Z, _P]),

@@ -5,12 +5,15 @@ without a single transpose:
 
   Conv2dFunction        nn.Conv2d = asis_im2col + asis_gemm (tcgen05 in bf16 mode; FFMA in fp32 parity mode);
                         backward: transposed GEMM + asis_col2im (gather, no atomics), MN-major GEMM for the weights
+  Conv3x3PaddedFunction the 3x3 / stride 1 / pad 1 layers in bf16 mode (two of the stem, four of the decoder): implicit
+                        GEMM over zero-padded maps (asis_conv3x3s1_gemm), forward, input and weight gradient; the
+                        BatchNorm / resize nodes either side read and write the padded storage directly
   BatchNormFunction     nn.BatchNorm2d / nn.SyncBatchNorm in training mode (+ the ReLU that follows): shifted
                         per-channel sums with fixed-order partials, one fused normalise pass, the same two the other way;
                         SyncBatchNorm exchanges ONE small tensor per layer and direction (statistics all_gather forward,
                         sum all_reduce backward), exactly the reference's semantics (global-batch statistics)
   MaxPoolFunction       nn.MaxPool2d(3, 2, 1) with ATen's tie rule (first maximum in window order)
-  SmallConvFunction     the 64 -> n_classes 3x3 head: direct kernels (its column matrix would be 3.7 G elements)
+  SegHeadFunction       the last x2 resize + the 64 -> n_classes 3x3 head, fused: contraction at low resolution
 """
 import weakref
 
@@ -84,7 +87,88 @@ class Conv2dFunction(Function):
 
 
 def conv2d(x, weight, bias, stride, pad, out_dtype=None, mode=None):
-    return Conv2dFunction.apply(x, weight, bias, stride, pad, mode or Fn.get_precision(), out_dtype)
+    mode = mode or Fn.get_precision()
+    # the bf16 kernels move 8-channel (16-byte) vectors and TMA needs 16-byte row pitches: layers whose channel
+    # counts are not multiples of 8 (toy configurations only; the real ones are multiples of 64) run in fp32
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    if mode == "bf16" and (Cout % 8 or (Cin % 8 and x.requires_grad)):
+        mode = "fp32"
+    return Conv2dFunction.apply(x, weight, bias, stride, pad, mode, out_dtype)
+
+
+def implicit_ok(conv, mode=None):
+    """can this nn.Conv2d run as the implicit GEMM (asis_conv3x3s1_gemm: 3x3 / stride 1 / pad 1, channels in 64s, bf16)?"""
+    mode = mode or Fn.get_precision()
+    return (mode == "bf16" and tuple(conv.kernel_size) == (3, 3) and tuple(conv.stride) == (1, 1) and tuple(conv.padding) == (1, 1)
+            and conv.groups == 1 and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0)
+
+
+class Conv3x3PaddedFunction(Function):
+    """3x3 / stride 1 / pad 1 convolution over a ZERO-PADDED channels-last bf16 map, as an implicit GEMM on the tcgen05
+    kernel (tap (ky, kx) of the K loop shifts the TMA row coordinate: no column matrix in memory).
+    xp [B, H+2, W+2, Cin] (zero border) -> yp [B, H+2, W+2, Cout] whose border rows are NOT meaningful: the consumer
+    (BatchNormFunction with pad_in=1) reads the logical pixels only.  Backward contract: the incoming gradient is in the
+    same padded storage with a ZERO border (BatchNormFunction writes it so); the returned dxp has a meaningless border."""
+
+    @staticmethod
+    def forward(ctx, xp, weight, bias, out_dtype):
+        B, Hp, Wp, Cin = xp.shape
+        Cout = weight.shape[0]
+        assert xp.dtype == torch.bfloat16 and xp.is_contiguous()
+        w2 = _conv_weight(weight, torch.bfloat16, 9 * Cin)
+        yp = torch.empty(B, Hp, Wp, Cout, dtype=out_dtype or torch.bfloat16, device=xp.device)
+        K.conv3x3s1_gemm(0, xp, w2, yp, Fn._f32(bias), B, Hp - 2, Wp - 2, Cin, Cout)
+        ctx.save_for_backward(xp, weight)
+        ctx.has_bias = bias is not None
+        return yp
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dyp):
+        xp, weight = ctx.saved_tensors
+        B, Hp, Wp, Cin = xp.shape
+        Cout = weight.shape[0]
+        dyp = K.cast(dyp.contiguous(), torch.bfloat16)
+        dxp = dw = db = None
+        if ctx.needs_input_grad[0]:
+            w2 = _conv_weight(weight, torch.bfloat16, 9 * Cin)
+            dxp = torch.empty_like(xp)
+            K.conv3x3s1_gemm(1, dyp, w2, dxp, None, B, Hp - 2, Wp - 2, Cin, Cout)
+        if ctx.needs_input_grad[1]:
+            dw2 = torch.empty(Cout, 9 * Cin, dtype=torch.float32, device=xp.device)
+            K.conv3x3s1_gemm(2, dyp, xp, dw2, None, B, Hp - 2, Wp - 2, Cin, Cout)
+            dw = dw2.view(Cout, 3, 3, Cin).permute(0, 3, 1, 2).to(weight.dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = K.colsum(dyp.view(-1, Cout))              # the border is zero: all rows may be summed
+        return dxp, dw, db, None
+
+
+def conv3x3_padded(xp, weight, bias, out_dtype=None):
+    return Conv3x3PaddedFunction.apply(xp, weight, bias, out_dtype)
+
+
+class RepadFunction(Function):
+    """change the storage padding (and dtype) of a channels-last map: [B, H+2pi, W+2pi, C] -> [B, H+2po, W+2po, C] with a
+    zero border (asis_bn_apply with a = 1, b = 0)."""
+
+    @staticmethod
+    def forward(ctx, x, pad_in, pad_out, dtype):
+        C = x.shape[-1]
+        one, zero = torch.ones(C, device=x.device), torch.zeros(C, device=x.device)
+        ctx.meta = (pad_in, pad_out, x.dtype)
+        ctx.save_for_backward(one, zero)
+        return K.bn_apply(x, one, zero, zero, False, dtype or x.dtype, pad_in, pad_out)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        one, zero = ctx.saved_tensors
+        pad_in, pad_out, xdt = ctx.meta
+        return K.cast(K.bn_apply(dy.contiguous(), one, zero, zero, False, dy.dtype, pad_out, pad_in), xdt), None, None, None
+
+
+def repad(x, pad_in, pad_out, dtype=None):
+    return RepadFunction.apply(x, pad_in, pad_out, dtype)
 
 
 def _sync_world(bn):
@@ -100,15 +184,16 @@ class BatchNormFunction(Function):
     Training mode: statistics of the (global, for SyncBatchNorm) batch; eval mode: the running statistics."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, bn, relu, out_dtype):
-        B, H, W, C = x.shape
+    def forward(ctx, x, weight, bias, bn, relu, out_dtype, pad_in=0, pad_out=0):
+        B, Hs, Ws, C = x.shape
+        H, W = Hs - 2 * pad_in, Ws - 2 * pad_in
         n_local = B * H * W
         world, group = _sync_world(bn)
         training = bn.training or bn.running_mean is None
         w32, b32 = Fn._f32(weight), Fn._f32(bias)
         if training:
-            shift = x[0, 0, 0].float().contiguous()                 # any value near the data: kills the cancellation
-            s = K.chan_stats(x, shift)
+            shift = x[0, pad_in, pad_in].float().contiguous()       # any value near the data: kills the cancellation
+            s = K.chan_stats(x, shift, pad_in)
             mean = shift + s[0] / n_local
             m2 = s[1] - s[0] * s[0] / n_local                       # sum of squared deviations from the local mean
             n_tot = n_local
@@ -135,19 +220,19 @@ class BatchNormFunction(Function):
             mean, var, n_tot = bn.running_mean.float(), bn.running_var.float(), n_local
         rstd = torch.rsqrt(var + bn.eps)
         a = (w32 * rstd).contiguous()
-        b = (b32 - mean * a).contiguous()
-        y = K.bn_apply(x, a, b, relu, out_dtype or x.dtype)
-        ctx.save_for_backward(x, a, b, mean.contiguous(), rstd.contiguous())
-        ctx.meta = (relu, training, world, group, n_tot)
+        b, mean = b32.contiguous(), mean.contiguous()           # y = a (x - mean) + b: the centred form (csrc/conv.cu)
+        y = K.bn_apply(x, a, b, mean, relu, out_dtype or x.dtype, pad_in, pad_out)
+        ctx.save_for_backward(x, a, b, mean, rstd.contiguous())
+        ctx.meta = (relu, training, world, group, n_tot, pad_in, pad_out)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         x, a, b, mean, rstd = ctx.saved_tensors
-        relu, training, world, group, n_tot = ctx.meta
+        relu, training, world, group, n_tot, pad_in, pad_out = ctx.meta
         dy = dy if dy.dtype == x.dtype else dy.to(x.dtype)
-        s = K.chan_stats_backward(x, dy, a, b, mean, rstd, relu)
+        s = K.chan_stats_backward(x, dy, a, b, mean, rstd, relu, pad_in, pad_out)
         dweight, dbias = s[1].clone(), s[0].clone()       # local sums: the gradient all-reduce averages them (as DDP does)
         dx = None
         if ctx.needs_input_grad[0]:
@@ -157,13 +242,24 @@ class BatchNormFunction(Function):
                 c1, c2 = (s[0] / n_tot).contiguous(), (s[1] / n_tot).contiguous()
             else:
                 c1 = c2 = torch.zeros_like(mean)
-            dx = K.bn_apply_backward(x, dy, a, b, mean, rstd, c1, c2, relu)
-        return dx, dweight, dbias, None, None, None
+            dx = K.bn_apply_backward(x, dy, a, b, mean, rstd, c1, c2, relu, pad_in, pad_out)
+        return dx, dweight, dbias, None, None, None, None, None
 
 
-def batch_norm(x, bn, relu=True, out_dtype=None):
-    """`bn`: the nn.BatchNorm2d / nn.SyncBatchNorm module that holds parameters and running statistics."""
-    return BatchNormFunction.apply(x, bn.weight, bn.bias, bn, relu, out_dtype)
+def batch_norm(x, bn, relu=True, out_dtype=None, pad_in=0, pad_out=0):
+    """`bn`: the nn.BatchNorm2d / nn.SyncBatchNorm module that holds parameters and running statistics.
+    x is stored with `pad_in` border pixels (not part of the statistics), the result with `pad_out` (zero) border pixels;
+    the gradient comes back in the latter storage and leaves in the former (zero border)."""
+    return BatchNormFunction.apply(x, bn.weight, bn.bias, bn, relu, out_dtype, pad_in, pad_out)
+
+
+def conv_bn_relu(x, conv, bn, x_pad=0, out_pad=0):
+    """relu(bn(conv(x))) on channels-last maps; x_pad = 1: x is zero-padded storage and `conv` runs as the implicit GEMM."""
+    if x_pad:
+        y = conv3x3_padded(x, conv.weight, conv.bias)
+    else:
+        y = conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])
+    return batch_norm(y, bn, relu=True, pad_in=x_pad, pad_out=out_pad)
 
 
 class MaxPoolFunction(Function):
@@ -185,28 +281,30 @@ def maxpool3x3s2(x):
     return MaxPoolFunction.apply(x)
 
 
-class SmallConvFunction(Function):
-    """3x3 / stride 1 / pad 1 convolution to a handful of channels: x [B,H,W,C] -> [B,H,W,CO] f32."""
+class SegHeadFunction(Function):
+    """nn.Upsample(x2, bilinear, align_corners=True) -> 3x3 / pad 1 convolution to <= 4 classes, fused
+    (decoders.py:125-129): z [B,H,W,C] channels-last -> logits [B,2H,2W,CO] f32.  The channel contraction runs at the
+    low resolution (csrc/conv.cu: the upsampled C-channel map is never materialised)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        w = weight.detach().permute(0, 2, 3, 1).contiguous().float()          # [CO, 3, 3, C]
-        y = K.smallconv3x3_forward(x, w, Fn._f32(bias))
-        ctx.save_for_backward(x, w)
-        ctx.wshape = (weight.shape, weight.dtype, bias is not None)
+    def forward(ctx, z, weight, bias):
+        CO, C = weight.shape[0], weight.shape[1]
+        w2 = weight.detach().float().permute(2, 3, 0, 1).reshape(9 * CO, C).contiguous()     # row (ky*3 + kx)*CO + co
+        y = K.seg_head_forward(z, w2, Fn._f32(bias), CO)
+        ctx.save_for_backward(z, w2)
+        ctx.meta = (CO, C, weight.dtype, bias is not None)
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        x, w = ctx.saved_tensors
-        wshape, wdt, has_bias = ctx.wshape
-        gx, gw = K.smallconv3x3_backward(x, w, gy, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
-        if gw is not None:
-            gw = gw.permute(0, 3, 1, 2).to(wdt)
-        gb = gy.reshape(-1, gy.shape[-1]).float().sum(0) if (has_bias and ctx.needs_input_grad[2]) else None     # [CO] <= 4
-        return gx, gw, gb
+        z, w2 = ctx.saved_tensors
+        CO, C, wdt, has_bias = ctx.meta
+        gz, gw2 = K.seg_head_backward(z, w2, gy, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        gw = gw2.view(3, 3, CO, C).permute(2, 3, 0, 1).to(wdt) if gw2 is not None else None
+        gb = gy.reshape(-1, CO).float().sum(0) if (has_bias and ctx.needs_input_grad[2]) else None        # [CO] <= 4
+        return gz, gw, gb
 
 
-def smallconv3x3(x, weight, bias):
-    return SmallConvFunction.apply(x, weight, bias)
+def seg_head(z, weight, bias):
+    return SegHeadFunction.apply(z, weight, bias)

@@ -14,6 +14,8 @@ char *err_buf() {
 // tcgen05 paths (gemm_tc.cu / attention_tc.cu)
 int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b_major, int64_t ldb, int M, int N,
                    int K, const EpiArgs &epi, cudaStream_t st);
+int gemm_tc_conv3x3(int op, const void *a, const void *b, void *c, int c_dtype, const float *bias, int B, int H, int W, int Cin,
+                    int Cout, cudaStream_t st);
 int attention_tc_forward(const void *qkv, void *out, float *lse, int B, int T, int H, int hd, cudaStream_t st);
 size_t attention_tc_bwd_ws(int B, int T, int H, int hd);
 int attention_tc_backward(const void *qkv, const void *out, const float *lse, const void *dout, void *dqkv, int B,
@@ -61,6 +63,13 @@ extern "C" int asis_gemm(int compute, const void *A, int a_major, int64_t lda, c
     return gemm_f32_launch(g, st);
   }
   return gemm_tc_launch(A, a_major, lda, B, b_major, ldb, M, N, K, e, st);
+}
+
+extern "C" int asis_conv3x3s1_gemm(int op, const void *a, const void *b, void *c, int c_dtype, const float *bias, int B, int H,
+                                   int W, int Cin, int Cout, void *stream) {
+  ASIS_REQUIRE(a && b && c, "conv3x3s1_gemm: null pointer");
+  ASIS_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && dtype_ok(c_dtype), "conv3x3s1_gemm: bad arguments");
+  return gemm_tc_conv3x3(op, a, b, c, c_dtype, bias, B, H, W, Cin, Cout, (cudaStream_t)stream);
 }
 
 extern "C" size_t asis_attention_forward_workspace_bytes(int compute, int B, int T, int H, int hd) {

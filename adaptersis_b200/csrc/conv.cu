@@ -154,9 +154,9 @@ __global__ void __launch_bounds__(256) col2im_kernel(const T *__restrict__ dcols
 // ---- per-channel statistics -------------------------------------------------------------------------
 // block (by) owns a strip of pixels; thread (tx) owns one channel vector and strides over the strip's pixels with
 // ty: partial[(by*TY + ty), 0:C] = sum (x - shift), partial[.., C:2C] = sum (x - shift)^2 over the logical pixels.
-// mode 1 (backward): sums of dz and dz * xhat with dz = dy * relu'(a x + b), xhat = (x - mean) * rstd.
+// mode 1 (backward): sums of dz and dz * xhat with dz = dy * relu'(a (x - mean) + b), xhat = (x - mean) * rstd.
 struct StatArgs {
-  int B, H, W, C, sp;
+  int B, H, W, C, sp, sp_dy;              // storage padding of x and of dy
   const float *shift;                     // mode 0
   const float *a, *b, *mean, *rstd;       // mode 1 (a, b: the forward's per-channel scale / offset)
   int relu;
@@ -201,10 +201,10 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const T *__restrict__ x
         }
       } else {
         float g[N];
-        CVec<T>::load(dy + off, g);
+        CVec<T>::load(dy + ((b * (s.H + 2 * s.sp_dy) + iy + s.sp_dy) * (s.W + 2 * s.sp_dy) + ix + s.sp_dy) * s.C + (size_t)cv * N, g);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          const float dz = (s.relu && fmaf(k0[i], v[i], k1[i]) <= 0.f) ? 0.f : g[i];
+          const float dz = (s.relu && fmaf(k0[i], v[i] - k2[i], k1[i]) <= 0.f) ? 0.f : g[i];
           s1[i] += dz;
           s2[i] = fmaf(dz, (v[i] - k2[i]) * k3[i], s2[i]);
         }
@@ -239,11 +239,12 @@ __global__ void __launch_bounds__(256) conv_reduce_partials_kernel(const float *
 }
 
 // ---- BatchNorm apply (+ReLU) and its gradient --------------------------------------------------------
-// forward:  y = act(a[c] * x + b[c])        (a = weight * rstd, b = bias - mean * a); y may have another storage
-//           padding than x; its border is written with zeros
-// backward: dx = a[c] * (dz - c1[c] - xhat * c2[c]),  dz = dy * relu'(a x + b),  c1 = mean(dz), c2 = mean(dz * xhat)
+// forward:  y = act(a[c] * (x - mean[c]) + b[c])        (a = weight * rstd, b = bias: the centred form -- a x + (b - mean a)
+//           cancels when |mean| >> std and moves the sign of near-zero pre-activations, i.e. the ReLU mask); y may have
+//           another storage padding than x; its border is written with zeros
+// backward: dx = a[c] * (dz - c1[c] - xhat * c2[c]),  dz = dy * relu'(a (x - mean) + b),  c1 = mean(dz), c2 = mean(dz * xhat)
 struct ApplyArgs {
-  int B, H, W, C, sp_in, sp_out;
+  int B, H, W, C, sp_in, sp_out, sp_dy;   // storage padding of x, of the output (y or dx) and of dy
   const float *a, *b, *mean, *rstd, *c1, *c2;
   int relu;
 };
@@ -278,22 +279,23 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const TI *__restrict__ x,
       if (MODE == 0) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          const float y = fmaf(s.a[cv * N + i], v[i], s.b[cv * N + i]);
+          const float y = fmaf(s.a[cv * N + i], v[i] - s.mean[cv * N + i], s.b[cv * N + i]);
           o[i] = s.relu ? fmaxf(y, 0.f) : y;
         }
       } else {
+        const size_t offd = ((b * (s.H + 2 * s.sp_dy) + iy + s.sp_dy) * (s.W + 2 * s.sp_dy) + ix + s.sp_dy) * s.C + (size_t)cv * N;
         float g[N];
         if (sizeof(TI) == sizeof(TO)) {
-          CVec<TO>::load(reinterpret_cast<const TO *>(dy + off), g);
+          CVec<TO>::load(reinterpret_cast<const TO *>(dy + offd), g);
         } else {
 #pragma unroll
-          for (int i = 0; i < N; ++i) g[i] = to_f(dy[off + i]);
+          for (int i = 0; i < N; ++i) g[i] = to_f(dy[offd + i]);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const int c = cv * N + i;
           const float a = s.a[c];
-          const float dz = (s.relu && fmaf(a, v[i], s.b[c]) <= 0.f) ? 0.f : g[i];
+          const float dz = (s.relu && fmaf(a, v[i] - s.mean[c], s.b[c]) <= 0.f) ? 0.f : g[i];
           const float xhat = (v[i] - s.mean[c]) * s.rstd[c];
           o[i] = a * (dz - s.c1[c] - xhat * s.c2[c]);
         }
@@ -387,157 +389,215 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const T *__restrict__ 
   }
 }
 
-// ---- 3x3 / stride-1 / pad-1 convolution with a handful of output channels (decoders.py:129: 64 -> n_classes) ------
-// The column matrix of this layer would be 12 x 672^2 x 576 elements; with <= 4 outputs a direct kernel is the natural
-// form: a warp owns one output pixel, its lanes split the channel vectors, the 9 x CO weights of a lane's channels stay
-// in registers, a shuffle tree finishes the dot products.  x: [B, H, W, C] plain; y: [B, H, W, CO] (f32).
-template <typename T, int CO>
-__global__ void __launch_bounds__(256) smallconv_fwd_kernel(const T *__restrict__ x, const float *__restrict__ w /*[CO,3,3,C]*/,
-                                                            const float *__restrict__ bias, float *__restrict__ y, int B, int H, int W, int C) {
+// ---- segmentation head: nn.Upsample(x2, bilinear, align_corners=True) -> 3x3 conv to n_classes <= 4 -----------------
+// (decoders.py:125-129 -- the last resize of decoder_4 followed by final_out.)  Both are linear and the resize acts
+// per channel, so  conv(up(z)) = sum_tap shift_tap( up( z . w_tap ) ):  the 64 -> n_classes contraction is done FIRST, at
+// the LOW resolution (U[pixel, tap, class], 18 numbers per pixel for 2 classes), and the high-resolution pass only
+// interpolates and adds 9 shifted taps.  The 12 x 672 x 672 x 64 upsampled activation (694 MB in bf16) and its gradient
+// are never materialised; the contraction runs on a quarter of the pixels.
+struct HeadSrc {
+  int i0, i1;
+  float l;
+};
+__device__ __forceinline__ HeadSrc head_src(int o, float scale, int in) {
+  const float sf = scale * (float)o;
+  HeadSrc r;
+  r.i0 = min((int)sf, in - 1);
+  r.i1 = r.i0 + (r.i0 < in - 1 ? 1 : 0);
+  r.l = sf - (float)r.i0;
+  return r;
+}
+__device__ __forceinline__ float head_weight(int o, int i, float scale, int in) {
+  const HeadSrc sr = head_src(o, scale, in);
+  return (sr.i0 == i ? 1.f - sr.l : 0.f) + (sr.i1 == i ? sr.l : 0.f);
+}
+
+// U[p, t] = sum_c z[p, c] * w2[t, c];  one thread per low-resolution pixel, weights broadcast from shared memory
+template <typename T, int NT>
+__global__ void __launch_bounds__(128) head_project_fwd_kernel(const T *__restrict__ z, const float *__restrict__ w2, float *__restrict__ U,
+                                                               size_t R, int C) {
   constexpr int N = CVec<T>::N;
-  const int lane = threadIdx.x & 31;
-  const int CV = C / N;                 // <= 32 handled (C <= 128 f32 / 256 bf16)
-  const size_t npix = (size_t)B * H * W;
-  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  float wr[CO][9][N];
-  if (lane < CV) {
+  extern __shared__ float sw[];          // [NT][C]
+  for (int i = threadIdx.x; i < NT * C; i += blockDim.x) sw[i] = w2[i];
+  __syncthreads();
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < R; p += (size_t)gridDim.x * blockDim.x) {
+    float acc[NT];
 #pragma unroll
-    for (int co = 0; co < CO; ++co)
+    for (int t = 0; t < NT; ++t) acc[t] = 0.f;
+    for (int c = 0; c < C; c += N) {
+      float v[N];
+      CVec<T>::load(z + p * C + c, v);
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap)
+      for (int t = 0; t < NT; ++t)
 #pragma unroll
-        for (int i = 0; i < N; ++i) wr[co][tap][i] = w[((size_t)co * 9 + tap) * C + lane * N + i];
+        for (int i = 0; i < N; ++i) acc[t] = fmaf(v[i], sw[t * C + c + i], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) U[p * NT + t] = acc[t];
   }
-  for (size_t p = warp0; p < npix; p += nwarps) {
-    const int ix = (int)(p % W);
-    const size_t q = p / W;
-    const int iy = (int)(q % H);
-    const size_t b = q / H;
+}
+
+// y[b, oy, ox, co] = bias[co] + sum_tap up(U[.., tap, co])(oy - 1 + ky, ox - 1 + kx)   (zero outside the 2H x 2W map)
+template <int CO>
+__global__ void __launch_bounds__(256) head_gather_fwd_kernel(const float *__restrict__ U, const float *__restrict__ bias, float *__restrict__ y,
+                                                              int B, int H, int W, float sy, float sx) {
+  constexpr int NT = 9 * CO;
+  const int OH = 2 * H, OW = 2 * W;
+  const size_t total = (size_t)B * OH * OW;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(t % OW);
+    const size_t q = t / OW;
+    const int oy = (int)(q % OH);
+    const size_t b = q / OH;
     float acc[CO];
 #pragma unroll
-    for (int co = 0; co < CO; ++co) acc[co] = 0.f;
-    if (lane < CV) {
+    for (int co = 0; co < CO; ++co) acc[co] = bias ? bias[co] : 0.f;
+    const float *Ub = U + b * H * W * NT;
 #pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int yy = iy - 1 + tap / 3, xx = ix - 1 + tap % 3;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        float v[N];
-        CVec<T>::load(x + ((b * H + yy) * W + xx) * C + (size_t)lane * N, v);
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = oy - 1 + ky;
+      if (yy < 0 || yy >= OH) continue;
+      const HeadSrc ys = head_src(yy, sy, H);
 #pragma unroll
-        for (int co = 0; co < CO; ++co)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = ox - 1 + kx;
+        if (xx < 0 || xx >= OW) continue;
+        const HeadSrc xs = head_src(xx, sx, W);
+        const int tap = ky * 3 + kx;
+        const float w00 = (1.f - ys.l) * (1.f - xs.l), w01 = (1.f - ys.l) * xs.l, w10 = ys.l * (1.f - xs.l), w11 = ys.l * xs.l;
+        const float *u00 = Ub + ((size_t)ys.i0 * W + xs.i0) * NT + tap * CO, *u01 = Ub + ((size_t)ys.i0 * W + xs.i1) * NT + tap * CO;
+        const float *u10 = Ub + ((size_t)ys.i1 * W + xs.i0) * NT + tap * CO, *u11 = Ub + ((size_t)ys.i1 * W + xs.i1) * NT + tap * CO;
 #pragma unroll
-          for (int i = 0; i < N; ++i) acc[co] = fmaf(v[i], wr[co][tap][i], acc[co]);
+        for (int co = 0; co < CO; ++co) acc[co] += w00 * u00[co] + w01 * u01[co] + w10 * u10[co] + w11 * u11[co];
       }
     }
 #pragma unroll
-    for (int co = 0; co < CO; ++co) acc[co] = warp_sum(acc[co]);
-    if (lane == 0) {
-#pragma unroll
-      for (int co = 0; co < CO; ++co) y[p * CO + co] = acc[co] + (bias ? bias[co] : 0.f);
-    }
+    for (int co = 0; co < CO; ++co) y[t * CO + co] = acc[co];
   }
 }
 
-// input gradient: dx[b, y, x, c] = sum_{tap, co} dy[b, y - dy(tap), x - dx(tap), co] * w[co, tap, c]
-template <typename T, int CO>
-__global__ void __launch_bounds__(256) smallconv_dgrad_kernel(const float *__restrict__ gy, const float *__restrict__ w, T *__restrict__ gx,
-                                                              int B, int H, int W, int C) {
-  constexpr int N = CVec<T>::N;
-  const int lane = threadIdx.x & 31;
-  const int CV = C / N;
-  const size_t npix = (size_t)B * H * W;
-  const size_t warp0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
-  float wr[CO][9][N];
-  if (lane < CV) {
-#pragma unroll
-    for (int co = 0; co < CO; ++co)
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-        for (int i = 0; i < N; ++i) wr[co][tap][i] = w[((size_t)co * 9 + tap) * C + lane * N + i];
-  }
-  for (size_t p = warp0; p < npix; p += nwarps) {
-    const int ix = (int)(p % W);
-    const size_t q = p / W;
+// dU[b, iy, ix, tap, co] = sum over the upsampled positions (uy, ux) that read (iy, ix) of
+//                          wy(uy) * wx(ux) * gy[b, uy + 1 - ky, ux + 1 - kx, co]        (gather, no atomics)
+// One thread per low-resolution pixel, all nine taps at once, separably: the upsampled rows / columns that read source
+// index i lie in [2i - 2, 2i + 3]; for every logit row oy of the 8-row window the three column sums
+// tx[kx] = sum_ox wx(ox - 1 + kx) g[oy, ox] are formed once and added to the three taps ky with weight wy(oy - 1 + ky).
+// (The first version looped over an 8 x 8 window per (pixel, tap) and re-derived the interpolation weights inside:
+// 5.4 ms; this one is ~0.2 ms.)
+template <int CO>
+__global__ void __launch_bounds__(128) head_gather_bwd_kernel(const float *__restrict__ gy, float *__restrict__ dU, int B, int H, int W,
+                                                              float sy, float sx) {
+  constexpr int NT = 9 * CO;
+  const int OH = 2 * H, OW = 2 * W;
+  const size_t total = (size_t)B * H * W;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int ix = (int)(t % W);
+    const size_t q = t / W;
     const int iy = (int)(q % H);
     const size_t b = q / H;
-    float acc[N];
+    // interpolation weights of the upsampled rows u = 2i - 4 + j, j = 0..9 (zero outside the map / when i is not read)
+    float wyw[10], wxw[10];
 #pragma unroll
-    for (int i = 0; i < N; ++i) acc[i] = 0.f;
+    for (int j = 0; j < 10; ++j) {
+      const int uy = 2 * iy - 4 + j, ux = 2 * ix - 4 + j;
+      wyw[j] = (uy >= 0 && uy < OH) ? head_weight(uy, iy, sy, H) : 0.f;
+      wxw[j] = (ux >= 0 && ux < OW) ? head_weight(ux, ix, sx, W) : 0.f;
+    }
+    float acc[9][CO];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      // output pixel (oy, ox) read input (oy - 1 + ky, ox - 1 + kx): this input pixel is its tap (ky, kx) when oy = iy + 1 - ky
-      const int oy = iy + 1 - tap / 3, ox = ix + 1 - tap % 3;
-      if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
-      const float *g = gy + ((b * H + oy) * W + ox) * CO;
+    for (int k = 0; k < 9; ++k)
 #pragma unroll
-      for (int co = 0; co < CO; ++co) {
-        const float d = g[co];
-        if (lane < CV) {
+      for (int co = 0; co < CO; ++co) acc[k][co] = 0.f;
 #pragma unroll
-          for (int i = 0; i < N; ++i) acc[i] = fmaf(d, wr[co][tap][i], acc[i]);
+    for (int r = 0; r < 8; ++r) {                  // logit row oy = 2 iy - 3 + r; its tap ky reads upsampled row oy - 1 + ky
+      const int oy = 2 * iy - 3 + r;
+      if (oy < 0 || oy >= OH) continue;
+      float tx[3][CO];
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) tx[kx][co] = 0.f;
+      const float *grow = gy + ((b * OH + oy) * OW) * CO;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {                // logit column ox = 2 ix - 3 + c; tap kx reads upsampled column ox - 1 + kx
+        const int ox = 2 * ix - 3 + c;
+        if (ox < 0 || ox >= OW) continue;
+        float g[CO];
+#pragma unroll
+        for (int co = 0; co < CO; ++co) g[co] = grow[(size_t)ox * CO + co];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float w = wxw[c + kx];             // u = ox - 1 + kx = 2 ix - 4 + (c + kx)
+#pragma unroll
+          for (int co = 0; co < CO; ++co) tx[kx][co] = fmaf(w, g[co], tx[kx][co]);
         }
       }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const float w = wyw[r + ky];               // u = oy - 1 + ky = 2 iy - 4 + (r + ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int co = 0; co < CO; ++co) acc[ky * 3 + kx][co] = fmaf(w, tx[kx][co], acc[ky * 3 + kx][co]);
+      }
     }
-    if (lane < CV) CVec<T>::store(gx + p * C + (size_t)lane * N, acc);
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int co = 0; co < CO; ++co) dU[t * NT + k * CO + co] = acc[k][co];
   }
 }
 
-// weight gradient partials: block strip of pixels -> partial[block, CO*9*C]; lanes own channel vectors as above, the
-// 8 warps of a block are combined through shared memory, blocks by conv_reduce_partials_kernel
-template <typename T, int CO>
-__global__ void __launch_bounds__(256) smallconv_wgrad_kernel(const T *__restrict__ x, const float *__restrict__ gy, float *__restrict__ partial,
-                                                              int B, int H, int W, int C, int pix_per_block) {
+// dz[p, c] = sum_t dU[p, t] * w2[t, c]
+template <typename T, int NT>
+__global__ void __launch_bounds__(128) head_project_dgrad_kernel(const float *__restrict__ dU, const float *__restrict__ w2, T *__restrict__ dz,
+                                                                 size_t R, int C) {
   constexpr int N = CVec<T>::N;
-  extern __shared__ float sh[];          // [8 warps][CO*9*C]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int CV = C / N;
-  const size_t npix = (size_t)B * H * W;
-  const size_t p0 = (size_t)blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
-  float acc[CO][9][N];
+  extern __shared__ float sw[];          // [NT][C]
+  for (int i = threadIdx.x; i < NT * C; i += blockDim.x) sw[i] = w2[i];
+  __syncthreads();
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < R; p += (size_t)gridDim.x * blockDim.x) {
+    float d[NT];
 #pragma unroll
-  for (int co = 0; co < CO; ++co)
+    for (int t = 0; t < NT; ++t) d[t] = dU[p * NT + t];
+    for (int c = 0; c < C; c += N) {
+      float o[N];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap)
+      for (int i = 0; i < N; ++i) o[i] = 0.f;
 #pragma unroll
-      for (int i = 0; i < N; ++i) acc[co][tap][i] = 0.f;
-  for (size_t p = p0 + warp; p < p1; p += 8) {
-    const int ix = (int)(p % W);
-    const size_t q = p / W;
-    const int iy = (int)(q % H);
-    const size_t b = q / H;
-    float d[CO];
+      for (int t = 0; t < NT; ++t)
 #pragma unroll
-    for (int co = 0; co < CO; ++co) d[co] = gy[p * CO + co];
-    if (lane < CV) {
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int yy = iy - 1 + tap / 3, xx = ix - 1 + tap % 3;
-        if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-        float v[N];
-        CVec<T>::load(x + ((b * H + yy) * W + xx) * C + (size_t)lane * N, v);
-#pragma unroll
-        for (int co = 0; co < CO; ++co)
-#pragma unroll
-          for (int i = 0; i < N; ++i) acc[co][tap][i] = fmaf(d[co], v[i], acc[co][tap][i]);
-      }
+        for (int i = 0; i < N; ++i) o[i] = fmaf(d[t], sw[t * C + c + i], o[i]);
+      CVec<T>::store(dz + p * C + c, o);
     }
   }
-  const int per = CO * 9 * C;
-  if (lane < CV) {
+}
+
+// dw2[t, c] = sum_p dU[p, t] * z[p, c]: a block owns a strip of pixels, a thread up to HEAD_WG outputs (t, c) with
+// c fastest across the threads (coalesced z reads); partial[block, NT*C], then conv_reduce_partials_kernel
+constexpr int HEAD_WG = 20;
+template <typename T>
+__global__ void __launch_bounds__(256) head_project_wgrad_kernel(const float *__restrict__ dU, const T *__restrict__ z, float *__restrict__ partial,
+                                                                 size_t R, int C, int NT, int pix_per_block) {
+  const int nout = NT * C;
+  float acc[HEAD_WG];
+  int oc[HEAD_WG], ot[HEAD_WG];
 #pragma unroll
-    for (int co = 0; co < CO; ++co)
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-        for (int i = 0; i < N; ++i) sh[(size_t)warp * per + (co * 9 + tap) * C + lane * N + i] = acc[co][tap][i];
+  for (int j = 0; j < HEAD_WG; ++j) {
+    const int o = threadIdx.x + j * 256;
+    acc[j] = 0.f;
+    oc[j] = o < nout ? o % C : 0;
+    ot[j] = o < nout ? o / C : -1;
   }
-  __syncthreads();
-  for (int e = threadIdx.x; e < per; e += blockDim.x) {
-    float t = 0.f;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block, p1 = min(R, p0 + pix_per_block);
+  for (size_t p = p0; p < p1; ++p) {
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) t += sh[(size_t)wv * per + e];
-    partial[(size_t)blockIdx.x * per + e] = t;
+    for (int j = 0; j < HEAD_WG; ++j)
+      if (ot[j] >= 0) acc[j] = fmaf(dU[p * NT + ot[j]], to_f(z[p * C + oc[j]]), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < HEAD_WG; ++j) {
+    const int o = threadIdx.x + j * 256;
+    if (o < nout) partial[(size_t)blockIdx.x * nout + o] = acc[j];
   }
 }
 
@@ -609,7 +669,7 @@ extern "C" size_t asis_chan_stats_workspace_bytes(int B, int H, int W, int C) {
 
 // mode 0: s1 = sum (x - shift), s2 = sum (x - shift)^2.   mode 1: s1 = sum dz, s2 = sum dz * xhat (see StatArgs).
 extern "C" int asis_chan_stats(int mode, const void *x, const void *dy, int dtype, int B, int H, int W, int C, int storage_pad,
-                               const float *shift, const float *a, const float *b, const float *mean, const float *rstd, int relu,
+                               int dy_pad, const float *shift, const float *a, const float *b, const float *mean, const float *rstd, int relu,
                                float *s1, float *s2, void *workspace, size_t workspace_bytes, void *stream) {
   ASIS_REQUIRE(x && s1 && s2 && workspace, "chan_stats: null pointer");
   ASIS_REQUIRE(dtype_ok(dtype), "chan_stats: bad dtype");
@@ -621,7 +681,7 @@ extern "C" int asis_chan_stats(int mode, const void *x, const void *dy, int dtyp
   if (workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "chan_stats: workspace %zu < %zu bytes", workspace_bytes, need);
   int ppb;
   const int nb = stat_blocks((size_t)B * H * W, ppb);
-  StatArgs s{B, H, W, C, storage_pad, shift, a, b, mean, rstd, relu};
+  StatArgs s{B, H, W, C, storage_pad, dy_pad, shift, a, b, mean, rstd, relu};
   const int CV = C / NV;
   dim3 grid(nb, (CV + 31) / 32 > 8 ? 8 : (CV + 31) / 32);
   cudaStream_t st = (cudaStream_t)stream;
@@ -637,17 +697,17 @@ extern "C" int asis_chan_stats(int mode, const void *x, const void *dy, int dtyp
   return ASIS_OK;
 }
 
-// mode 0: y = act(a x + b).  mode 1: dx = a (dz - c1 - xhat c2).
+// mode 0: y = act(a (x - mean) + b).  mode 1: dx = a (dz - c1 - xhat c2)  (dx in storage pad_out, dy in storage dy_pad).
 extern "C" int asis_bn_apply(int mode, const void *x, const void *dy, int in_dtype, void *out, int out_dtype, int B, int H, int W, int C,
-                             int pad_in, int pad_out, const float *a, const float *b, const float *mean, const float *rstd,
-                             const float *c1, const float *c2, int relu, void *stream) {
-  ASIS_REQUIRE(x && out && a && b, "bn_apply: null pointer");
+                             int pad_in, int pad_out, int dy_pad, const float *a, const float *b, const float *mean,
+                             const float *rstd, const float *c1, const float *c2, int relu, void *stream) {
+  ASIS_REQUIRE(x && out && a && b && mean, "bn_apply: null pointer");
   ASIS_REQUIRE(dtype_ok(in_dtype) && dtype_ok(out_dtype), "bn_apply: bad dtype");
   ASIS_REQUIRE(mode == 0 || (dy && mean && rstd && c1 && c2), "bn_apply: backward needs dy, mean, rstd, c1, c2");
   const int NV = out_dtype == ASIS_BF16 ? 8 : 4;
   ASIS_REQUIRE(C % NV == 0 && aligned16(x) && aligned16(out), "bn_apply: C=%d must be a multiple of %d", C, NV);
   ASIS_REQUIRE(!(in_dtype == ASIS_BF16 && out_dtype == ASIS_F32), "bn_apply: bf16 -> f32 is not provided");
-  ApplyArgs s{B, H, W, C, pad_in, pad_out, a, b, mean, rstd, c1, c2, relu};
+  ApplyArgs s{B, H, W, C, pad_in, pad_out, dy_pad, a, b, mean, rstd, c1, c2, relu};
   const size_t total = (size_t)B * (H + 2 * pad_out) * (W + 2 * pad_out) * (C / NV);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 0) {
@@ -685,87 +745,106 @@ extern "C" int asis_maxpool3x3s2_backward(const void *gy, const uint8_t *idx, vo
   return ASIS_OK;
 }
 
+static int head_check(int dtype, int C, int CO) {
+  ASIS_REQUIRE(dtype_ok(dtype), "seg_head: bad dtype");
+  const int NV = dtype == ASIS_BF16 ? 8 : 4;
+  ASIS_REQUIRE(C % NV == 0 && C >= NV, "seg_head: C=%d must be a multiple of %d", C, NV);
+  ASIS_REQUIRE(CO >= 1 && CO <= 4, "seg_head: 1..4 classes (got %d); wider heads go through asis_upsample2x + im2col + gemm", CO);
+  ASIS_REQUIRE(9 * CO * C <= HEAD_WG * 256 && (size_t)9 * CO * C * sizeof(float) <= 160 * 1024, "seg_head: C * classes too large");
+  return ASIS_OK;
+}
+
+#define ASIS_HEAD_CO(CO, ...)           \
+  do {                                  \
+    switch (CO) {                       \
+      case 1: { constexpr int CO_ = 1; __VA_ARGS__; } break; \
+      case 2: { constexpr int CO_ = 2; __VA_ARGS__; } break; \
+      case 3: { constexpr int CO_ = 3; __VA_ARGS__; } break; \
+      default: { constexpr int CO_ = 4; __VA_ARGS__; } break; \
+    }                                   \
+  } while (0)
+
+extern "C" size_t asis_seg_head_workspace_bytes(int B, int H, int W, int C, int CO) {
+  // U / dU [B*H*W, 9*CO] f32, followed by the weight-gradient partials of the backward
+  const size_t R = (size_t)B * H * W;
+  const size_t nb = std::min<size_t>((R + 1023) / 1024, 592);
+  return align_up(R * 9 * CO * sizeof(float), 256) + nb * 9 * CO * C * sizeof(float);
+}
+
 template <typename T, int CO>
-static int smallconv_launch(int what, const void *x, const float *w, const float *bias, float *y, const float *gy, void *gx,
-                            float *partial, int nb, int ppb, int B, int H, int W, int C, cudaStream_t st) {
-  const size_t npix = (size_t)B * H * W;
-  const unsigned blocks = (unsigned)std::min<size_t>((npix + 7) / 8, (size_t)148 * 16);
-  if (what == 0) smallconv_fwd_kernel<T, CO><<<blocks, 256, 0, st>>>((const T *)x, w, bias, y, B, H, W, C);
-  else if (what == 1) smallconv_dgrad_kernel<T, CO><<<blocks, 256, 0, st>>>(gy, w, (T *)gx, B, H, W, C);
-  else {
-    const size_t shb = (size_t)8 * CO * 9 * C * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
-      ASIS_CUDA(cudaFuncSetAttribute(smallconv_wgrad_kernel<T, CO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
-    smallconv_wgrad_kernel<T, CO><<<nb, 256, shb, st>>>((const T *)x, gy, partial, B, H, W, C, ppb);
+static int seg_head_fwd(const void *z, const float *w2, const float *bias, float *y, float *U, int B, int H, int W, int C, cudaStream_t st) {
+  constexpr int NT = 9 * CO;
+  const size_t R = (size_t)B * H * W;
+  const size_t shb = (size_t)NT * C * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    ASIS_CUDA(cudaFuncSetAttribute(head_project_fwd_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
   }
+  const unsigned pb = (unsigned)std::min<size_t>((R + 127) / 128, (size_t)148 * 16);
+  head_project_fwd_kernel<T, NT><<<pb, 128, shb, st>>>((const T *)z, w2, U, R, C);
+  ASIS_LAUNCHED();
+  const float sy = (float)(H - 1) / (float)(2 * H - 1), sx = (float)(W - 1) / (float)(2 * W - 1);
+  head_gather_fwd_kernel<CO><<<grid_for(R * 4), 256, 0, st>>>(U, bias, y, B, H, W, sy, sx);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }
 
-static int smallconv_check(int dtype, int C, int CO) {
-  ASIS_REQUIRE(dtype_ok(dtype), "smallconv: bad dtype");
-  const int NV = dtype == ASIS_BF16 ? 8 : 4;
-  ASIS_REQUIRE(C % NV == 0 && C / NV <= 32, "smallconv: C=%d must be a multiple of %d and at most %d", C, NV, 32 * NV);
-  ASIS_REQUIRE(CO >= 1 && CO <= 4, "smallconv: 1..4 output channels (got %d); wider layers go through im2col + gemm", CO);
-  ASIS_REQUIRE((size_t)8 * CO * 9 * C * sizeof(float) <= 200 * 1024, "smallconv: C * CO too large");
-  return ASIS_OK;
-}
-
-#define ASIS_SMALLCONV(T, CO, ...)                                   \
-  do {                                                               \
-    switch (CO) {                                                    \
-      case 1: rc = smallconv_launch<T, 1>(__VA_ARGS__); break;       \
-      case 2: rc = smallconv_launch<T, 2>(__VA_ARGS__); break;       \
-      case 3: rc = smallconv_launch<T, 3>(__VA_ARGS__); break;       \
-      default: rc = smallconv_launch<T, 4>(__VA_ARGS__); break;      \
-    }                                                                \
-  } while (0)
-
-extern "C" int asis_smallconv3x3_forward(const void *x, int dtype, const float *w, const float *bias, float *y, int B, int H, int W,
-                                         int C, int CO, void *stream) {
-  ASIS_REQUIRE(x && w && y, "smallconv: null pointer");
-  if (int rc = smallconv_check(dtype, C, CO)) return rc;
+// y [B, 2H, 2W, CO] f32 = conv3x3_pad1( upsample2x_bilinear_align_corners(z [B, H, W, C]) ) + bias;
+// w2 [9*CO, C] f32 with row index (ky*3 + kx)*CO + co.
+extern "C" int asis_seg_head_forward(const void *z, int dtype, const float *w2, const float *bias, float *y, int B, int H, int W, int C,
+                                     int CO, void *workspace, size_t workspace_bytes, void *stream) {
+  ASIS_REQUIRE(z && w2 && y && workspace, "seg_head: null pointer");
+  ASIS_REQUIRE(B > 0 && H > 1 && W > 1, "seg_head: need B > 0, H > 1, W > 1");
+  if (int rc = head_check(dtype, C, CO)) return rc;
+  if (workspace_bytes < asis_seg_head_workspace_bytes(B, H, W, C, CO)) ASIS_FAIL(ASIS_ERR_WORKSPACE, "seg_head: workspace too small");
   int rc = ASIS_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  ASIS_DISPATCH_DTYPE(dtype, T, ASIS_SMALLCONV(T, CO, 0, x, w, bias, y, nullptr, nullptr, nullptr, 0, 0, B, H, W, C, st));
+  ASIS_DISPATCH_DTYPE(dtype, T, ASIS_HEAD_CO(CO, rc = (seg_head_fwd<T, CO_>(z, w2, bias, y, (float *)workspace, B, H, W, C, st))));
   return rc;
 }
 
-static int smallconv_wgrad_blocks(size_t npix, int &ppb) {
-  int nb = (int)std::min<size_t>((npix + 2047) / 2048, 296);
-  if (nb < 1) nb = 1;
-  ppb = (int)((npix + nb - 1) / nb);
-  return nb;
-}
-
-extern "C" size_t asis_smallconv3x3_backward_workspace_bytes(int B, int H, int W, int C, int CO) {
-  int ppb;
-  return (size_t)smallconv_wgrad_blocks((size_t)B * H * W, ppb) * CO * 9 * C * sizeof(float);
-}
-
-// gx (dtype, may be null), gw [CO,3,3,C] f32 (may be null); the bias gradient is the column sum of gy (asis_colsum)
-extern "C" int asis_smallconv3x3_backward(const void *x, int dtype, const float *w, const float *gy, void *gx, float *gw, int B, int H,
-                                          int W, int C, int CO, void *workspace, size_t workspace_bytes, void *stream) {
-  ASIS_REQUIRE(x && w && gy, "smallconv: null pointer");
-  if (int rc = smallconv_check(dtype, C, CO)) return rc;
-  int rc = ASIS_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (gx) {
-    ASIS_DISPATCH_DTYPE(dtype, T, ASIS_SMALLCONV(T, CO, 1, x, w, nullptr, nullptr, gy, gx, nullptr, 0, 0, B, H, W, C, st));
-    if (rc) return rc;
-  }
-  if (gw) {
-    const size_t need = asis_smallconv3x3_backward_workspace_bytes(B, H, W, C, CO);
-    if (!workspace || workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "smallconv: workspace %zu < %zu bytes", workspace_bytes, need);
-    int ppb;
-    const int nb = smallconv_wgrad_blocks((size_t)B * H * W, ppb);
-    ASIS_DISPATCH_DTYPE(dtype, T, ASIS_SMALLCONV(T, CO, 2, x, w, nullptr, nullptr, gy, nullptr, (float *)workspace, nb, ppb, B, H, W, C, st));
-    if (rc) return rc;
-    conv_reduce_partials_kernel<<<(CO * 9 * C + 31) / 32, 256, 0, st>>>((const float *)workspace, nb, CO * 9 * C, gw);
+template <typename T, int CO>
+static int seg_head_bwd(const void *z, const float *w2, const float *gy, void *gz, float *gw2, float *dU, float *partial, int B, int H,
+                        int W, int C, cudaStream_t st) {
+  constexpr int NT = 9 * CO;
+  const size_t R = (size_t)B * H * W;
+  const float sy = (float)(H - 1) / (float)(2 * H - 1), sx = (float)(W - 1) / (float)(2 * W - 1);
+  head_gather_bwd_kernel<CO><<<(unsigned)std::min<size_t>((R + 127) / 128, (size_t)148 * 32), 128, 0, st>>>(gy, dU, B, H, W, sy, sx);
+  ASIS_LAUNCHED();
+  if (gz) {
+    const size_t shb = (size_t)NT * C * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      ASIS_CUDA(cudaFuncSetAttribute(head_project_dgrad_kernel<T, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      configured = true;
+    }
+    const unsigned pb = (unsigned)std::min<size_t>((R + 127) / 128, (size_t)148 * 16);
+    head_project_dgrad_kernel<T, NT><<<pb, 128, shb, st>>>(dU, w2, (T *)gz, R, C);
     ASIS_LAUNCHED();
   }
+  if (gw2) {
+    const int nb = (int)std::min<size_t>((R + 1023) / 1024, 592);
+    const int ppb = (int)((R + nb - 1) / nb);
+    head_project_wgrad_kernel<T><<<nb, 256, 0, st>>>(dU, (const T *)z, partial, R, C, NT, ppb);
+    ASIS_LAUNCHED();
+    conv_reduce_partials_kernel<<<(NT * C + 31) / 32, 256, 0, st>>>(partial, nb, NT * C, gw2);
+    ASIS_LAUNCHED();
+  }
+  return ASIS_OK;
+}
+
+// gz [B, H, W, C] (z's dtype, optional), gw2 [9*CO, C] f32 (optional); the bias gradient is the sum of gy over pixels
+extern "C" int asis_seg_head_backward(const void *z, int dtype, const float *w2, const float *gy, void *gz, float *gw2, int B, int H,
+                                      int W, int C, int CO, void *workspace, size_t workspace_bytes, void *stream) {
+  ASIS_REQUIRE(z && w2 && gy && workspace, "seg_head: null pointer");
+  if (int rc = head_check(dtype, C, CO)) return rc;
+  if (workspace_bytes < asis_seg_head_workspace_bytes(B, H, W, C, CO)) ASIS_FAIL(ASIS_ERR_WORKSPACE, "seg_head: workspace too small");
+  const size_t R = (size_t)B * H * W;
+  float *dU = (float *)workspace;
+  float *partial = (float *)((char *)workspace + align_up(R * 9 * CO * sizeof(float), 256));
+  int rc = ASIS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  ASIS_DISPATCH_DTYPE(dtype, T, ASIS_HEAD_CO(CO, rc = (seg_head_bwd<T, CO_>(z, w2, gy, gz, gw2, dU, partial, B, H, W, C, st))));
   return rc;
 }

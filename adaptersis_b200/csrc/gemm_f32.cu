@@ -17,13 +17,22 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
   const int t = threadIdx.x;
   const int tx = t & 15, ty = t >> 4;
   const bool a_kfast = p.a_k == 1, b_kfast = p.b_k == 1;
-  float acc[4][4];
+  // Blocked summation: `acc` holds at most 512 products, then it is folded into `tot`.  A weight gradient of the
+  // convolutional stages reduces over up to 10^6 pixels; one running fp32 sum of that length loses ~3 digits
+  // (measured against fp64: 2.8e-2 on a stem weight gradient where cuDNN's tree-like order gives 5e-3).
+  float acc[4][4], tot[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = tot[i][j] = 0.f;
 
   for (int k0 = 0; k0 < p.K; k0 += TK) {
+    if ((k0 & 511) == 0 && k0) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       int r, k;
@@ -49,6 +58,10 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(GemmF32 p) {
     }
     __syncthreads();
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] += tot[i][j];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int m = m0 + ty * 4 + i;

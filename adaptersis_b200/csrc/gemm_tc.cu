@@ -41,6 +41,16 @@ struct GemmTcParams {
   int M, N, K;
   int m_tiles, m_groups, n_tiles, splits, kb_per_split, kb_total;
   int atomic_out;  // split-K: combine with red.global.add.f32
+  // 3x3 / stride-1 convolution as an implicit GEMM over a zero-padded channels-last map (pair kernel only): the K loop
+  // runs over (tap, channel block); tap t reads the A rows shifted by conv_a_row_off[t] (TMA zero-fills rows outside
+  // the tensor) -- "im2col by TMA coordinates", no column matrix in memory.
+  int conv_taps;           // 0: plain GEMM
+  int conv_kpt;            // k-blocks per tap
+  int conv_b_k_tap;        // B's K coordinate of (tap, kk) = tap * conv_b_k_tap + kk * BK
+  int conv_b_n_tap;        // B's N coordinate shift of tap t = t * conv_b_n_tap
+  int conv_wp, conv_sign;  // row shift of tap t = conv_sign * ((t / 3 - 1) * conv_wp + t % 3 - 1)   (conv_wp = W + 2)
+  int conv_wg_cin;         // weight gradient of the implicit convolution (MN-major B = x_p, N = 9 Cin): the 64-column box
+                           // at N coordinate n belongs to tap n / Cin: it reads channels n % Cin of the rows shifted by that tap
   EpiArgs epi;
 };
 
@@ -355,9 +365,12 @@ __device__ __forceinline__ void epi3_chunk(const EpiLane &L, uint32_t rd0, uint3
 }
 
 // the epilogue of one 32-row x 128-column slab (entirely inside N) owned by one warp; `stage_u32`: its 4 KB buffer
-template <int KIND, bool CBF16>
+// `nch`: how many of the slab's four 32-column chunks lie inside N (a narrow GEMM -- N = 64 convolutions -- uses 2 or 0)
+// FULL: all four chunks, known at compile time (the hot instantiation: every loop bound and `last` are constants)
+template <int KIND, bool CBF16, bool FULL>
 __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr, uint32_t stage_u32, int row0, int col_base,
-                                          int lane, uint64_t *tfull, uint32_t tfull_phase, int tr_idx) {
+                                          int lane, uint64_t *tfull, uint32_t tfull_phase, int tr_idx, int nch_rt) {
+  const int nch = FULL ? 4 : nch_rt;
   const EpiArgs &e = p.epi;
   const int cg = lane & 7, r = lane >> 3;
   (void)tr_idx;
@@ -394,20 +407,25 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
   uint4 pre[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) pre[i] = make_uint4(0u, 0u, 0u, 0u);
-  float4 b4n, g4n;
-  epi3_colvec<KIND>(p, col, b4n, g4n);                    // chunk 0's columns
-  epi3_prefetch<KIND>(L, pre);                            // in flight while the MMAs of this tile finish
+  float4 b4n = make_float4(0.f, 0.f, 0.f, 0.f), g4n = b4n;
+  if (nch > 0) {
+    epi3_colvec<KIND>(p, col, b4n, g4n);                  // chunk 0's columns
+    epi3_prefetch<KIND>(L, pre);                          // in flight while the MMAs of this tile finish
+  }
   if (tr_idx >= 0) GEMM_TRACE(3, tr_idx);
   mbar_wait(tfull, tfull_phase);
   tc_fence_after();
   if (tr_idx >= 0) GEMM_TRACE(4, tr_idx);
+  if (nch <= 0) return;                     // (the wait above keeps this warp in step with the accumulator phases)
   float va[32], vb[32];
   tmem_ld32_issue(taddr, va);
 #pragma unroll 1
   for (int c2 = 0; c2 < 2; ++c2) {
+    if (2 * c2 >= nch) break;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {           // h = 0: registers va;  h = 1: registers vb
-      const bool last = (c2 == 1 && h == 1);
+      if (2 * c2 + h >= nch) break;
+      const bool last = (2 * c2 + h + 1 >= nch);
       tmem_ld_wait();
       if (!last) {
         if (h == 0) tmem_ld32_issue(taddr + (2 * c2 + 1) * 32, vb);
@@ -711,17 +729,33 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t lfull = mapa_u32(full_bar + stage, 0);   // the leader's barrier for this stage
           if (leader) mbar_arrive_expect_tx_cluster(lfull, 2 * STAGE2_BYTES);   // both CTAs' A + B halves
           else mbar_arrive_cluster(lfull);
+          int a_k = kb * BK, a_row = m_blk * BM, b_k = kb * BK, b_n = n0;
+          if (p.conv_taps) {                 // implicit 3x3 convolution: (tap, channel block) of this k-block
+            const int tap = kb / p.conv_kpt, kk = kb - tap * p.conv_kpt;
+            a_k = kk * BK;
+            a_row += p.conv_sign * ((tap / 3 - 1) * p.conv_wp + (tap % 3 - 1));
+            b_k = tap * p.conv_b_k_tap + kk * BK;
+            b_n += tap * p.conv_b_n_tap;
+          }
           if (A_MN == 0) {
-            tma_load_2d_pair(&tmA, lfull, sa, kb * BK, m_blk * BM);
+            tma_load_2d_pair(&tmA, lfull, sa, a_k, a_row);
           } else {
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(&tmA, lfull, sa + j * BOX_BYTES, m_blk * BM + j * 64, kb * BK);
           }
           if (B_MN == 0) {
-            tma_load_2d_pair(&tmB, lfull, sb, kb * BK, n0);
+            tma_load_2d_pair(&tmB, lfull, sb, b_k, b_n);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 2 / 64; ++j) tma_load_2d_pair(&tmB, lfull, sb + j * BOX_BYTES, n0 + j * 64, kb * BK);
+            for (int j = 0; j < BN / 2 / 64; ++j) {
+              int bn = b_n + j * 64, bk = b_k;
+              if (p.conv_wg_cin) {
+                const int tap = bn / p.conv_wg_cin;
+                bn -= tap * p.conv_wg_cin;
+                bk += (tap / 3 - 1) * p.conv_wp + (tap % 3 - 1);      // (taps >= 9: columns beyond N, never stored)
+              }
+              tma_load_2d_pair(&tmB, lfull, sb + j * BOX_BYTES, bn, bk);
+            }
           }
         }
         __syncwarp();
@@ -794,20 +828,21 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int col_base = n_blk * BN + half * 128;
       const int tr = ew == 0 ? tile / num_clusters : -1;     // (trace builds: stamps of epilogue warp 0)
       // slabs inside N with vectorisable pitches and a bf16 (or no) aux operand take the lean epilogue
-      const bool lean = vec_ok && !p.atomic_out && col_base + 128 <= p.N && (!p.epi.aux || p.epi.aux_dtype == ASIS_BF16);
+      const bool lean_ok = vec_ok && !p.atomic_out && (!p.epi.aux || p.epi.aux_dtype == ASIS_BF16);
+      const bool lean = lean_ok && col_base + 128 <= p.N;
       if (lean) {
         const uint32_t st32 = smem_u32(stage);
         const bool cb = p.epi.c_dtype == ASIS_BF16;
 #define ASIS_EPI3(K)                                                                                                   \
   do {                                                                                                                 \
-    if (cb) epi_slab3<K, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr);                  \
-    else epi_slab3<K, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr);                    \
+    if (cb) epi_slab3<K, true, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4);         \
+    else epi_slab3<K, false, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4);           \
   } while (0)
         switch (p.epi.kind) {
           case ASIS_EPI_GELU: ASIS_EPI3(ASIS_EPI_GELU); break;
-          case ASIS_EPI_SCALE_RESIDUAL: epi_slab3<ASIS_EPI_SCALE_RESIDUAL, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_SCALE_RESIDUAL: epi_slab3<ASIS_EPI_SCALE_RESIDUAL, false, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4); break;
           case ASIS_EPI_DGELU: ASIS_EPI3(ASIS_EPI_DGELU); break;
-          case ASIS_EPI_ACCUMULATE: epi_slab3<ASIS_EPI_ACCUMULATE, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr); break;
+          case ASIS_EPI_ACCUMULATE: epi_slab3<ASIS_EPI_ACCUMULATE, false, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4); break;
           case ASIS_EPI_GELU_GRAD: ASIS_EPI3(ASIS_EPI_GELU_GRAD); break;
           case ASIS_EPI_MUL_AUX: ASIS_EPI3(ASIS_EPI_MUL_AUX); break;
           default: ASIS_EPI3(ASIS_EPI_NONE); break;
@@ -992,6 +1027,81 @@ static int cluster_pref() {
     if (v != 1 && v != 2 && v != 4) v = 2;
   }
   return v;
+}
+
+// 3x3 / stride 1 / pad 1 convolution pieces as implicit GEMMs over zero-padded channels-last maps
+//   op 0 forward: y_p[R, Cout] = sum_t x_p[R + off_t, Cin] . W_t^T      A = x_p, B = w2 [Cout, 9 Cin] (K-major)
+//   op 1 dgrad:   dx_p[R, Cin] = sum_t dy_p[R - off_t, Cout] . W_t      A = dy_p, B = w2 read MN-major (rows = Cout)
+//   op 2 wgrad:   dW_t[Cout, Cin] = dy_p^T . x_p[. + off_t]  one split-K GEMM with N = 9 Cin: the 64-column boxes of B
+//                 carry their tap's row shift (conv_wg_cin)
+// R = B (H+2) (W+2) rows, off_t = (ky-1)(W+2) + (kx-1).  Border rows of the outputs of op 0 / 1 hold values of
+// positions outside the image: consumers read the logical pixels only.
+int gemm_tc_conv3x3(int op, const void *a, const void *b, void *c, int c_dtype, const float *bias, int B, int H, int W, int Cin,
+                    int Cout, cudaStream_t st) {
+  ASIS_REQUIRE(op >= 0 && op <= 2, "conv3x3_gemm: op must be 0 (forward), 1 (input gradient) or 2 (weight gradient)");
+  ASIS_REQUIRE(aligned16(a) && aligned16(b) && aligned16(c), "conv3x3_gemm: pointers must be 16-byte aligned");
+  ASIS_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "conv3x3_gemm: Cin=%d and Cout=%d must be multiples of 64", Cin, Cout);
+  const int64_t R64 = (int64_t)B * (H + 2) * (W + 2);
+  ASIS_REQUIRE(R64 < (1ll << 31) - 4096, "conv3x3_gemm: map too large");
+  const int R = (int)R64, Wp = W + 2;
+  const int sms = sm_count();
+  if (op == 2) {
+    ASIS_REQUIRE(c_dtype == ASIS_F32, "conv3x3_gemm: the weight gradient is f32");
+    GemmTcParams p{};
+    p.M = Cout; p.N = 9 * Cin; p.K = R;
+    p.m_tiles = (Cout + BM - 1) / BM;
+    p.n_tiles = (p.N + BN - 1) / BN;
+    p.kb_total = (R + BK - 1) / BK;
+    p.m_groups = (p.m_tiles + 1) / 2;
+    p.conv_wg_cin = Cin;
+    p.conv_wp = Wp;
+    p.conv_sign = 1;
+    p.epi = EpiArgs{ASIS_EPI_NONE, nullptr, nullptr, nullptr, nullptr, 0, 0, c, ASIS_F32, (int64_t)9 * Cin};
+    const int tiles = p.m_groups * p.n_tiles;       // cluster tiles
+    int splits = (sms / 2) / tiles;
+    if (splits > p.kb_total / 8) splits = p.kb_total / 8;
+    if (splits > 64) splits = 64;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (p.kb_total + splits - 1) / splits;
+    p.splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+    p.atomic_out = p.splits > 1;
+    if (p.atomic_out) ASIS_CUDA(cudaMemsetAsync(c, 0, (size_t)Cout * 9 * Cin * sizeof(float), st));
+    CUtensorMap ta, tb;
+    if (int rc = make_tmap_2d(&ta, a, Cout, R, Cout, 64, BK)) return rc;      // dy_p read MN-major: inner = Cout (M), rows = pixels (K)
+    if (int rc = make_tmap_2d(&tb, b, Cin, R, Cin, 64, BK)) return rc;        // x_p  read MN-major: inner = Cin, rows = pixels (K)
+    const int cluster_tiles = tiles * p.splits;
+    int clusters = sms / 2;
+    if (cluster_tiles < clusters) clusters = cluster_tiles;
+    return launch_pair(ASIS_MAJOR_MN, ASIS_MAJOR_MN, ta, tb, p, clusters * 2, st);
+  }
+  const int Ck = op == 0 ? Cin : Cout;          // channels contracted per tap
+  const int Nn = op == 0 ? Cout : Cin;
+  GemmTcParams p{};
+  p.M = R; p.N = Nn; p.K = 9 * Ck;
+  p.m_tiles = (R + BM - 1) / BM;
+  p.n_tiles = (Nn + BN - 1) / BN;
+  p.kb_total = 9 * (Ck / BK);
+  p.m_groups = (p.m_tiles + 1) / 2;
+  p.splits = 1;
+  p.kb_per_split = p.kb_total;
+  p.conv_taps = 9;
+  p.conv_kpt = Ck / BK;
+  p.conv_b_k_tap = op == 0 ? Cin : 0;
+  p.conv_b_n_tap = op == 0 ? 0 : Cin;
+  p.conv_wp = Wp;
+  p.conv_sign = op == 0 ? 1 : -1;
+  p.epi = EpiArgs{ASIS_EPI_NONE, op == 0 ? bias : nullptr, nullptr, nullptr, nullptr, 0, 0, c, c_dtype, (int64_t)Nn};
+  CUtensorMap ta, tb;
+  if (int rc = make_tmap_2d(&ta, a, Ck, R, Ck, BK, BM)) return rc;                    // K-major A: inner = channels of one tap
+  if (op == 0) {
+    if (int rc = make_tmap_2d(&tb, b, (uint64_t)9 * Cin, Cout, (uint64_t)9 * Cin, BK, BN / 2)) return rc;      // w2 K-major
+  } else {
+    if (int rc = make_tmap_2d(&tb, b, (uint64_t)9 * Cin, Cout, (uint64_t)9 * Cin, 64, BK)) return rc;          // w2 MN-major: rows = Cout (K)
+  }
+  const int cluster_tiles = p.m_groups * p.n_tiles;
+  int clusters = sms / 2;
+  if (cluster_tiles < clusters) clusters = cluster_tiles;
+  return launch_pair(ASIS_MAJOR_K, op == 0 ? ASIS_MAJOR_K : ASIS_MAJOR_MN, ta, tb, p, clusters * 2, st);
 }
 
 int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b_major, int64_t ldb, int M, int N,

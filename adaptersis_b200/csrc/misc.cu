@@ -275,29 +275,36 @@ __device__ __forceinline__ Up2Src up2_src(int o, float scale, int in) {
   return r;
 }
 
+// pi / po: storage padding of the input / output maps ([B, H + 2p, W + 2p, C], zeros in the border; 0 = plain)
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T *__restrict__ x, T *__restrict__ y, int B, int H,
-                                                             int W, int C, float sy, float sx) {
+                                                             int W, int C, float sy, float sx, int pi, int po) {
   constexpr int N = Up2Vec<T>::N;
   const int CV = C / N, OH = 2 * H, OW = 2 * W;
-  const size_t total = (size_t)B * OH * OW * CV;
+  const int Hi = H + 2 * pi, Wi = W + 2 * pi, Hs = OH + 2 * po, Ws = OW + 2 * po;
+  const size_t total = (size_t)B * Hs * Ws * CV;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int cv = (int)(t % CV);
     size_t r = t / CV;
-    const int ox = (int)(r % OW);
-    r /= OW;
-    const int oy = (int)(r % OH);
-    const int b = (int)(r / OH);
-    const Up2Src ys = up2_src(oy, sy, H), xs = up2_src(ox, sx, W);
-    const T *xb = x + (size_t)b * H * W * C + (size_t)cv * N;
-    float v00[N], v01[N], v10[N], v11[N], o[N];
-    Up2Vec<T>::load(xb + ((size_t)ys.i0 * W + xs.i0) * C, v00);
-    Up2Vec<T>::load(xb + ((size_t)ys.i0 * W + xs.i1) * C, v01);
-    Up2Vec<T>::load(xb + ((size_t)ys.i1 * W + xs.i0) * C, v10);
-    Up2Vec<T>::load(xb + ((size_t)ys.i1 * W + xs.i1) * C, v11);
-    const float w00 = (1.f - ys.l) * (1.f - xs.l), w01 = (1.f - ys.l) * xs.l, w10 = ys.l * (1.f - xs.l), w11 = ys.l * xs.l;
+    const int ox = (int)(r % Ws) - po;
+    r /= Ws;
+    const int oy = (int)(r % Hs) - po;
+    const int b = (int)(r / Hs);
+    float o[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) o[i] = w00 * v00[i] + w01 * v01[i] + w10 * v10[i] + w11 * v11[i];
+    for (int i = 0; i < N; ++i) o[i] = 0.f;
+    if (oy >= 0 && oy < OH && ox >= 0 && ox < OW) {
+      const Up2Src ys = up2_src(oy, sy, H), xs = up2_src(ox, sx, W);
+      const T *xb = x + ((size_t)b * Hi * Wi + (size_t)pi * Wi + pi) * C + (size_t)cv * N;
+      float v00[N], v01[N], v10[N], v11[N];
+      Up2Vec<T>::load(xb + ((size_t)ys.i0 * Wi + xs.i0) * C, v00);
+      Up2Vec<T>::load(xb + ((size_t)ys.i0 * Wi + xs.i1) * C, v01);
+      Up2Vec<T>::load(xb + ((size_t)ys.i1 * Wi + xs.i0) * C, v10);
+      Up2Vec<T>::load(xb + ((size_t)ys.i1 * Wi + xs.i1) * C, v11);
+      const float w00 = (1.f - ys.l) * (1.f - xs.l), w01 = (1.f - ys.l) * xs.l, w10 = ys.l * (1.f - xs.l), w11 = ys.l * xs.l;
+#pragma unroll
+      for (int i = 0; i < N; ++i) o[i] = w00 * v00[i] + w01 * v01[i] + w10 * v10[i] + w11 * v11[i];
+    }
     Up2Vec<T>::store(y + t * N, o);
   }
 }
@@ -310,35 +317,38 @@ __device__ __forceinline__ float up2_weight(int o, int i, float scale, int in) {
 
 template <typename T>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T *__restrict__ gy, T *__restrict__ gx, int B, int H,
-                                                             int W, int C, float sy, float sx) {
+                                                             int W, int C, float sy, float sx, int pi, int po) {
   constexpr int N = Up2Vec<T>::N;
   const int CV = C / N, OH = 2 * H, OW = 2 * W;
-  const size_t total = (size_t)B * H * W * CV;
+  const int Hi = H + 2 * pi, Wi = W + 2 * pi, Hs = OH + 2 * po, Ws = OW + 2 * po;
+  const size_t total = (size_t)B * Hi * Wi * CV;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int cv = (int)(t % CV);
     size_t r = t / CV;
-    const int ix = (int)(r % W);
-    r /= W;
-    const int iy = (int)(r % H);
-    const int b = (int)(r / H);
-    // output rows / columns that can touch this input pixel: src in (i - 1, i + 1)  ->  a window of at
-    // most 6 around 2 i (scale is just below 1/2); exact membership is decided by up2_weight
-    const int oy_lo = max(0, 2 * iy - 3), oy_hi = min(OH - 1, 2 * iy + 4);
-    const int ox_lo = max(0, 2 * ix - 3), ox_hi = min(OW - 1, 2 * ix + 4);
+    const int ix = (int)(r % Wi) - pi;
+    r /= Wi;
+    const int iy = (int)(r % Hi) - pi;
+    const int b = (int)(r / Hi);
     float acc[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) acc[i] = 0.f;
-    const T *gb = gy + (size_t)b * OH * OW * C + (size_t)cv * N;
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-      const float wy = up2_weight(oy, iy, sy, H);
-      if (wy == 0.f) continue;
-      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-        const float w = wy * up2_weight(ox, ix, sx, W);
-        if (w == 0.f) continue;
-        float v[N];
-        Up2Vec<T>::load(gb + ((size_t)oy * OW + ox) * C, v);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      // output rows / columns that can touch this input pixel: src in (i - 1, i + 1)  ->  a window of at
+      // most 6 around 2 i (scale is just below 1/2); exact membership is decided by up2_weight
+      const int oy_lo = max(0, 2 * iy - 3), oy_hi = min(OH - 1, 2 * iy + 4);
+      const int ox_lo = max(0, 2 * ix - 3), ox_hi = min(OW - 1, 2 * ix + 4);
+      const T *gb = gy + ((size_t)b * Hs * Ws + (size_t)po * Ws + po) * C + (size_t)cv * N;
+      for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+        const float wy = up2_weight(oy, iy, sy, H);
+        if (wy == 0.f) continue;
+        for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+          const float w = wy * up2_weight(ox, ix, sx, W);
+          if (w == 0.f) continue;
+          float v[N];
+          Up2Vec<T>::load(gb + ((size_t)oy * Ws + ox) * C, v);
 #pragma unroll
-        for (int i = 0; i < N; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+          for (int i = 0; i < N; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+        }
       }
     }
     Up2Vec<T>::store(gx + t * N, acc);
@@ -433,24 +443,36 @@ static int up2_check(const void *a, const void *b, int dtype, int B, int H, int 
   return ASIS_OK;
 }
 
-extern "C" int asis_upsample2x_bilinear_forward(const void *x, void *y, int dtype, int B, int H, int W, int C, void *stream) {
+extern "C" int asis_upsample2x_bilinear_forward_padded(const void *x, void *y, int dtype, int B, int H, int W, int C, int pad_in,
+                                                       int pad_out, void *stream) {
   if (int rc = up2_check(x, y, dtype, B, H, W, C)) return rc;
+  ASIS_REQUIRE(pad_in >= 0 && pad_out >= 0, "upsample2x: negative storage padding");
   const float sy = (float)(H - 1) / (float)(2 * H - 1), sx = (float)(W - 1) / (float)(2 * W - 1);
-  const size_t total = (size_t)B * 4 * H * W * (C / (dtype == ASIS_BF16 ? 8 : 4));
+  const size_t total = (size_t)B * (2 * H + 2 * pad_out) * (2 * W + 2 * pad_out) * (C / (dtype == ASIS_BF16 ? 8 : 4));
   const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
   cudaStream_t st = (cudaStream_t)stream;
-  ASIS_DISPATCH_DTYPE(dtype, T, (upsample2x_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)x, (T *)y, B, H, W, C, sy, sx)));
+  ASIS_DISPATCH_DTYPE(dtype, T, (upsample2x_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)x, (T *)y, B, H, W, C, sy, sx, pad_in, pad_out)));
   ASIS_LAUNCHED();
   return ASIS_OK;
 }
 
-extern "C" int asis_upsample2x_bilinear_backward(const void *gy, void *gx, int dtype, int B, int H, int W, int C, void *stream) {
+extern "C" int asis_upsample2x_bilinear_backward_padded(const void *gy, void *gx, int dtype, int B, int H, int W, int C, int pad_in,
+                                                        int pad_out, void *stream) {
   if (int rc = up2_check(gy, gx, dtype, B, H, W, C)) return rc;
+  ASIS_REQUIRE(pad_in >= 0 && pad_out >= 0, "upsample2x: negative storage padding");
   const float sy = (float)(H - 1) / (float)(2 * H - 1), sx = (float)(W - 1) / (float)(2 * W - 1);
-  const size_t total = (size_t)B * H * W * (C / (dtype == ASIS_BF16 ? 8 : 4));
+  const size_t total = (size_t)B * (H + 2 * pad_in) * (W + 2 * pad_in) * (C / (dtype == ASIS_BF16 ? 8 : 4));
   const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 32);
   cudaStream_t st = (cudaStream_t)stream;
-  ASIS_DISPATCH_DTYPE(dtype, T, (upsample2x_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)gy, (T *)gx, B, H, W, C, sy, sx)));
+  ASIS_DISPATCH_DTYPE(dtype, T, (upsample2x_bwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)gy, (T *)gx, B, H, W, C, sy, sx, pad_in, pad_out)));
   ASIS_LAUNCHED();
   return ASIS_OK;
+}
+
+extern "C" int asis_upsample2x_bilinear_forward(const void *x, void *y, int dtype, int B, int H, int W, int C, void *stream) {
+  return asis_upsample2x_bilinear_forward_padded(x, y, dtype, B, H, W, C, 0, 0, stream);
+}
+
+extern "C" int asis_upsample2x_bilinear_backward(const void *gy, void *gx, int dtype, int B, int H, int W, int C, void *stream) {
+  return asis_upsample2x_bilinear_backward_padded(gy, gx, dtype, B, H, W, C, 0, 0, stream);
 }

@@ -4,9 +4,9 @@ running on libasis_b200 kernels (adaptersis_b200/conv.py), channels-last:
   decoder_1..4   3x3 conv (pad 1, bias) + BatchNorm2d + ReLU + bilinear x2 (align_corners=True)    42 -> 84 -> 168 -> 336 -> 672
   final_out      3x3 conv 64 -> num_classes
 
-The four wide convolutions are asis_im2col + tcgen05 GEMM (the first one, 3 x embed_dim -> 512 at 42 x 42, is a
-K = 27648 GEMM); BatchNorm + ReLU is one statistics pass + one fused normalise pass; the resize is the channels-last
-kernel pair of csrc/misc.cu; the head is a direct kernel.  Plain BatchNorm2d: per-GPU statistics under data
+The four wide convolutions are implicit tcgen05 GEMMs over zero-padded maps in bf16 mode (asis_conv3x3s1_gemm; the
+first one, 3 x embed_dim -> 512 at 42 x 42, is a K = 27648 GEMM), asis_im2col + FFMA GEMM in fp32 parity mode; BatchNorm + ReLU is one statistics pass + one fused normalise pass; the resize is the channels-last
+kernel pair of csrc/misc.cu; the last resize and the head are one fused node (conv.SegHeadFunction).  Plain BatchNorm2d: per-GPU statistics under data
 parallelism, as in the reference."""
 import torch
 import torch.nn as nn
@@ -33,13 +33,17 @@ class FeatureDecoder(nn.Module):
     def forward(self, x):
         """x [B, 3*embed_dim, h, w] (any memory format; channels-last is free) -> logits [B, num_classes, 16h, 16w] f32."""
         x = x.permute(0, 2, 3, 1).contiguous()          # (asis_im2col converts to the compute dtype on the way)
+        fused_head = self.num_classes <= 4
+        imp = [int(Cv.implicit_ok(getattr(self, f"decoder_{k}")[0])) for k in range(1, 5)] + [0]
+        if imp[0]:          # bf16 mode: zero-padded bf16 storage, the convolutions are implicit GEMMs (no column matrix)
+            x = Cv.repad(x, 0, 1, torch.bfloat16)
         for k in range(1, 5):
             conv, bn, _, _ = getattr(self, f"decoder_{k}")
-            x = Cv.conv2d(x, conv.weight, conv.bias, 1, 1)
-            x = Cv.batch_norm(x, bn, relu=True)
-            x = Fn.upsample2x_nhwc(x)
-        if self.num_classes <= 4:
-            y = Cv.smallconv3x3(x, self.final_out.weight, self.final_out.bias)
+            x = Cv.conv_bn_relu(x, conv, bn, imp[k - 1], 0)
+            if k < 4 or not fused_head:
+                x = Fn.upsample2x_nhwc(x, 0, imp[k] if k < 4 else 0)
+        if fused_head:      # decoder_4's resize + final_out as one node: the 64-channel 672 x 672 map is never built
+            y = Cv.seg_head(x, self.final_out.weight, self.final_out.bias)
         else:
             y = Cv.conv2d(x, self.final_out.weight, self.final_out.bias, 1, 1, out_dtype=torch.float32)
         return y.permute(0, 3, 1, 2)

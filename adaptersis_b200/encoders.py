@@ -7,7 +7,9 @@ on libasis_b200 kernels (adaptersis_b200/conv.py, csrc/conv.cu), channels-last f
   fc1..4     1x1 convolutions to embed_dim = one GEMM each on the token-major maps: the reference's
              ``c.view(bs, dim, -1).transpose(1, 2)`` is the identity here (the maps already are [B, H*W, C])
 
-Every convolution is asis_im2col + the tcgen05 GEMM (bf16 mode) or the FFMA GEMM (fp32 parity mode); every
+The two stride-1 convolutions of the stem run as implicit GEMMs over zero-padded maps in bf16 mode
+(asis_conv3x3s1_gemm), every other convolution is asis_im2col + the tcgen05 GEMM (bf16 mode) or the FFMA GEMM (fp32
+parity mode); every
 SyncBatchNorm exchanges one small tensor per direction (global-batch statistics, the reference's semantics).
 ``with_cp`` (activation checkpointing; the reference's own implementation of it is broken, encoders.py:71) is
 accepted and ignored."""
@@ -52,8 +54,11 @@ class FeatureEncoder(nn.Module):
     def forward(self, x, need_c1=True):
         """x [B, 3, H, W] (as the reference) -> (c1 [B, D, H/4, W/4] or None, c2, c3, c4 tokens [B, n, D])."""
         x = x.permute(0, 2, 3, 1).contiguous().float()                   # channels-last image
-        for i in (0, 3, 6):
-            x = _conv_bn_relu(x, self.stem[i], self.stem[i + 1])
+        s = self.stem
+        p3, p6 = int(Cv.implicit_ok(s[3])), int(Cv.implicit_ok(s[6]))     # bf16 mode: implicit GEMMs over zero-padded maps
+        x = Cv.conv_bn_relu(x, s[0], s[1], 0, p3)
+        x = Cv.conv_bn_relu(x, s[3], s[4], p3, p6)
+        x = Cv.conv_bn_relu(x, s[6], s[7], p6, 0)
         c1 = Cv.maxpool3x3s2(x)
         c2 = _conv_bn_relu(c1, self.conv2[0], self.conv2[1])
         c3 = _conv_bn_relu(c2, self.conv3[0], self.conv3[1])

@@ -500,14 +500,17 @@ class Upsample2xNHWCFunction(Function):
     """the same resize on a channels-last map [B, H, W, C] -> [B, 2H, 2W, C] (adaptersis_b200/decoders.py)."""
 
     @staticmethod
-    def forward(ctx, x):
-        return K.upsample2x_forward(x.contiguous())
+    def forward(ctx, x, pad_in=0, pad_out=0):
+        ctx.pads = (pad_in, pad_out)
+        return K.upsample2x_forward(x.contiguous(), pad_in, pad_out)
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gy):
-        return K.upsample2x_backward(gy.contiguous())
+        # (gy has the forward's dtype: produced by our own nodes; only its logical pixels are read)
+        return K.upsample2x_backward(gy.contiguous(), *ctx.pads), None, None
 
 
-def upsample2x_nhwc(x):
-    return Upsample2xNHWCFunction.apply(x)
+def upsample2x_nhwc(x, pad_in=0, pad_out=0):
+    """storage padding: x with pad_in border pixels, the result with pad_out zero border pixels (feeds the implicit GEMM)."""
+    return Upsample2xNHWCFunction.apply(x, pad_in, pad_out)

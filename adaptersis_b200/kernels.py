@@ -326,26 +326,29 @@ def dwconv3x3_backward(dy, pre, x, weight, maps, fuse_gelu):
 
 
 # ------------------------------------------------------------------------------------------ decoder
-def upsample2x_forward(x_nhwc):
-    """x [B, H, W, C] contiguous -> [B, 2H, 2W, C]; bilinear, align_corners=True."""
+def upsample2x_forward(x_nhwc, pad_in=0, pad_out=0):
+    """x [B, H(+2pi), W(+2pi), C] contiguous -> [B, 2H(+2po), 2W(+2po), C]; bilinear, align_corners=True."""
     need_cuda(x_nhwc)
-    B, H, W, C = x_nhwc.shape
-    y = torch.empty(B, 2 * H, 2 * W, C, dtype=x_nhwc.dtype, device=x_nhwc.device)
+    B, Hs, Ws, C = x_nhwc.shape
+    H, W = Hs - 2 * pad_in, Ws - 2 * pad_in
+    y = torch.empty(B, 2 * H + 2 * pad_out, 2 * W + 2 * pad_out, C, dtype=x_nhwc.dtype, device=x_nhwc.device)
     nb = x_nhwc.element_size() * B * H * W * C * 5
     with _Span("upsample2x_fwd", nb, "B"):
-        check(_lib.load().asis_upsample2x_bilinear_forward(ptr(x_nhwc), ptr(y), dt(x_nhwc), B, H, W, C, stream()))
+        check(_lib.load().asis_upsample2x_bilinear_forward_padded(ptr(x_nhwc), ptr(y), dt(x_nhwc), B, H, W, C, pad_in, pad_out,
+                                                                  stream()))
     return y
 
 
-def upsample2x_backward(gy_nhwc):
-    """gy [B, 2H, 2W, C] contiguous -> gx [B, H, W, C]."""
+def upsample2x_backward(gy_nhwc, pad_in=0, pad_out=0):
+    """gy [B, 2H(+2po), 2W(+2po), C] contiguous -> gx [B, H(+2pi), W(+2pi), C]."""
     need_cuda(gy_nhwc)
-    B, OH, OW, C = gy_nhwc.shape
-    gx = torch.empty(B, OH // 2, OW // 2, C, dtype=gy_nhwc.dtype, device=gy_nhwc.device)
-    nb = gy_nhwc.element_size() * B * (OH // 2) * (OW // 2) * C * 5
+    B, OHs, OWs, C = gy_nhwc.shape
+    H, W = (OHs - 2 * pad_out) // 2, (OWs - 2 * pad_out) // 2
+    gx = torch.empty(B, H + 2 * pad_in, W + 2 * pad_in, C, dtype=gy_nhwc.dtype, device=gy_nhwc.device)
+    nb = gy_nhwc.element_size() * B * H * W * C * 5
     with _Span("upsample2x_bwd", nb, "B"):
-        check(_lib.load().asis_upsample2x_bilinear_backward(ptr(gy_nhwc), ptr(gx), dt(gy_nhwc), B, OH // 2, OW // 2, C,
-                                                            stream()))
+        check(_lib.load().asis_upsample2x_bilinear_backward_padded(ptr(gy_nhwc), ptr(gx), dt(gy_nhwc), B, H, W, C, pad_in, pad_out,
+                                                                   stream()))
     return gx
 
 
@@ -394,48 +397,48 @@ def chan_stats(x, shift, storage_pad=0):
     nbytes = lib.asis_chan_stats_workspace_bytes(B, H, W, C)
     ws = workspace(nbytes, x.device)
     with _Span("bn_stats", x.numel() * x.element_size(), "B"):
-        check(lib.asis_chan_stats(0, ptr(x), None, dt(x), B, H, W, C, storage_pad, ptr(shift), None, None, None, None, 0,
+        check(lib.asis_chan_stats(0, ptr(x), None, dt(x), B, H, W, C, storage_pad, 0, ptr(shift), None, None, None, None, 0,
                                   ptr(s), ptr(s[1]), ptr(ws), nbytes, stream()))
     return s
 
 
-def chan_stats_backward(x, dy, a, b, mean, rstd, relu, storage_pad=0):
-    """-> s [2, C] f32: sum dz, sum dz * xhat  (dz = dy * relu'(a x + b))."""
+def chan_stats_backward(x, dy, a, b, mean, rstd, relu, storage_pad=0, dy_pad=0):
+    """-> s [2, C] f32: sum dz, sum dz * xhat  (dz = dy * relu'(a (x - mean) + b)); x / dy may use different storage padding."""
     lib = _lib.load()
     B, Hs, Ws, C = x.shape
     H, W = Hs - 2 * storage_pad, Ws - 2 * storage_pad
     x, dy = _c(x), _c(dy)
-    assert dy.dtype == x.dtype and dy.shape == x.shape
+    assert dy.dtype == x.dtype and dy.shape == (B, H + 2 * dy_pad, W + 2 * dy_pad, C)
     s = torch.empty(2, C, dtype=torch.float32, device=x.device)
     nbytes = lib.asis_chan_stats_workspace_bytes(B, H, W, C)
     ws = workspace(nbytes, x.device)
     with _Span("bn_bwd_stats", 2 * x.numel() * x.element_size(), "B"):
-        check(lib.asis_chan_stats(1, ptr(x), ptr(dy), dt(x), B, H, W, C, storage_pad, None, ptr(a), ptr(b), ptr(mean),
+        check(lib.asis_chan_stats(1, ptr(x), ptr(dy), dt(x), B, H, W, C, storage_pad, dy_pad, None, ptr(a), ptr(b), ptr(mean),
                                   ptr(rstd), int(relu), ptr(s), ptr(s[1]), ptr(ws), nbytes, stream()))
     return s
 
 
-def bn_apply(x, a, b, relu, out_dtype, pad_in=0, pad_out=0):
-    """y = act(a[c] x + b[c]) on a channels-last map (optionally re-padding the storage)."""
-    need_cuda(x, a, b)
+def bn_apply(x, a, b, mean, relu, out_dtype, pad_in=0, pad_out=0):
+    """y = act(a[c] (x - mean[c]) + b[c]) on a channels-last map (optionally re-padding the storage)."""
+    need_cuda(x, a, b, mean)
     B, Hs, Ws, C = x.shape
     H, W = Hs - 2 * pad_in, Ws - 2 * pad_in
     x = _c(x)
     y = torch.empty(B, H + 2 * pad_out, W + 2 * pad_out, C, dtype=out_dtype, device=x.device)
     with _Span("bn_apply", x.numel() * x.element_size() + y.numel() * y.element_size(), "B"):
-        check(_lib.load().asis_bn_apply(0, ptr(x), None, dt(x), ptr(y), dt(y), B, H, W, C, pad_in, pad_out, ptr(a), ptr(b),
-                                        None, None, None, None, int(relu), stream()))
+        check(_lib.load().asis_bn_apply(0, ptr(x), None, dt(x), ptr(y), dt(y), B, H, W, C, pad_in, pad_out, 0, ptr(a), ptr(b),
+                                        ptr(mean), None, None, None, int(relu), stream()))
     return y
 
 
-def bn_apply_backward(x, dy, a, b, mean, rstd, c1, c2, relu, pad=0):
-    """dx = a * (dz - c1 - xhat * c2), same storage as x."""
+def bn_apply_backward(x, dy, a, b, mean, rstd, c1, c2, relu, pad=0, dy_pad=0):
+    """dx = a * (dz - c1 - xhat * c2), in x's storage (zero border); dy in storage dy_pad."""
     B, Hs, Ws, C = x.shape
     H, W = Hs - 2 * pad, Ws - 2 * pad
     x, dy = _c(x), _c(dy)
     dx = torch.empty_like(x)
     with _Span("bn_bwd_apply", 3 * x.numel() * x.element_size(), "B"):
-        check(_lib.load().asis_bn_apply(1, ptr(x), ptr(dy), dt(x), ptr(dx), dt(dx), B, H, W, C, pad, pad, ptr(a), ptr(b),
+        check(_lib.load().asis_bn_apply(1, ptr(x), ptr(dy), dt(x), ptr(dx), dt(dx), B, H, W, C, pad, pad, dy_pad, ptr(a), ptr(b),
                                         ptr(mean), ptr(rstd), ptr(c1), ptr(c2), int(relu), stream()))
     return dx
 
@@ -459,28 +462,40 @@ def maxpool3x3s2_backward(gy, idx, H, W):
     return gx
 
 
-def smallconv3x3_forward(x, w, bias):
-    """x [B,H,W,C] channels-last, w [CO,3,3,C] f32 -> y [B,H,W,CO] f32."""
-    need_cuda(x, w)
-    B, H, W, C = x.shape
-    CO = w.shape[0]
-    x = _c(x)
-    y = torch.empty(B, H, W, CO, dtype=torch.float32, device=x.device)
-    with _Span("smallconv_fwd", x.numel() * x.element_size() + y.numel() * 4, "B"):
-        check(_lib.load().asis_smallconv3x3_forward(ptr(x), dt(x), ptr(w), ptr(bias), ptr(y), B, H, W, C, CO, stream()))
+def seg_head_forward(z, w2, bias, CO):
+    """conv3x3_pad1(upsample2x(z)) + bias, fused: z [B,H,W,C] channels-last, w2 [9*CO, C] f32 -> y [B,2H,2W,CO] f32."""
+    need_cuda(z, w2)
+    lib = _lib.load()
+    B, H, W, C = z.shape
+    z = _c(z)
+    y = torch.empty(B, 2 * H, 2 * W, CO, dtype=torch.float32, device=z.device)
+    nbytes = lib.asis_seg_head_workspace_bytes(B, H, W, C, CO)
+    ws = workspace(nbytes, z.device)
+    with _Span("seg_head_fwd", z.numel() * z.element_size() + y.numel() * 4, "B"):
+        check(lib.asis_seg_head_forward(ptr(z), dt(z), ptr(w2), ptr(bias), ptr(y), B, H, W, C, CO, ptr(ws), nbytes, stream()))
     return y
 
 
-def smallconv3x3_backward(x, w, gy, need_gx, need_gw):
+def seg_head_backward(z, w2, gy, need_gz, need_gw):
     lib = _lib.load()
-    B, H, W, C = x.shape
-    CO = w.shape[0]
-    x, gy = _c(x), _c(gy.float())
-    gx = torch.empty_like(x) if need_gx else None
-    gw = torch.empty(CO, 3, 3, C, dtype=torch.float32, device=x.device) if need_gw else None
-    nbytes = lib.asis_smallconv3x3_backward_workspace_bytes(B, H, W, C, CO)
-    ws = workspace(nbytes, x.device)
-    with _Span("smallconv_bwd", 2 * x.numel() * x.element_size() + gy.numel() * 4, "B"):
-        check(lib.asis_smallconv3x3_backward(ptr(x), dt(x), ptr(w), ptr(gy), ptr(gx), ptr(gw), B, H, W, C, CO, ptr(ws), nbytes,
-                                             stream()))
-    return gx, gw
+    B, H, W, C = z.shape
+    CO = gy.shape[-1]
+    z, gy = _c(z), _c(gy.float())
+    gz = torch.empty_like(z) if need_gz else None
+    gw2 = torch.empty(9 * CO, C, dtype=torch.float32, device=z.device) if need_gw else None
+    nbytes = lib.asis_seg_head_workspace_bytes(B, H, W, C, CO)
+    ws = workspace(nbytes, z.device)
+    with _Span("seg_head_bwd", 2 * z.numel() * z.element_size() + gy.numel() * 4, "B"):
+        check(lib.asis_seg_head_backward(ptr(z), dt(z), ptr(w2), ptr(gy), ptr(gz), ptr(gw2), B, H, W, C, CO, ptr(ws), nbytes,
+                                         stream()))
+    return gz, gw2
+
+
+def conv3x3s1_gemm(op, a, b, out, bias, B, H, W, Cin, Cout):
+    """Implicit-GEMM pieces of a 3x3 / stride 1 / pad 1 convolution over zero-padded channels-last bf16 maps
+    (include/asis_b200.h: asis_conv3x3s1_gemm).  `out` is allocated by the caller."""
+    need_cuda(a, b, out)
+    flops = 2.0 * B * (H + 2) * (W + 2) * 9 * Cin * Cout
+    with _Span("gemm_bf16", flops, "FLOP", f"conv3x3 op={op} B={B} {H}x{W} Cin={Cin} Cout={Cout}" if _PROF[0] is not None else None):
+        check(_lib.load().asis_conv3x3s1_gemm(op, ptr(a), ptr(b), ptr(out), dt(out), ptr(bias), B, H, W, Cin, Cout, stream()))
+    return out

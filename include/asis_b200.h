@@ -205,6 +205,12 @@ int asis_upsample2x_bilinear_forward(const void *x, void *y, int dtype, int B, i
                                      void *stream);
 int asis_upsample2x_bilinear_backward(const void *gy, void *gx, int dtype, int B, int H, int W, int C,
                                       void *stream);
+/* the same with storage padding on either side (maps [B, H + 2p, W + 2p, C], zero border): pad_in belongs to x / gx,
+ * pad_out to y / gy -- the decoder keeps the maps that feed asis_conv3x3s1_gemm zero-padded */
+int asis_upsample2x_bilinear_forward_padded(const void *x, void *y, int dtype, int B, int H, int W, int C,
+                                            int pad_in, int pad_out, void *stream);
+int asis_upsample2x_bilinear_backward_padded(const void *gy, void *gx, int dtype, int B, int H, int W,
+                                             int C, int pad_in, int pad_out, void *stream);
 
 /* LayerScale backward (dinov2/layers/layer_scale.py:26-27 behind x + ls(branch(x)), block.py:112-113) in
  * one pass over the incoming gradient d [M, N] f32:  du = d * gamma (dtype, the branch-output gradient),
@@ -229,23 +235,35 @@ int asis_im2col(const void *x, int x_dtype, void *cols, int cols_dtype, int B, i
 int asis_col2im(const void *dcols, void *dx, int dtype, int B, int H, int W, int C, int storage_pad,
                 int k, int stride, int pad, int64_t ldk, void *stream);
 
+/* The 3x3 / stride 1 / pad 1 convolutions (two of the stem, the four of the decoder) as IMPLICIT GEMMs on the tcgen05
+ * kernel: maps are stored zero-padded, [B, H+2, W+2, C] bf16 (storage padding 1), and tap (ky, kx) of the K loop
+ * reads the A rows shifted by (ky-1)(W+2) + (kx-1) through the TMA coordinates -- no column matrix in memory.
+ *   op 0: y_p [B,H+2,W+2,Cout] (c_dtype) = conv(x_p = a, w2 = b [Cout, 9*Cin] bf16, K = (ky, kx, cin)) + bias
+ *   op 1: dx_p [B,H+2,W+2,Cin] (c_dtype) from dy_p = a (ZERO border) and w2 = b
+ *   op 2: dw2 [Cout, 9*Cin] f32 = c from dy_p = a (ZERO border) and x_p = b
+ * The border rows of the outputs of op 0 / 1 hold values of positions outside the image: read the logical pixels only.
+ * Cin, Cout multiples of 64. */
+int asis_conv3x3s1_gemm(int op, const void *a, const void *b, void *c, int c_dtype, const float *bias,
+                        int B, int H, int W, int Cin, int Cout, void *stream);
+
 /* BatchNorm in training mode (nn.SyncBatchNorm encoders.py:12-40, nn.BatchNorm2d decoders.py:100-125), two
  * kernels each way.  Statistics: per-channel sums over the logical pixels, fixed-order partials (no atomics):
  *   mode 0: s1 = sum (x - shift[c]),  s2 = sum (x - shift[c])^2        (shifted: no cancellation)
- *   mode 1: s1 = sum dz,  s2 = sum dz * xhat,   dz = dy * relu'(a x + b),  xhat = (x - mean) * rstd
+ *   mode 1: s1 = sum dz,  s2 = sum dz * xhat,   dz = dy * relu'(a (x - mean) + b),  xhat = (x - mean) * rstd
  * s1, s2 are the two halves of ONE [2C] f32 buffer; the cross-rank exchange of SyncBatchNorm acts on it.
- * Apply:  mode 0: y = act(a[c] x + b[c])   (a = weight * rstd, b = bias - mean * a; y may use another storage
+ * Apply:  mode 0: y = act(a[c] (x - mean[c]) + b[c])   (a = weight * rstd, b = bias; y may use another storage
  *                                             padding; its border is zero-filled)
- *         mode 1: dx = a[c] * (dz - c1[c] - xhat * c2[c])            (c1 = mean dz, c2 = mean dz * xhat)   */
+ *         mode 1: dx = a[c] * (dz - c1[c] - xhat * c2[c])            (c1 = mean dz, c2 = mean dz * xhat);
+ *                 dx is written in storage pad_out, dy is read in storage dy_pad                         */
 size_t asis_chan_stats_workspace_bytes(int B, int H, int W, int C);
 int asis_chan_stats(int mode, const void *x, const void *dy, int dtype, int B, int H, int W, int C,
-                    int storage_pad, const float *shift, const float *a, const float *b,
+                    int storage_pad, int dy_pad, const float *shift, const float *a, const float *b,
                     const float *mean, const float *rstd, int relu, float *s1, float *s2,
                     void *workspace, size_t workspace_bytes, void *stream);
 int asis_bn_apply(int mode, const void *x, const void *dy, int in_dtype, void *out, int out_dtype,
-                  int B, int H, int W, int C, int pad_in, int pad_out, const float *a, const float *b,
-                  const float *mean, const float *rstd, const float *c1, const float *c2, int relu,
-                  void *stream);
+                  int B, int H, int W, int C, int pad_in, int pad_out, int dy_pad, const float *a,
+                  const float *b, const float *mean, const float *rstd, const float *c1, const float *c2,
+                  int relu, void *stream);
 
 /* nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (encoders.py:20): idx [same shape as y] u8 = winning tap
  * (first maximum in window order, as ATen); the backward is a gather over the <= 4 windows of an input pixel. */
@@ -254,15 +272,20 @@ int asis_maxpool3x3s2_forward(const void *x, void *y, uint8_t *idx, int dtype, i
 int asis_maxpool3x3s2_backward(const void *gy, const uint8_t *idx, void *gx, int dtype, int B, int H,
                                int W, int C, int pad_in, int pad_out, void *stream);
 
-/* 3x3 / stride 1 / pad 1 convolution with 1..4 output channels (final_out, decoders.py:129: its column
- * matrix would be 12 x 672^2 x 576 elements): direct kernels.  x [B,H,W,C] plain, w [CO,3,3,C] f32,
- * y / gy [B,H,W,CO] f32; backward: gx (x's dtype, optional), gw [CO,3,3,C] f32 (optional). */
-int asis_smallconv3x3_forward(const void *x, int dtype, const float *w, const float *bias, float *y,
-                              int B, int H, int W, int C, int CO, void *stream);
-size_t asis_smallconv3x3_backward_workspace_bytes(int B, int H, int W, int C, int CO);
-int asis_smallconv3x3_backward(const void *x, int dtype, const float *w, const float *gy, void *gx,
-                               float *gw, int B, int H, int W, int C, int CO, void *workspace,
-                               size_t workspace_bytes, void *stream);
+/* Segmentation head: nn.Upsample(scale_factor=2, bilinear, align_corners=True) followed by the 3x3 / pad 1
+ * convolution to n_classes <= 4 (decoders.py:125-129: the resize of decoder_4 + final_out), fused.  Both are linear
+ * and the resize acts per channel, so the C -> n_classes contraction runs FIRST, at the low resolution, and the
+ * high-resolution pass interpolates and adds the nine shifted taps: the upsampled C-channel map (694 MB at the
+ * reference's sizes) and its gradient are never materialised.
+ *   z [B,H,W,C] channels-last, w2 [9*CO, C] f32 with row (ky*3 + kx)*CO + co, bias [CO] f32 or null,
+ *   y / gy [B,2H,2W,CO] f32;  backward: gz (z's dtype, optional), gw2 [9*CO, C] f32 (optional). */
+size_t asis_seg_head_workspace_bytes(int B, int H, int W, int C, int CO);
+int asis_seg_head_forward(const void *z, int dtype, const float *w2, const float *bias, float *y, int B,
+                          int H, int W, int C, int CO, void *workspace, size_t workspace_bytes,
+                          void *stream);
+int asis_seg_head_backward(const void *z, int dtype, const float *w2, const float *gy, void *gz,
+                           float *gw2, int B, int H, int W, int C, int CO, void *workspace,
+                           size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }
