@@ -253,13 +253,19 @@ def batch_norm(x, bn, relu=True, out_dtype=None, pad_in=0, pad_out=0):
     return BatchNormFunction.apply(x, bn.weight, bn.bias, bn, relu, out_dtype, pad_in, pad_out)
 
 
-def conv_bn_relu(x, conv, bn, x_pad=0, out_pad=0):
-    """relu(bn(conv(x))) on channels-last maps; x_pad = 1: x is zero-padded storage and `conv` runs as the implicit GEMM."""
+def conv_bn_relu(x, conv, bn, x_pad=0, out_pad=0, record=None, name=None):
+    """relu(bn(conv(x))) on channels-last maps; x_pad = 1: x is zero-padded storage and `conv` runs as the implicit GEMM.
+    ``record`` (parity tests): dict that receives the ReLU mask of the layer as ``record[name]`` [B, C, H, W] bool."""
     if x_pad:
         y = conv3x3_padded(x, conv.weight, conv.bias)
     else:
         y = conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])
-    return batch_norm(y, bn, relu=True, pad_in=x_pad, pad_out=out_pad)
+    y = batch_norm(y, bn, relu=True, pad_in=x_pad, pad_out=out_pad)
+    if record is not None:
+        z = y.detach()
+        z = z[:, out_pad:z.shape[1] - out_pad, out_pad:z.shape[2] - out_pad]
+        record[name] = (z > 0).permute(0, 3, 1, 2)
+    return y
 
 
 class MaxPoolFunction(Function):

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) col2im_kernel(const T *__restrict__ dcols
 
 // ---- per-channel statistics -------------------------------------------------------------------------
 // block (by) owns a strip of pixels; thread (tx) owns one channel vector and strides over the strip's pixels with
-// ty: partial[(by*TY + ty), 0:C] = sum (x - shift), partial[.., C:2C] = sum (x - shift)^2 over the logical pixels.
+// ty (PL = 256 / cl pixel lanes): partial[(by*PL + ty), 0:C] = sum (x - shift), partial[.., C:2C] = sum (x - shift)^2 over the logical pixels.
 // mode 1 (backward): sums of dz and dz * xhat with dz = dy * relu'(a (x - mean) + b), xhat = (x - mean) * rstd.
 struct StatArgs {
   int B, H, W, C, sp, sp_dy;              // storage padding of x and of dy
@@ -164,14 +164,16 @@ struct StatArgs {
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) chan_stats_kernel(const T *__restrict__ x, const T *__restrict__ dy, float *__restrict__ partial,
-                                                         const StatArgs s, int pix_per_block) {
+                                                         const StatArgs s, int pix_per_block, int cl) {
   constexpr int N = CVec<T>::N;
   const int CV = s.C / N;
-  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // 32 channel vectors x 8 pixel lanes
-  const int Hs = s.H + 2 * s.sp, Ws = s.W + 2 * s.sp;
+  // cl channel-vector lanes x (256 / cl) pixel lanes: a 64-channel bf16 map has only 8 channel vectors, so a fixed 32 x 8
+  // split left three quarters of the threads idle on the largest maps of the step (stem, decoder_4)
+  const int tx = threadIdx.x % cl, ty = threadIdx.x / cl, PL = 256 / cl;
+  const int Hs = s.H + 2 * s.sp, Ws = s.W + 2 * s.sp, Hd = s.H + 2 * s.sp_dy, Wd = s.W + 2 * s.sp_dy;
   const size_t npix = (size_t)s.B * s.H * s.W;
   const size_t p0 = (size_t)blockIdx.x * pix_per_block, p1 = min(npix, p0 + pix_per_block);
-  for (int cv = blockIdx.y * 32 + tx; cv < CV; cv += gridDim.y * 32) {
+  for (int cv = blockIdx.y * cl + tx; cv < CV; cv += gridDim.y * cl) {
     float k0[N], k1[N], k2[N], k3[N], s1[N], s2[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) { s1[i] = s2[i] = 0.f; }
@@ -184,33 +186,42 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const T *__restrict__ x
         k0[i] = s.a[cv * N + i]; k1[i] = s.b[cv * N + i]; k2[i] = s.mean[cv * N + i]; k3[i] = s.rstd[cv * N + i];
       }
     }
-    for (size_t p = p0 + ty; p < p1; p += 8) {
-      const int ix = (int)(p % s.W);
-      const size_t q = p / s.W;
-      const int iy = (int)(q % s.H);
-      const size_t b = q / s.H;
-      const size_t off = ((b * Hs + iy + s.sp) * Ws + ix + s.sp) * s.C + (size_t)cv * N;
-      float v[N];
-      CVec<T>::load(x + off, v);
-      if (MODE == 0) {
+    for (size_t pa = p0 + ty; pa < p1; pa += 2 * PL) {           // two pixels per iteration: twice the loads in flight
+      float v[2][N], g[2][N];
+      bool ok[2];
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const float d = v[i] - k0[i];
-          s1[i] += d;
-          s2[i] = fmaf(d, d, s2[i]);
-        }
-      } else {
-        float g[N];
-        CVec<T>::load(dy + ((b * (s.H + 2 * s.sp_dy) + iy + s.sp_dy) * (s.W + 2 * s.sp_dy) + ix + s.sp_dy) * s.C + (size_t)cv * N, g);
+      for (int u = 0; u < 2; ++u) {
+        const size_t p = pa + (size_t)u * PL;
+        ok[u] = p < p1;
+        const size_t pc = ok[u] ? p : pa;
+        const int ix = (int)(pc % s.W);
+        const size_t q = pc / s.W;
+        const int iy = (int)(q % s.H);
+        const size_t b = q / s.H;
+        CVec<T>::load(x + ((b * Hs + iy + s.sp) * Ws + ix + s.sp) * s.C + (size_t)cv * N, v[u]);
+        if (MODE == 1) CVec<T>::load(dy + ((b * Hd + iy + s.sp_dy) * Wd + ix + s.sp_dy) * s.C + (size_t)cv * N, g[u]);
+      }
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const float dz = (s.relu && fmaf(k0[i], v[i] - k2[i], k1[i]) <= 0.f) ? 0.f : g[i];
-          s1[i] += dz;
-          s2[i] = fmaf(dz, (v[i] - k2[i]) * k3[i], s2[i]);
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        if (MODE == 0) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const float d = v[u][i] - k0[i];
+            s1[i] += d;
+            s2[i] = fmaf(d, d, s2[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const float dz = (s.relu && fmaf(k0[i], v[u][i] - k2[i], k1[i]) <= 0.f) ? 0.f : g[u][i];
+            s1[i] += dz;
+            s2[i] = fmaf(dz, (v[u][i] - k2[i]) * k3[i], s2[i]);
+          }
         }
       }
     }
-    float *dst = partial + ((size_t)blockIdx.x * 8 + ty) * 2 * s.C + (size_t)cv * N;
+    float *dst = partial + ((size_t)blockIdx.x * PL + ty) * 2 * s.C + (size_t)cv * N;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       dst[i] = s1[i];
@@ -572,12 +583,66 @@ __global__ void __launch_bounds__(128) head_project_dgrad_kernel(const float *__
   }
 }
 
-// dw2[t, c] = sum_p dU[p, t] * z[p, c]: a block owns a strip of pixels, a thread up to HEAD_WG outputs (t, c) with
-// c fastest across the threads (coalesced z reads); partial[block, NT*C], then conv_reduce_partials_kernel
+// dw2[t, c] = sum_p dU[p, t] * z[p, c]: a block owns a strip of pixels, a WARP one pixel at a time (4 in flight), a lane
+// CPL = C / 32 adjacent channels with all NT tap accumulators in registers: per pixel one coalesced row load of z and NT
+// warp-uniform (broadcast) loads of dU feed NT * CPL FMAs per lane.  Warps are combined through shared memory in a fixed
+// order, blocks through partial[block, NT*C] + conv_reduce_partials_kernel.  (The first version gave every thread five
+// scattered (t, c) outputs and two dependent loads per FMA: 5.0 ms at the reference's sizes, 3.5 % of the step.)
+template <typename T, int NT, int CPL>
+__global__ void __launch_bounds__(256) head_project_wgrad_kernel(const float *__restrict__ dU, const T *__restrict__ z, float *__restrict__ partial,
+                                                                 size_t R, int pix_per_block) {
+  constexpr int C = 32 * CPL;
+  __shared__ float red[8][CPL][33];                 // one tap at a time: [warp][i][lane] (+1: conflict-free column reads)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float acc[NT][CPL];
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) acc[t][i] = 0.f;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_block, p1 = min(R, p0 + pix_per_block);
+  constexpr int UN = 4;
+  for (size_t pb = p0 + warp * UN; pb < p1; pb += 8 * UN) {
+    float zv[UN][CPL], du[UN][NT];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const size_t p = pb + u;
+      const bool ok = p < p1;
+      const size_t pc = ok ? p : p0;                 // (clamped address; the contribution is zeroed below)
+      const T *zp = z + pc * C + lane * CPL;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) zv[u][i] = ok ? to_f(zp[i]) : 0.f;
+      const float *dp = dU + pc * NT;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) du[u][t] = __ldg(dp + t);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) acc[t][i] = fmaf(du[u][t], zv[u][i], acc[t][i]);
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) red[warp][i][lane] = acc[t][i];
+    __syncthreads();
+    if (threadIdx.x < C) {                           // channel c = l * CPL + i, warps added in a fixed order
+      const int l = threadIdx.x / CPL, i = threadIdx.x % CPL;
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) a += red[w][i][l];
+      partial[(size_t)blockIdx.x * (NT * C) + t * C + threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+}
+
+// generic shape (any C): a block owns a strip of pixels, a thread up to HEAD_WG outputs (t, c), c fastest across the threads
 constexpr int HEAD_WG = 20;
 template <typename T>
-__global__ void __launch_bounds__(256) head_project_wgrad_kernel(const float *__restrict__ dU, const T *__restrict__ z, float *__restrict__ partial,
-                                                                 size_t R, int C, int NT, int pix_per_block) {
+__global__ void __launch_bounds__(256) head_project_wgrad_generic_kernel(const float *__restrict__ dU, const T *__restrict__ z,
+                                                                         float *__restrict__ partial, size_t R, int C, int NT, int pix_per_block) {
   const int nout = NT * C;
   float acc[HEAD_WG];
   int oc[HEAD_WG], ot[HEAD_WG];
@@ -664,7 +729,14 @@ static int stat_blocks(size_t npix, int &ppb) {
 extern "C" size_t asis_chan_stats_workspace_bytes(int B, int H, int W, int C) {
   int ppb;
   const int nb = stat_blocks((size_t)B * H * W, ppb);
-  return (size_t)nb * 8 * 2 * C * sizeof(float);
+  return (size_t)nb * 64 * 2 * C * sizeof(float);       // up to 64 pixel lanes per block (stat_lanes)
+}
+
+// channel-vector lanes of a block: the largest power of two <= min(32, CV), at least 4
+static int stat_lanes(int CV) {
+  int cl = 32;
+  while (cl > 4 && cl > CV) cl >>= 1;
+  return cl;
 }
 
 // mode 0: s1 = sum (x - shift), s2 = sum (x - shift)^2.   mode 1: s1 = sum dz, s2 = sum dz * xhat (see StatArgs).
@@ -683,16 +755,17 @@ extern "C" int asis_chan_stats(int mode, const void *x, const void *dy, int dtyp
   const int nb = stat_blocks((size_t)B * H * W, ppb);
   StatArgs s{B, H, W, C, storage_pad, dy_pad, shift, a, b, mean, rstd, relu};
   const int CV = C / NV;
-  dim3 grid(nb, (CV + 31) / 32 > 8 ? 8 : (CV + 31) / 32);
+  const int cl = stat_lanes(CV), PL = 256 / cl;
+  dim3 grid(nb, (CV + cl - 1) / cl > 8 ? 8 : (CV + cl - 1) / cl);
   cudaStream_t st = (cudaStream_t)stream;
   float *partial = (float *)workspace;
   if (mode == 0) {
-    ASIS_DISPATCH_DTYPE(dtype, T, (chan_stats_kernel<T, 0><<<grid, 256, 0, st>>>((const T *)x, nullptr, partial, s, ppb)));
+    ASIS_DISPATCH_DTYPE(dtype, T, (chan_stats_kernel<T, 0><<<grid, 256, 0, st>>>((const T *)x, nullptr, partial, s, ppb, cl)));
   } else {
-    ASIS_DISPATCH_DTYPE(dtype, T, (chan_stats_kernel<T, 1><<<grid, 256, 0, st>>>((const T *)x, (const T *)dy, partial, s, ppb)));
+    ASIS_DISPATCH_DTYPE(dtype, T, (chan_stats_kernel<T, 1><<<grid, 256, 0, st>>>((const T *)x, (const T *)dy, partial, s, ppb, cl)));
   }
   ASIS_LAUNCHED();
-  conv_reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nb * 8, 2 * C, s1);
+  conv_reduce_partials_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial, nb * PL, 2 * C, s1);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }
@@ -826,7 +899,9 @@ static int seg_head_bwd(const void *z, const float *w2, const float *gy, void *g
   if (gw2) {
     const int nb = (int)std::min<size_t>((R + 1023) / 1024, 592);
     const int ppb = (int)((R + nb - 1) / nb);
-    head_project_wgrad_kernel<T><<<nb, 256, 0, st>>>(dU, (const T *)z, partial, R, C, NT, ppb);
+    if (C == 64) head_project_wgrad_kernel<T, NT, 2><<<nb, 256, 0, st>>>(dU, (const T *)z, partial, R, ppb);
+    else if (C == 128) head_project_wgrad_kernel<T, NT, 4><<<nb, 256, 0, st>>>(dU, (const T *)z, partial, R, ppb);
+    else head_project_wgrad_generic_kernel<T><<<nb, 256, 0, st>>>(dU, (const T *)z, partial, R, C, NT, ppb);
     ASIS_LAUNCHED();
     conv_reduce_partials_kernel<<<(NT * C + 31) / 32, 256, 0, st>>>(partial, nb, NT * C, gw2);
     ASIS_LAUNCHED();

@@ -41,6 +41,7 @@ struct GemmTcParams {
   int M, N, K;
   int m_tiles, m_groups, n_tiles, splits, kb_per_split, kb_total;
   int atomic_out;  // split-K: combine with red.global.add.f32
+  int n_mma;       // pair kernel: N of the MMA instruction (256; 128 / 64 for narrow outputs -- each CTA stages n_mma / 2 rows of B)
   // 3x3 / stride-1 convolution as an implicit GEMM over a zero-padded channels-last map (pair kernel only): the K loop
   // runs over (tap, channel block); tap t reads the A rows shifted by conv_a_row_off[t] (TMA zero-fills rows outside
   // the tensor) -- "im2col by TMA coordinates", no column matrix in memory.
@@ -718,7 +719,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int split = rest / p.m_groups;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-      const int n0 = n_blk * BN + crank * (BN / 2);            // this CTA's half of the B tile
+      const int n0 = n_blk * BN + crank * (p.n_mma / 2);       // this CTA's half of the B tile
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar + stage, phase ^ 1);
         if (kb == kb0) GEMM_TRACE(5, tile / num_clusters);
@@ -767,7 +768,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == MMA_WARP) {
     if (leader) {
-      constexpr uint32_t idesc = make_idesc(2 * BM, BN, A_MN, B_MN);
+      const uint32_t idesc = make_idesc(2 * BM, p.n_mma, A_MN, B_MN);
       const uint32_t smem_base = smem_u32(smem);
       int stage = 0;
       uint32_t phase = 0;
@@ -1029,6 +1030,14 @@ static int cluster_pref() {
   return v;
 }
 
+// narrow outputs (the N = 64 / 128 convolutions and adapter projections): a 256-wide MMA would spend 4x / 2x the tensor
+// time on columns nobody stores.  MN-major B comes in 64-column boxes, one per CTA at least: 128 is its minimum.
+static int pick_n_mma(int N, int b_major) {
+  if (N <= 64 && b_major == ASIS_MAJOR_K) return 64;
+  if (N <= 128) return 128;
+  return BN;
+}
+
 // 3x3 / stride 1 / pad 1 convolution pieces as implicit GEMMs over zero-padded channels-last maps
 //   op 0 forward: y_p[R, Cout] = sum_t x_p[R + off_t, Cin] . W_t^T      A = x_p, B = w2 [Cout, 9 Cin] (K-major)
 //   op 1 dgrad:   dx_p[R, Cin] = sum_t dy_p[R - off_t, Cout] . W_t      A = dy_p, B = w2 read MN-major (rows = Cout)
@@ -1049,6 +1058,7 @@ int gemm_tc_conv3x3(int op, const void *a, const void *b, void *c, int c_dtype, 
     ASIS_REQUIRE(c_dtype == ASIS_F32, "conv3x3_gemm: the weight gradient is f32");
     GemmTcParams p{};
     p.M = Cout; p.N = 9 * Cin; p.K = R;
+    p.n_mma = BN;
     p.m_tiles = (Cout + BM - 1) / BM;
     p.n_tiles = (p.N + BN - 1) / BN;
     p.kb_total = (R + BK - 1) / BK;
@@ -1078,6 +1088,7 @@ int gemm_tc_conv3x3(int op, const void *a, const void *b, void *c, int c_dtype, 
   const int Nn = op == 0 ? Cout : Cin;
   GemmTcParams p{};
   p.M = R; p.N = Nn; p.K = 9 * Ck;
+  p.n_mma = pick_n_mma(Nn, op == 0 ? ASIS_MAJOR_K : ASIS_MAJOR_MN);
   p.m_tiles = (R + BM - 1) / BM;
   p.n_tiles = (Nn + BN - 1) / BN;
   p.kb_total = 9 * (Ck / BK);
@@ -1110,6 +1121,7 @@ int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b
   ASIS_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "gemm(bf16): lda=%lld, ldb=%lld must be multiples of 8 elements (TMA 16-byte pitch)", (long long)lda, (long long)ldb);
   GemmTcParams p{};
   p.M = M; p.N = N; p.K = K;
+  p.n_mma = pick_n_mma(N, b_major);
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = (N + BN - 1) / BN;
   p.kb_total = (K + BK - 1) / BK;

@@ -30,8 +30,9 @@ class FeatureDecoder(nn.Module):
                 nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)))
         self.final_out = nn.Conv2d(features[4], num_classes, 3, padding=1)
 
-    def forward(self, x):
-        """x [B, 3*embed_dim, h, w] (any memory format; channels-last is free) -> logits [B, num_classes, 16h, 16w] f32."""
+    def forward(self, x, record=None):
+        """x [B, 3*embed_dim, h, w] (any memory format; channels-last is free) -> logits [B, num_classes, 16h, 16w] f32.
+        ``record`` (parity tests): dict that receives every layer's ReLU mask under its BatchNorm's key prefix."""
         x = x.permute(0, 2, 3, 1).contiguous()          # (asis_im2col converts to the compute dtype on the way)
         fused_head = self.num_classes <= 4
         imp = [int(Cv.implicit_ok(getattr(self, f"decoder_{k}")[0])) for k in range(1, 5)] + [0]
@@ -39,7 +40,7 @@ class FeatureDecoder(nn.Module):
             x = Cv.repad(x, 0, 1, torch.bfloat16)
         for k in range(1, 5):
             conv, bn, _, _ = getattr(self, f"decoder_{k}")
-            x = Cv.conv_bn_relu(x, conv, bn, imp[k - 1], 0)
+            x = Cv.conv_bn_relu(x, conv, bn, imp[k - 1], 0, record, f"decoder_{k}.1.")
             if k < 4 or not fused_head:
                 x = Fn.upsample2x_nhwc(x, 0, imp[k] if k < 4 else 0)
         if fused_head:      # decoder_4's resize + final_out as one node: the 64-channel 672 x 672 map is never built

@@ -25,11 +25,6 @@ def _cbr(cin, cout, stride, padding):
             nn.SyncBatchNorm(cout), nn.ReLU(inplace=True)]
 
 
-def _conv_bn_relu(x, conv, bn):
-    y = Cv.conv2d(x, conv.weight, conv.bias, conv.stride[0], conv.padding[0])
-    return Cv.batch_norm(y, bn, relu=True)
-
-
 class FeatureEncoder(nn.Module):
     def __init__(self, inplanes=64, embed_dim=1024, with_cp=False):
         super().__init__()
@@ -51,18 +46,19 @@ class FeatureEncoder(nn.Module):
         B, H, W, C = c.shape
         return Fn.linear(c.reshape(B, H * W, C), fc.weight.view(fc.out_channels, C), fc.bias, out_dtype=torch.float32)
 
-    def forward(self, x, need_c1=True):
-        """x [B, 3, H, W] (as the reference) -> (c1 [B, D, H/4, W/4] or None, c2, c3, c4 tokens [B, n, D])."""
+    def forward(self, x, need_c1=True, record=None):
+        """x [B, 3, H, W] (as the reference) -> (c1 [B, D, H/4, W/4] or None, c2, c3, c4 tokens [B, n, D]).
+        ``record`` (parity tests): dict that receives every layer's ReLU mask under its BatchNorm's key prefix."""
         x = x.permute(0, 2, 3, 1).contiguous().float()                   # channels-last image
         s = self.stem
         p3, p6 = int(Cv.implicit_ok(s[3])), int(Cv.implicit_ok(s[6]))     # bf16 mode: implicit GEMMs over zero-padded maps
-        x = Cv.conv_bn_relu(x, s[0], s[1], 0, p3)
-        x = Cv.conv_bn_relu(x, s[3], s[4], p3, p6)
-        x = Cv.conv_bn_relu(x, s[6], s[7], p6, 0)
+        x = Cv.conv_bn_relu(x, s[0], s[1], 0, p3, record, "stem.1.")
+        x = Cv.conv_bn_relu(x, s[3], s[4], p3, p6, record, "stem.4.")
+        x = Cv.conv_bn_relu(x, s[6], s[7], p6, 0, record, "stem.7.")
         c1 = Cv.maxpool3x3s2(x)
-        c2 = _conv_bn_relu(c1, self.conv2[0], self.conv2[1])
-        c3 = _conv_bn_relu(c2, self.conv3[0], self.conv3[1])
-        c4 = _conv_bn_relu(c3, self.conv4[0], self.conv4[1])
+        c2 = Cv.conv_bn_relu(c1, self.conv2[0], self.conv2[1], 0, 0, record, "conv2.1.")
+        c3 = Cv.conv_bn_relu(c2, self.conv3[0], self.conv3[1], 0, 0, record, "conv3.1.")
+        c4 = Cv.conv_bn_relu(c3, self.conv4[0], self.conv4[1], 0, 0, record, "conv4.1.")
         o1 = None
         if need_c1:        # fc1(c1) feeds nothing downstream in train.py (:279, then unused); need_c1=False skips it
             B, H, W, _ = c1.shape

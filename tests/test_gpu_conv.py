@@ -163,111 +163,88 @@ def _torch_spm(inplanes, embed_dim):
     return m
 
 
-def _yardstick(ref64, mode, run):
-    """errors of the STOCK modules at the same precision (fp32, or bf16 autocast) against the fp64 run: BatchNorm over a
-    few hundred samples amplifies rounding differences, and ReLU'(0) is a discontinuity: a pre-activation within ~1e-6
-    of zero takes the other branch in ANY fp32 evaluation (tools/spm_debug.py counts 1-3 such flips per layer for the
-    stock fp32 modules and for ours alike, at different pixels), which moves one channel's sum of dz by 0.1-3 %.  So
-    the chain tests hold gradients to max(floor, 3 x the stock modules' own error at the same precision), floor 1e-2;
-    the 1e-4 bound is enforced per node above, where no discontinuity is chained."""
-    import copy
-    m = copy.deepcopy(ref64).float()
-    if mode == "bf16":
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            return run(m, torch.float32)
-    return run(m, torch.float32)
+def _sd64(module):
+    return {k: (v.detach().double().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+            for k, v in module.state_dict().items()}
 
 
-def _check(names, ours, stock, ref64, floor, factor=3.0, skip=()):
+def _grad_check(names, ours, sd, tol, skip=()):
     bad = []
-    for n, a, s_, r in zip(names, ours, stock, ref64):
-        if n.endswith(skip) or float(r.abs().max()) < 1e-12:
+    for n, a in zip(names, ours):
+        r = sd[n].grad
+        if n.endswith(skip) or r is None or float(r.abs().max()) < 1e-12:
             continue
-        e, es = relerr(a.float(), r), relerr(s_.float(), r)
-        if not e < max(floor, factor * es):
-            bad.append((n, e, es))
+        e = relerr(a.float(), r)
+        if not e < tol:
+            bad.append((n, e))
     assert not bad, bad
 
 
-def _run_spm(m, dt, x, gs):
-    c1 = m.stem(x.to(dt))
-    c2 = m.conv2(c1)
-    c3 = m.conv3(c2)
-    c4 = m.conv4(c3)
-    outs = [f(c).flatten(2).transpose(1, 2) for f, c in ((m.fc2, c2), (m.fc3, c3), (m.fc4, c4))]
-    names = [n for n, _ in m.named_parameters() if not n.startswith("fc1")]
-    gr = torch.autograd.grad(outs, [dict(m.named_parameters())[n] for n in names], [g.to(o.dtype) for g, o in zip(gs, outs)])
-    return names, [o.detach() for o in outs], gr
-
-
-@pytest.mark.parametrize("mode,tol,gfloor", [("fp32", 1e-4, 1e-2), ("bf16", 2e-2, 2e-2)])
-def test_spatial_prior_module_vs_torch(mode, tol, gfloor):
-    """FeatureEncoder end to end (stem, three stride-2 stages, 1x1 projections) at 292 x 292: outputs and every parameter
-    gradient against the stock-module stack with the same state_dict, evaluated in fp64."""
+# Gradient parity of the two layer stacks.  ReLU' is discontinuous at 0: a pre-activation within rounding distance of
+# zero takes the other branch in ANY two fp32 evaluations (tools/spm_debug.py: 1-3 such elements per layer for the stock
+# fp32 modules and for ours alike, at different pixels), and on these small maps one flipped element moves a channel's
+# gradients by 1-3 %.  So the fp64 oracle (oracle/encoder.py, the reference's layer stack restated) is evaluated twice:
+# with its own ReLU for the forward outputs, and ON THE MASKS OF THE RUN UNDER TEST for the gradients -- the function is
+# then smooth and the bound is the plain one: 1e-4 on outputs, 2e-3 on parameter gradients (1e5-term fp32 sums) in fp32
+# mode; 2e-2 / 3e-2 in bf16 mode.  The spatial prior module keeps one more discontinuity the masks do not remove -- the
+# arg-max of the stem's 3x3 max pooling between near-equal neighbours (~1 of 7e5 windows) -- and is six bf16 layers deep:
+# 1e-2 on its gradients in fp32 mode (measured 6e-3 on stem.6.weight, everything else < 1e-3), 3e-2 / 4e-2 in bf16 mode.
+@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 1e-2), ("bf16", 3e-2, 4e-2)])
+def test_spatial_prior_module_vs_oracle(mode, tol, gtol):
+    """FeatureEncoder end to end (stem, three stride-2 stages, 1x1 projections) at 292 x 292, batch 2."""
     import adaptersis_b200 as asis
     from adaptersis_b200.encoders import FeatureEncoder
+    from oracle import encoder as o_enc
     torch.manual_seed(6)
-    ref = _torch_spm(64, 128).to(DEV).double()
     ours = FeatureEncoder(inplanes=64, embed_dim=128).to(DEV)
-    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()}, strict=True)
-    x = torch.rand(2, 3, 292, 292, device=DEV)
     with torch.no_grad():
-        shapes = [o.shape for o in _run_spm_fwd_shapes(ref, x)]
-    gs = [torch.randn(s, device=DEV) for s in shapes]
-    names, outs_r, gr = _run_spm(ref, torch.float64, x, gs)
-    _, outs_s, gst = _yardstick(ref, mode, lambda m, dt: _run_spm(m, dt, x, gs))
+        for n, p in ours.named_parameters():           # BatchNorm away from its (1, 0) initialisation
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.rand(2, 3, 292, 292, device=DEV)
+    names = [n for n, _ in ours.named_parameters() if not n.startswith("fc1")]
+    rec = {}
     with asis.precision(mode):
-        _, o2, o3, o4 = ours(x, need_c1=False)
+        _, o2, o3, o4 = ours(x, need_c1=False, record=rec)
+        gs = [torch.randn_like(o) for o in (o2, o3, o4)]
         go = torch.autograd.grad([o2, o3, o4], [dict(ours.named_parameters())[n] for n in names], gs)
-    for a, s_, b in zip((o2, o3, o4), outs_s, outs_r):
-        assert a.shape == b.shape and relerr(a.float(), b) < max(tol, 3 * relerr(s_.float(), b))
-    _check(names, go, gst, gr, gfloor)
+    assert sorted(rec) == ["conv2.1.", "conv3.1.", "conv4.1.", "stem.1.", "stem.4.", "stem.7."]
+    sd = _sd64(ours)
+    with torch.no_grad():
+        fwd = o_enc.spm(sd, x.double())[1:]
+    for a, b in zip((o2, o3, o4), fwd):
+        assert a.shape == b.shape and relerr(a.float(), b) < tol
+    outs = o_enc.spm(sd, x.double(), relu_masks=rec)[1:]
+    torch.autograd.backward(outs, [g.double() for g in gs])
+    _grad_check(names, go, sd, gtol)
 
 
-def _run_spm_fwd_shapes(m, x):
-    c1 = m.stem(x.double())
-    c2 = m.conv2(c1)
-    c3 = m.conv3(c2)
-    c4 = m.conv4(c3)
-    return [f(c).flatten(2).transpose(1, 2) for f, c in ((m.fc2, c2), (m.fc3, c3), (m.fc4, c4))]
-
-
-def _run_dec(m, dt, x, gy):
-    xr = x.to(dt).clone().requires_grad_(True)
-    h = xr
-    for k in range(1, 5):
-        h = getattr(m, f"decoder_{k}")(h)
-    y = m.final_out(h)
-    names = [n for n, _ in m.named_parameters()]
-    g = torch.autograd.grad(y, [xr] + [dict(m.named_parameters())[n] for n in names], gy.to(y.dtype))
-    return names, y.detach(), g
-
-
-@pytest.mark.parametrize("mode,tol,gfloor", [("fp32", 1e-4, 1e-2), ("bf16", 2e-2, 2e-2)])
-def test_feature_decoder_vs_torch(mode, tol, gfloor):
-    """FeatureDecoder (decoders.py:92-164) at a 10 x 10 token grid: logits, the input gradient and every parameter
-    gradient vs the stock-module stack evaluated in fp64."""
+@pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 2e-3), ("bf16", 2e-2, 3e-2)])
+def test_feature_decoder_vs_oracle(mode, tol, gtol):
+    """FeatureDecoder (decoders.py:92-164) at a 10 x 10 token grid: logits, the input gradient, every parameter gradient."""
     import adaptersis_b200 as asis
     from adaptersis_b200.decoders import FeatureDecoder
+    from oracle import encoder as o_enc
     torch.manual_seed(7)
     feats = [64, 128, 64, 64, 64]
     ours = FeatureDecoder(img_size=140, embed_dim=64, num_classes=2, features=feats).to(DEV)
-    chans = [feats[0] * 3] + feats[1:]
-    ref = nn.Module()
-    for k in range(1, 5):
-        setattr(ref, f"decoder_{k}", nn.Sequential(nn.Conv2d(chans[k - 1], chans[k], 3, padding=1), nn.BatchNorm2d(chans[k]),
-                                                   nn.ReLU(inplace=True), nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)))
-    ref.final_out = nn.Conv2d(feats[4], 2, 3, padding=1)
-    ref = ref.to(DEV).double()
-    ours.load_state_dict({k: v.float() for k, v in ref.state_dict().items()}, strict=True)
-    x = torch.randn(2, chans[0], 10, 10, device=DEV)
+    with torch.no_grad():
+        for n, p in ours.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    x = torch.randn(2, 3 * feats[0], 10, 10, device=DEV)
     gy = torch.randn(2, 2, 160, 160, device=DEV)
-    names, yr, gr = _run_dec(ref, torch.float64, x, gy)
-    _, ys, gst = _yardstick(ref, mode, lambda m, dt: _run_dec(m, dt, x, gy))
+    names = [n for n, _ in ours.named_parameters()]
+    rec = {}
     xo = x.clone().requires_grad_(True)
     with asis.precision(mode):
-        y = ours(xo)
+        y = ours(xo, record=rec)
         go = torch.autograd.grad(y, [xo] + [dict(ours.named_parameters())[n] for n in names], gy)
-    assert y.shape == yr.shape and relerr(y.float(), yr) < max(tol, 3 * relerr(ys.float(), yr))
+    sd = _sd64(ours)
+    with torch.no_grad():
+        yr = o_enc.feature_decoder(sd, x.double())
+    assert y.shape == yr.shape and relerr(y.float(), yr) < tol
+    sd["input"] = x.double().requires_grad_(True)
+    o_enc.feature_decoder(sd, sd["input"], relu_masks=rec).backward(gy.double())
     # (a convolution bias in front of BatchNorm has an analytically zero gradient: rounding noise on both sides)
-    _check(["input"] + names, go, gst, gr, gfloor, skip=(".0.bias",))
+    _grad_check(["input"] + names, go, sd, gtol, skip=(".0.bias",))

@@ -172,7 +172,12 @@ def _compare(fs, mode, act_tol, grad_floor, grad_factor):
         e_t32 = relerr(o32["grads"][k], g64)
         rep["grads"][k] = dict(ours=e_ours, torch_same_precision=e_t32, numel=g64.numel())
         worst.append((e_ours, e_t32, k))
-        if not e_ours < max(grad_floor, grad_factor * e_t32):
+        # ReLU'(0) is a discontinuity: the convolutional stages (spm.*, dec.*) flip a handful of near-zero pre-activations
+        # in ANY fp32 evaluation -- the PyTorch yardstick included, at other pixels -- and each flip moves a channel's
+        # gradient by up to a few per cent, so a multiple of the yardstick's own (random) flip error is not a bound there.
+        # tests/test_gpu_conv.py holds those stacks to 2e-3 against the oracle evaluated on shared masks; here 5e-2.
+        floor_k = max(grad_floor, 5e-2) if k.startswith(("spm.", "dec.")) else grad_floor
+        if not e_ours < max(floor_k, grad_factor * e_t32):
             fails.append((k, e_ours, e_t32))
     worst.sort(reverse=True)
     rep["worst_grads"] = [dict(param=k, ours=a, torch_same_precision=b) for a, b, k in worst[:8]]

@@ -17,7 +17,8 @@ TOL = 2e-2
 GEMM_TOL = 2e-3      # fp32 accumulation of exact bf16 products: only summation order differs
 
 
-@pytest.mark.parametrize("M,N,K_", [(128, 256, 64), (300, 200, 136), (1765, 1024, 1024), (2000, 96, 1024), (70, 32, 40)])
+@pytest.mark.parametrize("M,N,K_", [(128, 256, 64), (300, 200, 136), (1765, 1024, 1024), (2000, 96, 1024), (70, 32, 40),
+                                    (1000, 64, 192), (600, 128, 576), (2000, 48, 320)])      # narrow N: 64- / 128-wide MMAs
 @pytest.mark.parametrize("am,bm", [(MAJOR_K, MAJOR_K), (MAJOR_K, MAJOR_MN), (MAJOR_MN, MAJOR_MN), (MAJOR_MN, MAJOR_K)])
 def test_gemm_tc_majors(M, N, K_, am, bm):
     torch.manual_seed(0)
