@@ -529,7 +529,7 @@ constexpr int F8_STAGES = 4;
 constexpr int F8_SMEM = 2 * 2 * T16K /*Q: 2 warpgroups x 2 buffers*/ + F8_STAGES * 2 * T16K /*K, V rings*/ + 1024 /*align*/ + 512 /*barriers*/;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const int num_items, const int npair) {
+attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, const int num_items, const int npair, const int stagger) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sQ = smem;                            // [buffer][warpgroup] tiles
@@ -542,6 +542,9 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, 
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(o_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef ASIS_TRACE
+  unsigned long long *tr = g_attn_trace;
+#endif
   constexpr int TMA_WARP = 8, MMA_WARP = 9;      // the SMSP arbiter favours the highest warp id (see v7b)
   const int C = p.H * HD;
   const int nkv = (p.T + TILE - 1) / TILE;
@@ -619,56 +622,82 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, 
     constexpr uint32_t idesc_o = make_idesc(TILE, HD, 0, 1);     // O = P V   : V is MN-major
     const uint64_t dQ = desc_kmajor(smem_u32(sQ), 0), dK = desc_kmajor(smem_u32(sK), 0), dV = desc_mnmajor(smem_u32(sV), 0);
     constexpr uint32_t STAGE16 = T16K >> 4;
-    // incremental (item, tile, stage, phase) counters of the score stream (one tile ahead) and of the P V stream
-    struct Stream { int g, k, j, st; uint32_t ph; } ss{0, 0, 0, 0, 0}, ps{0, 0, 0, 0, 0};
+    // Event-driven issue: each warpgroup has its own score stream (one tile ahead of its softmax) and its own P V
+    // stream; the warp polls the barriers of both and issues whatever is ready.  (The first v8 walked the tiles in a
+    // fixed order -- S(g+1) for both warpgroups, then P V(g) for w = 0, then for w = 1 -- which re-aligned the two
+    // warpgroups every tile: they ran in lockstep, both in the MUFU-bound exponential phase for ~2400 clk, then both in
+    // the load / max / wait phases for ~1000 clk with the MUFU pipe idle.  Decoupled, the warpgroup that wins the MUFU
+    // arbitration pulls ahead and the phases interleave by themselves.)
+    // A K (V) stage is released by whichever warpgroup issues its S (P V) of that tile second; tcgen05.commit covers
+    // all earlier MMAs of this thread, so the release is ordered after both.
+    struct Stream { int g, k, j, st; uint32_t ph; };
+    Stream ss[2] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}}, ps[2] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
     auto step = [&](Stream &x) {
       ++x.g;
       if (++x.j == nkv) { x.j = 0; ++x.k; }
       if (++x.st == F8_STAGES) { x.st = 0; x.ph ^= 1; }
     };
-    auto issue_s = [&]() {              // S_w(g) = Q_w K(g)^T for both warpgroups
-      const int qbuf = ss.k & 1;
-      if (ss.j == 0) mbar_wait_wd(q_full + qbuf, (ss.k >> 1) & 1);
-      mbar_wait_wd(k_full + ss.st, ss.ph);
+    long long t_idle = 0;
+    while (ps[0].g < G || ps[1].g < G) {
+      bool progress = false;
 #pragma unroll
       for (int w = 0; w < 2; ++w) {
-        if (ss.g > 0) mbar_wait_wd(s_free + w, (ss.g - 1) & 1);        // the softmax warps hold S_w(g-1) in registers
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t a = dQ + (uint32_t)((qbuf * 2 + w) * STAGE16), bdesc = dK + (uint32_t)(ss.st * STAGE16);
-          const uint32_t d = tmem + w * WG_COLS;
+        // ---- S_w(g) = Q_w K(g)^T: needs Q (first tile of an item), the K stage, and S_w(g-1) pulled into registers
+        Stream &x = ss[w];
+        if (x.g < G) {
+          const int qbuf = x.k & 1;
+          bool ok = mbar_test(k_full + x.st, x.ph);
+          if (ok && x.j == 0) ok = mbar_test(q_full + qbuf, (x.k >> 1) & 1);
+          if (ok && x.g > 0) ok = mbar_test(s_free + w, (x.g - 1) & 1);
+          if (ok) {
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t a = dQ + (uint32_t)((qbuf * 2 + w) * STAGE16), bdesc = dK + (uint32_t)(x.st * STAGE16);
+              const uint32_t d = tmem + w * WG_COLS;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_bf16(d, a + 2 * kk, bdesc + 2 * kk, idesc_s, kk > 0);
-          umma_commit(s_full + w);
-          if (w == 1) {
-            umma_commit(k_empty + ss.st);
-            if (ss.j == nkv - 1) umma_commit(q_empty + qbuf);      // both Q tiles may be refilled (item k + 2)
+              for (int kk = 0; kk < 4; ++kk) umma_bf16(d, a + 2 * kk, bdesc + 2 * kk, idesc_s, kk > 0);
+              umma_commit(s_full + w);
+              if (ss[w ^ 1].g > x.g) {                     // the other warpgroup has issued this tile already
+                umma_commit(k_empty + x.st);
+                if (x.j == nkv - 1) umma_commit(q_empty + qbuf);      // both Q tiles may be refilled (item k + 2)
+              }
+            }
+            __syncwarp();
+            if (w == 1) ATTN_TRACE(2, x.g);
+            step(x);
+            progress = true;
           }
         }
-        __syncwarp();
-      }
-      step(ss);
-    };
-    if (G > 0) issue_s();
-    for (; ps.g < G; step(ps)) {
-      if (ss.g < G) issue_s();
-      mbar_wait_wd(v_full + ps.st, ps.ph);
+        // ---- O_w (+)= P_w(g) V(g): needs P_w(g), the V stage, and (first tile of an item) the previous O_w read out
+        Stream &y = ps[w];
+        if (y.g < G) {
+          bool ok = mbar_test(p_full + w, y.g & 1);
+          if (ok) ok = mbar_test(v_full + y.st, y.ph);
+          if (ok && y.j == 0 && y.k > 0) ok = mbar_test(o_empty + w, (y.k - 1) & 1);
+          if (ok) {
+            ATTN_TRACE(w, y.g);            // slots 0 / 1: P_w ready (seen by the MMA warp)
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t bdesc = dV + (uint32_t)(y.st * STAGE16);
+              const uint32_t d = tmem + w * WG_COLS + O_OFF, a = tmem + w * WG_COLS + P_OFF;
+              const uint32_t acc0 = y.j > 0;
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        mbar_wait_wd(p_full + w, ps.g & 1);
-        if (ps.j == 0 && ps.k > 0) mbar_wait_wd(o_empty + w, (ps.k - 1) & 1);   // the previous item's O_w has been read
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t bdesc = dV + (uint32_t)(ps.st * STAGE16);
-          const uint32_t d = tmem + w * WG_COLS + O_OFF, a = tmem + w * WG_COLS + P_OFF;
-          const uint32_t acc0 = ps.j > 0;
-#pragma unroll
-          for (int kk = 0; kk < 8; ++kk)     // O_w (+)= P_w V, accumulated in TMEM over the item's key tiles
-            umma_bf16_ts(d, a + kk * 8, bdesc + 128 * kk, idesc_o, kk > 0 ? 1u : acc0);
-          umma_commit(o_full + w);
-          if (w == 1) umma_commit(v_empty + ps.st);
+              for (int kk = 0; kk < 8; ++kk)     // O_w (+)= P_w V, accumulated in TMEM over the item's key tiles
+                umma_bf16_ts(d, a + kk * 8, bdesc + 128 * kk, idesc_o, kk > 0 ? 1u : acc0);
+              umma_commit(o_full + w);
+              if (ps[w ^ 1].g > y.g) umma_commit(v_empty + y.st);
+            }
+            __syncwarp();
+            step(y);
+            progress = true;
+          }
         }
-        __syncwarp();
+      }
+      if (progress) {
+        t_idle = 0;
+      } else {                               // watchdog of the polling loop (as mbar_wait_wd): ~2 s without progress
+        if (t_idle == 0) t_idle = clock64();
+        else if (clock64() - t_idle > 4000000000LL) __trap();
       }
     }
   } else {
@@ -677,6 +706,14 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, 
     const int row = quarter * 32 + lane;            // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t tS = tmem + lane_addr + w * WG_COLS, tP = tS + P_OFF, tO = tS + O_OFF;
+    // Phase shift between the warpgroups.  Every scheduler hosts one warp of each warpgroup; started together they run in
+    // lockstep (timeline: both in the MUFU-bound exponential phase for ~2400 clk, then both in the load / max / wait
+    // phases for ~1000 clk with the MUFU pipe idle: period 3500 clk).  Half a period apart, one warp's exponentials
+    // cover the other's issue-bound phases.  Nothing re-aligns them: S is issued a tile ahead, P V per warpgroup.
+    if (w == 1 && stagger > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < stagger) { }
+    }
     for (int k = 0; k < n_my; ++k) {
       const int item = (int)blockIdx.x + k * (int)gridDim.x;
       const int pr = item % npair, bh = item / npair, h = bh % p.H, b = bh / p.H;
@@ -687,8 +724,10 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, 
       for (int j = 0; j < nkv; ++j) {
         const int g = g0 + j;
         const int kv0 = j * TILE;
+        if (quarter == 0) ATTN_TRACE(3 + 6 * w, g);       // begin
         mbar_wait_wd(s_full + w, g & 1);
         tc_fence_after();
+        if (quarter == 0) ATTN_TRACE(4 + 6 * w, g);       // S ready
         float s[4][32];
 #pragma unroll
         for (int c = 0; c < 4; ++c) tmem_ld32_issue(tS + c * 32, s[c]);
@@ -696,6 +735,7 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, 
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free + w);            // S_w may be overwritten by the next score tile
+        if (quarter == 0) ATTN_TRACE(5 + 6 * w, g);       // ld done
         if (kv0 + TILE > p.T) {                            // only the last key block has invalid columns
 #pragma unroll
           for (int c = 0; c < 4; ++c)
@@ -703,60 +743,78 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, 
             for (int i = 0; i < 32; ++i)
               if (kv0 + c * 32 + i >= p.T) s[c][i] = -INFINITY;
         }
-        float mx4[4];
+        // row maximum: 16 independent chains of 8, then a tree (four chains of 32 were a ~380-clk dependent sequence)
+        float mx16[16];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          mx4[c] = fmaxf(s[c][0], s[c][1]);
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-          for (int i = 2; i < 32; i += 2) mx4[c] = fmaxf(mx4[c], fmaxf(s[c][i], s[c][i + 1]));
+          for (int q = 0; q < 4; ++q) {
+            float a = fmaxf(s[c][q * 8], s[c][q * 8 + 1]);
+#pragma unroll
+            for (int i = 2; i < 8; i += 2) a = fmaxf(a, fmaxf(s[c][q * 8 + i], s[c][q * 8 + i + 1]));
+            mx16[c * 4 + q] = a;
+          }
+#pragma unroll
+        for (int st2 = 8; st2 >= 1; st2 >>= 1)
+#pragma unroll
+          for (int q = 0; q < st2; ++q) mx16[q] = fmaxf(mx16[q], mx16[q + st2]);
+        const float m_new = fmaxf(m_use, mx16[0] * p.scale_log2);
+        if (quarter == 0) ATTN_TRACE(6 + 6 * w, g);       // max done
+        // The running maximum is settled from the scores alone (lazy: it only moves when it grows by more than 2^8), so
+        // the exponentials do not wait for P V(g-1); O_w and the P columns are touched after them.
+        float alpha = 1.f;
+        bool grow = false;
+        if (j == 0) {
+          m_use = m_new;
+        } else {
+          grow = m_new - m_use > 8.f;
+          if (grow) {
+            alpha = fast_exp2(m_use - m_new);
+            m_use = m_new;
+            l_run *= alpha;
+          }
         }
-        const float m_new = fmaxf(m_use, fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2);
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t pk[64];                                 // the 128 keys of the tile, two per word
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float e0 = fast_exp2(fmaf(s[c][i], p.scale_log2, -m_use));
+            const float e1 = fast_exp2(fmaf(s[c][i + 1], p.scale_log2, -m_use));
+            l4[(i >> 1) & 3] += e0 + e1;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+            pk[c * 16 + (i >> 1)] = *reinterpret_cast<uint32_t *>(&hh);
+          }
+        if (quarter == 0) ATTN_TRACE(7 + 6 * w, g);       // exponentials done
         if (j > 0) {
           // P V(g-1) complete: O_w is consistent and the P columns are free.  Every phase of o_full[w] is observed
           // in order (here, or at the end of the item), so the parity waits cannot alias (see v7b's post-mortem).
           mbar_wait_wd(o_full + w, (g - 1) & 1);
           tc_fence_after();
-        }
-        if (j == 0) {
-          m_use = m_new;
-        } else {
-          const bool grow = m_new - m_use > 8.f;
           if (__any_sync(0xffffffffu, grow)) {
-            const float alpha = grow ? fast_exp2(m_use - m_new) : 1.f;
-            if (grow) m_use = m_new;
-            l_run *= alpha;
 #pragma unroll 1
-            for (int c = 0; c < 2; ++c) {                // 32 columns at a time: the score row owns the registers
+            for (int c = 0; c < 2; ++c) {                // 32 columns at a time
               float o0[32];
               tmem_ld32(tO + c * 32, o0);
 #pragma unroll
               for (int i = 0; i < 32; ++i) o0[i] *= alpha;
               tmem_st32(tO + c * 32, o0);
             }
-            tmem_st_wait();
           }
         }
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t pk[32];                               // keys [64 half, 64 half + 64), two per word
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              const float e0 = fast_exp2(fmaf(s[2 * half + c][i], p.scale_log2, -m_use));
-              const float e1 = fast_exp2(fmaf(s[2 * half + c][i + 1], p.scale_log2, -m_use));
-              l4[(i >> 1) & 3] += e0 + e1;
-              __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
-              pk[c * 16 + (i >> 1)] = *reinterpret_cast<uint32_t *>(&hh);
-            }
-          tmem_st32u(tP + half * 32, pk);
+        {
+          uint32_t (&pk0)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[0]);
+          uint32_t (&pk1)[32] = *reinterpret_cast<uint32_t (*)[32]>(&pk[32]);
+          tmem_st32u(tP, pk0);
+          tmem_st32u(tP + 32, pk1);
         }
         l_run += (l4[0] + l4[1]) + (l4[2] + l4[3]);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full + w);
+        if (quarter == 0) ATTN_TRACE(8 + 6 * w, g);       // P arrived
       }
       // ---- item epilogue: this warpgroup's query tile is complete -- normalise and store, nobody to wait for
       mbar_wait_wd(o_full + w, (g0 + nkv - 1) & 1);
@@ -1249,7 +1307,12 @@ int attention_tc_forward(const void *qkv, void *out, float *lse, int B, int T, i
   const int npair = (nqb + 1) / 2;
   const int num_items = npair * H * B;
   const int grid = num_items < sm_count() ? num_items : sm_count();
-  attn_fwd8_kernel<<<grid, ATT_THREADS, F8_SMEM, st>>>(tq, p, num_items, npair);
+  static int stagger = -1;      // ASIS_ATTN_STAGGER: initial delay of warpgroup 1 in clocks (see the kernel)
+  if (stagger < 0) {
+    const char *e = getenv("ASIS_ATTN_STAGGER");
+    stagger = e ? atoi(e) : 1600;
+  }
+  attn_fwd8_kernel<<<grid, ATT_THREADS, F8_SMEM, st>>>(tq, p, num_items, npair, stagger);
   ASIS_LAUNCHED();
   return ASIS_OK;
 }

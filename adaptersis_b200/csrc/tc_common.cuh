@@ -48,6 +48,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// non-blocking test (mbarrier.test_wait has no suspend-time hint): for issuers that poll several barriers
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // mbar_wait_wd: a wait that has not been satisfied after ~2 s of SM clocks traps, so a protocol bug aborts the
 // launch with an error instead of hanging the GPU; the clock is only read on the slow path (the first try_wait
 // failed).  A translation unit that defines ASIS_WATCHDOG before including this header gets it for every mbar_wait.
