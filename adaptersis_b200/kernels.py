@@ -496,6 +496,6 @@ def conv3x3s1_gemm(op, a, b, out, bias, B, H, W, Cin, Cout):
     (include/asis_b200.h: asis_conv3x3s1_gemm).  `out` is allocated by the caller."""
     need_cuda(a, b, out)
     flops = 2.0 * B * (H + 2) * (W + 2) * 9 * Cin * Cout
-    with _Span("gemm_bf16", flops, "FLOP", f"conv3x3 op={op} B={B} {H}x{W} Cin={Cin} Cout={Cout}" if _PROF[0] is not None else None):
+    with _Span("conv_bf16", flops, "FLOP", f"conv3x3 op={op} B={B} {H}x{W} Cin={Cin} Cout={Cout}" if _PROF[0] is not None else None):
         check(_lib.load().asis_conv3x3s1_gemm(op, ptr(a), ptr(b), ptr(out), dt(out), ptr(bias), B, H, W, Cin, Cout, stream()))
     return out

@@ -168,16 +168,25 @@ def _sd64(module):
             for k, v in module.state_dict().items()}
 
 
-def _grad_check(names, ours, sd, tol, skip=()):
+def _grad_check(names, ours, sd, tol, skip=(), yard=None):
+    """ours vs the fp64 oracle gradients in ``sd[n].grad``; ``yard`` (bf16 mode): the same oracle under
+    torch.autocast(bfloat16) -- the reference's own arithmetic at that precision -- whose distance from fp64 sets the
+    bound where it exceeds ``tol`` (3 x, the rule of tests/test_gpu_fullsize.py)."""
     bad = []
     for n, a in zip(names, ours):
         r = sd[n].grad
         if n.endswith(skip) or r is None or float(r.abs().max()) < 1e-12:
             continue
         e = relerr(a.float(), r)
-        if not e < tol:
-            bad.append((n, e))
+        bound = tol if yard is None else max(tol, 3.0 * relerr(yard[n].grad.float(), r))
+        if not e < bound:
+            bad.append((n, e, bound))
     assert not bad, bad
+
+
+def _sd32(module):
+    return {k: (v.detach().float().clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+            for k, v in module.state_dict().items()}
 
 
 # Gradient parity of the two layer stacks.  ReLU' is discontinuous at 0: a pre-activation within rounding distance of
@@ -188,7 +197,9 @@ def _grad_check(names, ours, sd, tol, skip=()):
 # then smooth and the bound is the plain one: 1e-4 on outputs, 2e-3 on parameter gradients (1e5-term fp32 sums) in fp32
 # mode; 2e-2 / 3e-2 in bf16 mode.  The spatial prior module keeps one more discontinuity the masks do not remove -- the
 # arg-max of the stem's 3x3 max pooling between near-equal neighbours (~1 of 7e5 windows) -- and is six bf16 layers deep:
-# 1e-2 on its gradients in fp32 mode (measured 6e-3 on stem.6.weight, everything else < 1e-3), 3e-2 / 4e-2 in bf16 mode.
+# 1e-2 on its gradients in fp32 mode (measured 6e-3 on stem.6.weight, everything else < 1e-3).  In bf16 mode the masks of
+# a bf16 run differ from the fp64 ones at thousands of elements and BatchNorm over small maps amplifies bf16 rounding
+# (PyTorch's own autocast gradients of the stem are 10-30 % from fp64 here): bound = max(tol, 3 x autocast's distance).
 @pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 1e-2), ("bf16", 3e-2, 4e-2)])
 def test_spatial_prior_module_vs_oracle(mode, tol, gtol):
     """FeatureEncoder end to end (stem, three stride-2 stages, 1x1 projections) at 292 x 292, batch 2."""
@@ -216,7 +227,13 @@ def test_spatial_prior_module_vs_oracle(mode, tol, gtol):
         assert a.shape == b.shape and relerr(a.float(), b) < tol
     outs = o_enc.spm(sd, x.double(), relu_masks=rec)[1:]
     torch.autograd.backward(outs, [g.double() for g in gs])
-    _grad_check(names, go, sd, gtol)
+    yard = None
+    if mode == "bf16":
+        yard = _sd32(ours)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            youts = o_enc.spm(yard, x)[1:]
+        torch.autograd.backward(youts, [g.to(o.dtype) for g, o in zip(gs, youts)])
+    _grad_check(names, go, sd, gtol, yard=yard)
 
 
 @pytest.mark.parametrize("mode,tol,gtol", [("fp32", 1e-4, 2e-3), ("bf16", 2e-2, 3e-2)])
@@ -246,5 +263,12 @@ def test_feature_decoder_vs_oracle(mode, tol, gtol):
     assert y.shape == yr.shape and relerr(y.float(), yr) < tol
     sd["input"] = x.double().requires_grad_(True)
     o_enc.feature_decoder(sd, sd["input"], relu_masks=rec).backward(gy.double())
+    yard = None
+    if mode == "bf16":
+        yard = _sd32(ours)
+        yard["input"] = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            yo = o_enc.feature_decoder(yard, yard["input"])
+        yo.backward(gy.to(yo.dtype))
     # (a convolution bias in front of BatchNorm has an analytically zero gradient: rounding noise on both sides)
-    _grad_check(["input"] + names, go, sd, gtol, skip=(".0.bias",))
+    _grad_check(["input"] + names, go, sd, gtol, skip=(".0.bias",), yard=yard)
