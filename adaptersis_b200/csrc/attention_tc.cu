@@ -4,21 +4,17 @@
 // dropout); T = 1765 is not a multiple of the 128-row tiles: TMA zero-fills rows >= T and the
 // softmax masks key columns >= T.
 //
-// All three kernels: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 and 6-9 = two softmax
-// warpgroups (1 thread = 1 TMEM lane = 1 row).  Consecutive tiles alternate between the two
-// warpgroups, each with its own TMEM score buffers and smem P buffer, so the tensor core works on
-// tile i+1 / the GEMMs that consume tile i-1 while a warpgroup is in the MUFU/FMA-bound softmax of
-// tile i, and every SM sub-partition has two softmax warps to hide latency.  (A first version with
-// one warpgroup per CTA measured 16 % of the tensor peak; two resident single-buffered CTAs per SM
-// were slower still in the backward: the per-tile barrier round trips dominate.)
-// Forward  (grid: 128-query blocks x H x B), 128-key tiles:  S = Q K^T (TMEM) -> online softmax in
-//   registers -> P (bf16) into 128B-swizzled smem -> O_j = P V (V consumed MN-major straight from
-//   its TMA tile) -> accumulated in registers with the usual max-rescaling.  The two warpgroups keep
-//   separate (max, sum, O) states over the even / odd key tiles and merge them at the end.
-// Backward (two atomic-free kernels, both recompute P from the saved log-sum-exp), 64-wide tiles:
-//   dK/dV kernel, one CTA per 128 keys:    S^T = K Q^T, dP^T = V dO^T  -> P^T, dS^T -> smem ->
-//                                          dV += P^T dO, dK += dS^T Q   (accumulated in TMEM)
-//   dQ kernel,    one CTA per 128 queries: S = Q K^T, dP = dO V^T -> dS -> smem -> dQ += dS K
+// Forward (attn_fwd8_kernel; the earlier v7b is kept as attn_fwd_kernel behind ASIS_ATTN_FWD=7): persistent CTAs walk
+//   items = PAIRS of 128-query tiles of one (image, head).  Warps 0-3 / 4-7 are two softmax warpgroups (1 thread = 1 TMEM
+//   lane = 1 query row), warpgroup w owns query tile 2*pair + w over all key tiles; warp 8 = TMA producer (K and V rings,
+//   double-buffered Q pair), warp 9 = MMA issuer, event driven (polls the barriers of both warpgroups).  TMEM per
+//   warpgroup: S [128 columns] | P [64, bf16 pairs] | O [64].  S = Q K^T -> registers -> ex2 -> bf16 P written to its own
+//   TMEM columns and consumed by P V as the A operand straight from TMEM (V MN-major from its TMA tile); O accumulates in
+//   TMEM with lazy rescaling (only when the row maximum grows by more than 2^8); the item ends with normalise + store.
+// Backward (two atomic-free kernels, both recompute P from the saved log-sum-exp; 576 threads: TMA warp, MMA warp, 2 x 8
+//   softmax warps = two threads per row), 64-wide query / key sub-tiles:
+//   dK/dV kernel, one CTA per 128 keys:    S^T = K Q^T, dP^T = V dO^T -> P^T, dS^T (TMEM) -> dV += P^T dO, dK += dS^T Q
+//   dQ kernel,    one CTA per 128 queries: S = Q K^T, dP = dO V^T -> dS (TMEM) -> dQ += dS K
 // Every gradient element is produced by exactly one CTA: deterministic, no atomics.
 #include "tc_common.cuh"
 

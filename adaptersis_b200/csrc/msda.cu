@@ -455,6 +455,10 @@ __global__ void __launch_bounds__(1024) msda_bwd_scan_kernel(int *__restrict__ t
 // the program and, for lanes of one instruction that hit the same pixel, by the lane arbitration of
 // the shared-memory atomic unit -- so the gather below sums every pixel in the same order on every
 // run (tests/test_gpu_msda.py checks bit-identical results).  No float atomics, no sort.
+// CAVEAT: the order in which the lanes of ONE shared-memory atomic instruction that hit the same address are served is
+// not specified by CUDA; it has been stable on every B200 run (the test would catch a change), and only the ORDER of
+// the summands of such a pixel depends on it, never the set -- a different arbitration would change low-order bits of
+// grad_value at pixels that two lanes of one round hit at once (rare), not correctness.
 // PACK16: two 16-bit cursors per word (a bucket then holds at most 65535 entries); levels with more
 // pixels than `wmax` are processed window by window.
 // ---------------------------------------------------------------------------------------------
