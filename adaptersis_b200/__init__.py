@@ -14,6 +14,7 @@ from .vision_transformer import (DinoVisionTransformer, ModelWithIntermediateLay
 from .encoders import FeatureEncoder  # noqa: F401
 from .decoders import FeatureDecoder  # noqa: F401
 from .encoder import AdapterEncoder  # noqa: F401
+from .masktrans import MaskTransformer  # noqa: F401
 from .dp import BucketedGradAllReduce  # noqa: F401
 
 __version__ = "0.1.0"

@@ -728,7 +728,9 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint8_t *sa = smem + stage * STAGE2_BYTES;
           uint8_t *sb = sa + A_BYTES;
           const uint32_t lfull = mapa_u32(full_bar + stage, 0);   // the leader's barrier for this stage
-          if (leader) mbar_arrive_expect_tx_cluster(lfull, 2 * STAGE2_BYTES);   // both CTAs' A + B halves
+          // both CTAs' A tile + their B slices: n_mma / 2 rows (K-major box) or n_mma / 128 64-column boxes (MN-major) --
+          // a narrow output loads (and zero-fills) only the B rows its MMA reads
+          if (leader) mbar_arrive_expect_tx_cluster(lfull, 2 * (A_BYTES + (p.n_mma / 2) * BK * 2));
           else mbar_arrive_cluster(lfull);
           int a_k = kb * BK, a_row = m_blk * BM, b_k = kb * BK, b_n = n0;
           if (p.conv_taps) {                 // implicit 3x3 convolution: (tap, channel block) of this k-block
@@ -748,7 +750,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d_pair(&tmB, lfull, sb, b_k, b_n);
           } else {
 #pragma unroll
-            for (int j = 0; j < BN / 2 / 64; ++j) {
+            for (int j = 0; j < p.n_mma / 2 / 64; ++j) {
               int bn = b_n + j * 64, bk = b_k;
               if (p.conv_wg_cin) {
                 const int tap = bn / p.conv_wg_cin;
@@ -1105,7 +1107,7 @@ int gemm_tc_conv3x3(int op, const void *a, const void *b, void *c, int c_dtype, 
   CUtensorMap ta, tb;
   if (int rc = make_tmap_2d(&ta, a, Ck, R, Ck, BK, BM)) return rc;                    // K-major A: inner = channels of one tap
   if (op == 0) {
-    if (int rc = make_tmap_2d(&tb, b, (uint64_t)9 * Cin, Cout, (uint64_t)9 * Cin, BK, BN / 2)) return rc;      // w2 K-major
+    if (int rc = make_tmap_2d(&tb, b, (uint64_t)9 * Cin, Cout, (uint64_t)9 * Cin, BK, p.n_mma / 2)) return rc;      // w2 K-major
   } else {
     if (int rc = make_tmap_2d(&tb, b, (uint64_t)9 * Cin, Cout, (uint64_t)9 * Cin, 64, BK)) return rc;          // w2 MN-major: rows = Cout (K)
   }
@@ -1153,14 +1155,15 @@ int gemm_tc_launch(const void *A, int a_major, int64_t lda, const void *B, int b
   if (a_major == ASIS_MAJOR_K) rc = make_tmap_2d(&ta, A, K, M, lda, BK, BM);
   else rc = make_tmap_2d(&ta, A, M, K, lda, 64, BK);
   if (rc) return rc;
-  if (b_major == ASIS_MAJOR_K) rc = make_tmap_2d(&tb, B, K, N, ldb, BK, BN / CL);   // one slice per CTA of the cluster
+  const bool pair = CL == 2 && pair_pref();
+  if (b_major == ASIS_MAJOR_K) rc = make_tmap_2d(&tb, B, K, N, ldb, BK, pair ? p.n_mma / 2 : BN / CL);   // one slice per CTA of the cluster
   else rc = make_tmap_2d(&tb, B, N, K, ldb, 64, BK);
   if (rc) return rc;
   const int cluster_tiles = p.m_groups * p.n_tiles * splits;
   int clusters = sms / CL;
   if (cluster_tiles < clusters) clusters = cluster_tiles;
   const int grid = clusters * CL;
-  if (CL == 2 && pair_pref()) return launch_pair(a_major, b_major, ta, tb, p, grid, st);
+  if (pair) return launch_pair(a_major, b_major, ta, tb, p, grid, st);
   if (CL == 4) return launch_majors<4>(a_major, b_major, ta, tb, p, grid, st);
   if (CL == 2) return launch_majors<2>(a_major, b_major, ta, tb, p, grid, st);
   return launch_majors<1>(a_major, b_major, ta, tb, p, grid, st);

@@ -347,7 +347,60 @@ def gold_encoder(name="encoder.pt", dim=32, heads=2, depth=5, seed=19, full_grad
                             loss=loss.detach(), aux=aux.detach(), grads=gsel, amp_err=amp_err))
 
 
+def _reference_mask_transformer():
+    """The reference's ``MaskTransformer`` class object, built from its unmodified source text.
+    backbones/masktrans_block.py imports ``timm`` (absent here) for DropPath only -- which the reference instantiates
+    with drop_path 0.0, i.e. never: a stand-in module named ``timm.models.layers`` supplies the name; the evaluation
+    script itself imports torchmetrics / dataset tooling at module level, so only its ``init_weights`` function and
+    ``MaskTransformer`` class nodes (eval/eval_dinov2_masktrans.py:389-480) are compiled, from the file's own text."""
+    import ast
+    import types
+    for name in ("timm", "timm.models", "timm.models.layers"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["timm.models.layers"].DropPath = ref_ab.DropPath          # the reference's own local DropPath (adapter_blocks.py:41-60)
+    sys.modules["timm.models.layers"].trunc_normal_ = nn.init.trunc_normal_
+    from backbones.masktrans_block import Block as MTBlock
+    path = "/root/reference/eval/eval_dinov2_masktrans.py"
+    tree = ast.parse(open(path).read())
+    keep = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in ("init_weights", "MaskTransformer")]
+    assert len(keep) == 2
+    from einops import rearrange
+    ns = dict(torch=torch, nn=nn, Block=MTBlock, trunc_normal_=nn.init.trunc_normal_, rearrange=rearrange)
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns["MaskTransformer"]
+
+
+def gold_masktrans():
+    """BASELINE config[3]'s decoder: MaskTransformer(n_cls=8) on a [B, 36, d] token grid (6 x 6 patches of 14 px),
+    eval mode (dropout = identity), logits resized to the image and arg-maxed as validate_network does (:361-366)."""
+    MaskTransformer = _reference_mask_transformer()
+    gen = torch.Generator().manual_seed(29)
+    torch.manual_seed(29)
+    d, heads, n_cls, gs, B = 128, 2, 8, 6, 2
+    m = MaskTransformer(n_cls=n_cls, patch_size=14, d_encoder=d, n_layers=2, n_heads=heads, d_model=d, d_ff=4 * d,
+                        drop_path_rate=0.0, dropout=0.1)
+    stress_init(m, gen)
+    with torch.no_grad():
+        m.cls_emb.copy_(0.5 * torch.randn(m.cls_emb.shape, generator=gen))
+    m.eval()
+    x = torch.randn(B, gs * gs, d, generator=gen)
+    im = (gs * 14, gs * 14)
+    with torch.no_grad():
+        masks = m(x, im)
+        out = torch.nn.functional.interpolate(masks, size=im, mode="bilinear")
+        pred = torch.softmax(out, dim=1).argmax(1)
+    # gradients too (the reference trains this decoder, eval_dinov2_masktrans.py:262-300), dropout still off
+    xg = x.clone().requires_grad_(True)
+    gy = torch.randn(masks.shape, generator=gen)
+    mg = m(xg, im)
+    grads = torch.autograd.grad(mg, [xg] + list(m.parameters()), gy)
+    names = ["input"] + [n for n, _ in m.named_parameters()]
+    save("masktrans.pt", dict(cfg=dict(d=d, heads=heads, n_cls=n_cls, gs=gs), sd=m.state_dict(), x=x, masks=masks, logits=out,
+                              pred=pred.to(torch.uint8), gy=gy, grads=dict(zip(names, grads))))
+
+
 if __name__ == "__main__":
+    gold_masktrans()
     gold_msda_core()
     gold_msda_module()
     gold_block()

@@ -213,6 +213,75 @@ def test_fullsize_bf16_mode(fullsize):
     _compare(fullsize, "bf16", 2e-2, 2e-2, 3.0)
 
 
+def test_config3_masktrans_inference(fullsize):
+    """BASELINE config[3]: ViT-L/14 + adapters + MaskTransformer(n_cls=8) multi-class INFERENCE on an EndoVis2018-shaped
+    synthetic frame (1280 x 1024 RGB resized to 588 x 588 bilinear, tools/dataset.py:106-108), against the oracle
+    (adapter encoder + mask transformer + resize + arg-max) evaluated on the GPU in fp64.  fp32 mode: logits 1e-4, the
+    8-class arg-max mask bit-exact wherever the top-2 margin exceeds the tolerance granted to the logits (flips reported);
+    bf16 mode: 2e-2."""
+    if fullsize["name"] != "vit_large":
+        pytest.skip("config[3] is quoted on ViT-L/14")
+    import torch.nn.functional as F
+    from adaptersis_b200.masktrans import MaskTransformer
+    from oracle import masktrans as o_mt
+    ts = fullsize["ts"]
+    enc = ts.encoder
+    C = enc.model.embed_dim
+    gen = torch.Generator().manual_seed(77)
+    frame = torch.rand(1, 3, 1024, 1280, generator=gen)
+    img = F.interpolate(frame, size=(588, 588), mode="bilinear").to(DEV)
+    torch.manual_seed(77)
+    mt = MaskTransformer(n_cls=8, patch_size=14, d_encoder=C, n_layers=2, n_heads=C // 64, d_model=C, d_ff=4 * C,
+                         drop_path_rate=0.0, dropout=0.1).to(DEV).eval()
+    with torch.no_grad():
+        for name, p in mt.named_parameters():          # away from the (1, 0) / 0.02 initialisation: every class gets signal
+            r = torch.randn(p.shape, generator=gen).to(DEV)
+            if name == "cls_emb":
+                p.copy_(0.5 * r)
+            elif name.endswith("bias"):
+                p.copy_(0.05 * r)
+            elif "norm" in name:
+                p.copy_(1.0 + 0.1 * r)
+    sds = {"vit": enc.model.state_dict(), "spm": enc.backbone_encoder.state_dict(), "inj": enc.cross_vit.state_dict(),
+           "ext": enc.cross_cnn.state_dict()}
+    w = {tag: {k: (v.detach().double() if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+         for tag, sd in sds.items()}
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            res = o_enc.adapter_encoder(w["vit"], w["spm"], w["inj"], w["ext"], img.double(), enc.model.num_heads)
+            sd64 = {k: v.detach().double() for k, v in mt.state_dict().items()}
+            masks64 = o_mt.mask_transformer(sd64, res["x"], (588, 588), 14, 8, C // 64)
+            out64, pred64 = o_mt.segment(masks64, (588, 588))
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    top2 = out64.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    scale = float(out64.abs().max())
+    report = {}
+    for mode, tol in (("fp32", 1e-4), ("bf16", 2e-2)):
+        with asis.precision(mode), torch.no_grad():
+            x = enc(img)["x"]
+            masks = mt(x, (588, 588))
+            out = F.interpolate(masks.float(), size=(588, 588), mode="bilinear")
+            pred = torch.softmax(out, 1).argmax(1)
+        e = relerr(out, out64)
+        flips = pred != pred64
+        decided = margin > 2 * tol * scale
+        report[mode] = dict(logits_relerr=e, classes_present=int(pred64.unique().numel()), pixels=int(flips.numel()), flips=int(flips.sum()),
+                            flips_at_determined_pixels=int((flips & decided).sum()),
+                            max_margin_at_flips=float(margin[flips].max()) if bool(flips.any()) else 0.0)
+        print(f"[config3 {mode}] {report[mode]}")
+        assert e < tol, (mode, e)
+        assert report[mode]["flips_at_determined_pixels"] == 0, report[mode]
+    assert report["fp32"]["flips"] <= 5, report["fp32"]
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "parity_config3_masktrans.json"), "w") as f:
+            json.dump(report, f, indent=1)
+
+
 def test_weight_cache_follows_parameter_updates():
     """the bf16 operand cache must refresh after optimizer.step() / load_state_dict(), and writes
     through .data are caught by invalidate_weight_cache()."""

@@ -31,6 +31,21 @@ def test_state_dict_keys_match_reference(golden):
     asis.FeatureDecoder(embed_dim=cfg["dim"], num_classes=2, features=cfg["dec_features"]).load_state_dict(g["dec_sd"], strict=True)
 
 
+def test_mask_transformer_keys_match_reference(golden):
+    # config[3]: same constructor call as eval/eval_dinov2_masktrans.py:136-139 (scaled down), same state_dict keys / shapes
+    from adaptersis_b200.masktrans import MaskTransformer
+    g = golden("masktrans.pt")
+    c = g["cfg"]
+    m = MaskTransformer(n_cls=c["n_cls"], patch_size=14, d_encoder=c["d"], n_layers=2, n_heads=c["heads"], d_model=c["d"],
+                        d_ff=4 * c["d"], drop_path_rate=0.0, dropout=0.1)
+    res = m.load_state_dict(g["sd"], strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert m.no_weight_decay() == {"cls_emb"}
+    import pytest
+    with pytest.raises(NotImplementedError):
+        m.get_attention_map(g["x"], 0)
+
+
 def test_vit_factories_match_reference_sizes():
     # parameter counts probed from the reference: block 12,598,272; ViT-L 304,368,640
     blk = asis.Block(dim=1024, num_heads=16, qkv_bias=True, init_values=1e-5, attn_class=asis.MemEffAttention)

@@ -8,7 +8,7 @@ import pytest
 from conftest import as_fixture_entry, grad_err, mask_check, relerr
 from synth import adapter_data, encoder_data
 import oracle
-from oracle import adapter, encoder, layers, msda, vit
+from oracle import adapter, encoder, layers, masktrans, msda, vit
 
 TOL = 2e-5
 
@@ -192,6 +192,25 @@ def test_gradient_tolerance_is_fp32_summation_noise(golden, fixture):
     # activations: fp32 is within 1e-4 of fp64, and so is the fixture
     assert relerr(g["feat"], o64["feat"]) < 1e-4 and relerr(o32["feat"], o64["feat"]) < 1e-4
     assert relerr(g["logits_s4"], o64["logits"][:, :, ::4, ::4]) < 1e-4
+
+
+def test_mask_transformer(golden):
+    # BASELINE config[3]'s decoder: the oracle vs the reference's own MaskTransformer (eval mode), logits, resized logits,
+    # arg-max prediction bit for bit, and every gradient
+    g = golden("masktrans.pt")
+    c = g["cfg"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in g["sd"].items()}
+    x = g["x"].clone().requires_grad_(True)
+    im = (c["gs"] * 14, c["gs"] * 14)
+    masks = masktrans.mask_transformer(sd, x, im, 14, c["n_cls"], c["heads"])
+    assert masks.shape == g["masks"].shape and relerr(masks, g["masks"]) < TOL
+    out, pred = masktrans.segment(masks.detach(), im)
+    assert relerr(out, g["logits"]) < TOL
+    assert torch.equal(pred.to(torch.uint8), g["pred"])
+    names = [n for n in g["grads"] if n != "input"]
+    grads = torch.autograd.grad(masks, [x] + [sd[n] for n in names], g["gy"])
+    for n, a in zip(["input"] + names, grads):
+        assert relerr(a, g["grads"][n]) < 5 * TOL, n
 
 
 def test_oracle_is_test_infrastructure_only():
