@@ -199,7 +199,8 @@ class BatchNormFunction(Function):
             n_tot = n_local
             if world > 1:
                 # ONE all_gather per layer: [mean, m2, count] of every rank, merged with Chan's formula
-                mine = torch.cat([mean, m2, mean.new_tensor([float(n_local)])])
+                # (torch.full: a fill kernel -- a host tensor copied in would break CUDA-graph capture of the step)
+                mine = torch.cat([mean, m2, torch.full((1,), float(n_local), dtype=mean.dtype, device=mean.device)])
                 every = [torch.empty_like(mine) for _ in range(world)]
                 dist.all_gather(every, mine, group=group)
                 st = torch.stack(every)
