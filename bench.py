@@ -216,16 +216,16 @@ def run_reference(args, rank):
         t0 = time.perf_counter()
         step_fn(img, tgt)
         dt_ = time.perf_counter() - t0
-        if i >= min(args.warmup, 1):          # CPU arm: one warm-up is enough (no JIT, no autotune)
+        if i >= args.warmup:
             times.append(dt_)
-        if time.perf_counter() - t_begin > budget_s and times:
+        if time.perf_counter() - t_begin > budget_s and times:       # bounded run: stop early, report what was timed
             break
     ms = 1e3 * sum(times) / len(times)
     val = 1.0 / (ms / 1e3)
     sample = (f"{len(times)} timed step(s) of 1 image each (of the 12-image batch), full {args.arch} /14 + adapters + decoder "
               f"fwd+bwd, {what}, {ncores} threads")
     line = {"impl": "reference", "metric": METRIC, "value": round(val, 5), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(ms, 1), "higher_is_better": True,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": round(ms, 1), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args, 1, "cpu"),
             "cpu_baseline": {"value": round(val, 5), "unit": UNIT, "cores": ncores, "kind": kind, "sample": sample},
