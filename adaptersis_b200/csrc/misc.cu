@@ -359,6 +359,35 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T *__restrict
 
 using namespace asis;
 
+// ---- input ingest (tools/dataset.py:111-118): uint8 HWC frames -> float CHW / 255, uint8 masks -> int64 ---------------
+// one thread per pixel: three coalesced-enough byte reads, three plane-strided float writes (each plane coalesced);
+// IEEE division (torch computes uint8 / 255.0 in fp32), so the batch is bit-identical to the host pipeline's tensor
+__global__ void __launch_bounds__(256) frames_to_batch_kernel(const uint8_t *__restrict__ frames, float *__restrict__ img,
+                                                              const uint8_t *__restrict__ masks, int64_t *__restrict__ target,
+                                                              int B, int HW) {
+  const size_t total = (size_t)B * HW;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = t / HW, p = t - b * HW;
+    const uint8_t *src = frames + t * 3;
+    float *dst = img + b * 3 * (size_t)HW + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) dst[(size_t)c * HW] = __fdiv_rn((float)src[c], 255.0f);
+    if (masks) target[t] = (int64_t)masks[t];
+  }
+}
+
+extern "C" int asis_frames_to_batch(const uint8_t *frames, float *img, const uint8_t *masks, int64_t *target, int B, int H,
+                                    int W, void *stream) {
+  ASIS_REQUIRE(frames && img, "frames_to_batch: null pointer");
+  ASIS_REQUIRE((masks == nullptr) == (target == nullptr), "frames_to_batch: masks and target go together");
+  ASIS_REQUIRE(B > 0 && H > 0 && W > 0, "frames_to_batch: non-positive dimension");
+  const size_t total = (size_t)B * H * W;
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)148 * 16);
+  frames_to_batch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(frames, img, masks, target, B, H * W);
+  ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
 extern "C" int asis_patchify(const float *img, void *cols, int out_dtype, int B, int Cin, int Himg, int Wimg,
                              int patch, int64_t ldk, void *stream) {
   ASIS_REQUIRE(img && cols, "patchify: null pointer");

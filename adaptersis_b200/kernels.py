@@ -325,6 +325,25 @@ def dwconv3x3_backward(dy, pre, x, weight, maps, fuse_gelu):
     return dx, dw, db
 
 
+# ------------------------------------------------------------------------------------------ input ingest
+def frames_to_batch(frames_u8, masks_u8=None, img_out=None, target_out=None):
+    """frames [B, H, W, 3] uint8 (device) -> img [B, 3, H, W] f32 = frames / 255; masks [B, H, W] uint8 -> target int64
+    (tools/dataset.py:111-118 on the device).  ``img_out`` / ``target_out``: write into existing buffers (the captured
+    step's static inputs)."""
+    need_cuda(frames_u8)
+    B, H, W, C = frames_u8.shape
+    assert C == 3 and frames_u8.dtype == torch.uint8 and frames_u8.is_contiguous()
+    img = img_out if img_out is not None else torch.empty(B, 3, H, W, dtype=torch.float32, device=frames_u8.device)
+    assert img.shape == (B, 3, H, W) and img.dtype == torch.float32 and img.is_contiguous()
+    tgt = None
+    if masks_u8 is not None:
+        assert masks_u8.shape == (B, H, W) and masks_u8.dtype == torch.uint8 and masks_u8.is_contiguous()
+        tgt = target_out if target_out is not None else torch.empty(B, H, W, dtype=torch.int64, device=frames_u8.device)
+        assert tgt.shape == (B, H, W) and tgt.dtype == torch.int64 and tgt.is_contiguous()
+    check(_lib.load().asis_frames_to_batch(ptr(frames_u8), ptr(img), ptr(masks_u8), ptr(tgt), B, H, W, stream()))
+    return img, tgt
+
+
 # ------------------------------------------------------------------------------------------ decoder
 def upsample2x_forward(x_nhwc, pad_in=0, pad_out=0):
     """x [B, H(+2pi), W(+2pi), C] contiguous -> [B, 2H(+2po), 2W(+2po), C]; bilinear, align_corners=True."""

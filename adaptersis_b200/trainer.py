@@ -134,6 +134,23 @@ class TrainStep(nn.Module):
         self._replayed = True
         return loss
 
+    def step_frames(self, frames_host, masks_host):
+        """The same call fed as the dataset produces its samples (tools/dataset.py:111-118): uint8 HWC frames
+        [B, H, W, 3] and uint8 masks [B, H, W] in pinned host memory.  The / 255, the HWC -> CHW transposition and the
+        .long() run on the device (asis_frames_to_batch) straight into the step's input buffers: a quarter of the
+        host-to-device bytes of the float batch, bit-identical tensors."""
+        from . import kernels as K
+        fr = frames_host.to(self.device, non_blocking=True)
+        mk = masks_host.to(self.device, non_blocking=True)
+        if self._graph is not None:
+            graph, g_inp, g_tgt, loss, _ = self._graph
+            K.frames_to_batch(fr, mk, img_out=g_inp, target_out=g_tgt)
+            graph.replay()
+            self._replayed = True
+            return float(loss.item())
+        inp, target = K.frames_to_batch(fr, mk)
+        return float(self.step_device(inp, target).item())
+
     def step(self, inp_host, target_host):
         """The call a user makes (train.py:270-271, :432-440): pinned host batch in, python float out."""
         if self._graph is not None:           # straight into the graph's static input buffers

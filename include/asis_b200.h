@@ -212,6 +212,13 @@ int asis_upsample2x_bilinear_forward_padded(const void *x, void *y, int dtype, i
 int asis_upsample2x_bilinear_backward_padded(const void *gy, void *gx, int dtype, int B, int H, int W,
                                              int C, int pad_in, int pad_out, void *stream);
 
+/* Input ingest (tools/dataset.py:111-118: np.uint8 HWC image -> torch.from_numpy(img.transpose(2, 0, 1)) / 255.0, mask
+ * -> .long()) on the device: frames [B, H, W, 3] u8 -> img [B, 3, H, W] f32 = frames / 255 (IEEE division: bit-identical
+ * to the host pipeline), masks [B, H, W] u8 -> target [B, H, W] i64 (both or neither).  A quarter of the host-to-device
+ * bytes of the float batch. */
+int asis_frames_to_batch(const uint8_t *frames, float *img, const uint8_t *masks, int64_t *target, int B, int H,
+                         int W, void *stream);
+
 /* LayerScale backward (dinov2/layers/layer_scale.py:26-27 behind x + ls(branch(x)), block.py:112-113) in
  * one pass over the incoming gradient d [M, N] f32:  du = d * gamma (dtype, the branch-output gradient),
  * dgamma = colsum(d * u) (optional, needs the saved branch output u), dbias = colsum(du) (optional: the

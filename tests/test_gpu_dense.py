@@ -153,3 +153,17 @@ def test_upsample2x_matches_torch(B, C, H, W, dtype):
     tol = 1e-5 if dtype == torch.float32 else 1e-2
     assert y.shape == yr.shape and relerr(y.float(), yr) < tol
     assert relerr(gx.float(), gxr) < tol
+
+
+def test_frames_to_batch_matches_host_pipeline():
+    # tools/dataset.py:111-118: torch.from_numpy(img_np.transpose(2, 0, 1)) / 255.0 and mask.long(), bit for bit
+    g = torch.Generator().manual_seed(9)
+    frames = torch.randint(0, 256, (3, 70, 42, 3), generator=g, dtype=torch.uint8)
+    masks = torch.randint(0, 2, (3, 70, 42), generator=g, dtype=torch.uint8)
+    ref_img = frames.permute(0, 3, 1, 2) / 255.0
+    ref_tgt = masks.long()
+    img, tgt = K.frames_to_batch(frames.to(DEV), masks.to(DEV))
+    assert img.dtype == torch.float32 and tgt.dtype == torch.int64
+    assert torch.equal(img.cpu(), ref_img) and torch.equal(tgt.cpu(), ref_tgt)
+    img2, none = K.frames_to_batch(frames.to(DEV))
+    assert none is None and torch.equal(img2.cpu(), ref_img)

@@ -310,3 +310,24 @@ def test_weight_cache_follows_parameter_updates():
     import gc
     gc.collect()
     assert len(asis.functional._wcache) < n_before   # entries die with their parameters
+
+
+def test_step_frames_equals_step_on_the_host_pipeline_tensors():
+    # uint8 HWC frames ingested on the device give the SAME training step as the float batch the reference's
+    # dataset builds on the host (tools/dataset.py:111-118) -- same loss, same parameters afterwards, bit for bit
+    g = torch.Generator().manual_seed(31)
+    frames = torch.randint(0, 256, (2, 588, 588, 3), generator=g, dtype=torch.uint8)
+    masks = torch.randint(0, 2, (2, 588, 588), generator=g, dtype=torch.uint8)
+    img_host = (frames.permute(0, 3, 1, 2) / 255.0).contiguous()
+    tgt_host = masks.long()
+    outs = []
+    for feed in ("float", "u8"):
+        torch.manual_seed(5)
+        ts = TrainStep(arch="vit_small", adapter_heads=6, device=DEV, precision="fp32")
+        if feed == "float":
+            loss = ts.step(img_host.pin_memory(), tgt_host.pin_memory())
+        else:
+            loss = ts.step_frames(frames.pin_memory(), masks.pin_memory())
+        outs.append((loss, ts.seg_decoder.final_out.weight.detach().clone(), ts.encoder.cross_cnn.attn.value_proj.weight.detach().clone()))
+    assert outs[0][0] == outs[1][0]
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
