@@ -331,7 +331,7 @@ __device__ __forceinline__ void epi3_chunk(const EpiLane &L, uint32_t rd0, uint3
       const float4 t = lds128(((it & 1) ? rd1 : rd0) + it * 512);
       float w[4] = {t.x, t.y, t.z, t.w};
       if (EpiHasBias<KIND>::value) { w[0] += b4.x; w[1] += b4.y; w[2] += b4.z; w[3] += b4.w; }
-      if (KIND == ASIS_EPI_GELU || KIND == ASIS_EPI_SCALE_RESIDUAL) {
+      if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
         if (L.aux) *reinterpret_cast<uint2 *>(L.aux + (size_t)((uint32_t)it * L.astep)) = pack_bf16x4(w);
       }
       if (KIND == ASIS_EPI_GELU) {
@@ -388,7 +388,7 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
     L.astep = (uint32_t)(4 * e.ldaux) * 2u;
     L.in2 = nullptr;
     L.istep = 0;
-    if ((KIND == ASIS_EPI_GELU || KIND == ASIS_EPI_SCALE_RESIDUAL || KIND == ASIS_EPI_GELU_GRAD) && e.aux)
+    if ((KIND == ASIS_EPI_SCALE_RESIDUAL || KIND == ASIS_EPI_GELU_GRAD) && e.aux)      // (GELU + saved pre-activation: generic path)
       L.aux = reinterpret_cast<char *>(e.aux) + ((size_t)(row0 + r) * e.ldaux + col) * 2;
     if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
       L.in2 = reinterpret_cast<const char *>(e.residual) + eoff * 4;
@@ -831,7 +831,10 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int col_base = n_blk * BN + half * 128;
       const int tr = ew == 0 ? tile / num_clusters : -1;     // (trace builds: stamps of epilogue warp 0)
       // slabs inside N with vectorisable pitches and a bf16 (or no) aux operand take the lean epilogue
-      const bool lean_ok = vec_ok && !p.atomic_out && (!p.epi.aux || p.epi.aux_dtype == ASIS_BF16);
+      // (GELU with a saved pre-activation -- round 1's backward, tests and tools only -- takes the generic path: the lean GELU
+      //  instantiation, the taps pass's fc1, carries no aux code at all)
+      const bool lean_ok = vec_ok && !p.atomic_out && (!p.epi.aux || p.epi.aux_dtype == ASIS_BF16) &&
+                           !(p.epi.kind == ASIS_EPI_GELU && p.epi.aux);
       const bool lean = lean_ok && col_base + 128 <= p.N;
       if (lean) {
         const uint32_t st32 = smem_u32(stage);
