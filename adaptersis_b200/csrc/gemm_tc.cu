@@ -663,7 +663,11 @@ constexpr int EPI2_STAGE_BYTES = EPI_STAGE_BYTES;     // one 4 KB transposition 
 constexpr int GEMM2_SMEM = STAGES2 * STAGE2_BYTES + EPI2_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 static_assert(GEMM2_SMEM <= 227 * 1024, "pair kernel: shared memory over the 227 KB limit");
 
-template <int A_MN, int B_MN>
+// EPI: -1 = every epilogue kind behind a run-time switch (any combination the C ABI allows); >= 0 = the kernel is compiled
+// for that ONE kind (the switch collapses): the hot (majors, kind) pairs of the step each get their own kernel.  With all
+// fourteen epilogue bodies (7 lean + 7 generic) in one kernel the code was ~23 k SASS lines and the register allocation
+// the union of all of them -- removing one `if (aux)` store from the lean GELU body alone made that call 20 % faster.
+template <int A_MN, int B_MN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -844,7 +848,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (cb) epi_slab3<K, true, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4);         \
     else epi_slab3<K, false, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4);           \
   } while (0)
-        switch (p.epi.kind) {
+        switch (EPI >= 0 ? EPI : p.epi.kind) {
           case ASIS_EPI_GELU: ASIS_EPI3(ASIS_EPI_GELU); break;
           case ASIS_EPI_SCALE_RESIDUAL: epi_slab3<ASIS_EPI_SCALE_RESIDUAL, false, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4); break;
           case ASIS_EPI_DGELU: ASIS_EPI3(ASIS_EPI_DGELU); break;
@@ -855,7 +859,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
 #undef ASIS_EPI3
       } else {
-        switch (p.epi.kind) {
+        switch (EPI >= 0 ? EPI : p.epi.kind) {
           case ASIS_EPI_GELU: epi_slab<ASIS_EPI_GELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
           case ASIS_EPI_SCALE_RESIDUAL: epi_slab<ASIS_EPI_SCALE_RESIDUAL>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
           case ASIS_EPI_DGELU: epi_slab<ASIS_EPI_DGELU>(p, taddr, stage, row0, col_base, vec_ok, lane, tfull_bar + acc, acc_phase, tr); break;
@@ -983,11 +987,11 @@ static int launch_majors(int a_major, int b_major, const CUtensorMap &ta, const 
   return launch_variant<1, 0, CL>(ta, tb, p, grid, st);
 }
 
-template <int A_MN, int B_MN>
+template <int A_MN, int B_MN, int EPI>
 static int launch_pair_variant(const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ASIS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
+    ASIS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -1002,17 +1006,32 @@ static int launch_pair_variant(const CUtensorMap &ta, const CUtensorMap &tb, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ASIS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN>, ta, tb, p));
+  ASIS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN, EPI>, ta, tb, p));
   ASIS_LAUNCHED();
   return ASIS_OK;
 }
 
 static int launch_pair(int a_major, int b_major, const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p,
                        int grid, cudaStream_t st) {
-  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_K) return launch_pair_variant<0, 0>(ta, tb, p, grid, st);
-  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_MN) return launch_pair_variant<0, 1>(ta, tb, p, grid, st);
-  if (a_major == ASIS_MAJOR_MN && b_major == ASIS_MAJOR_MN) return launch_pair_variant<1, 1>(ta, tb, p, grid, st);
-  return launch_pair_variant<1, 0>(ta, tb, p, grid, st);
+  const int kind = p.epi.kind;
+  // the (majors, epilogue) pairs of the training step: one specialised kernel each
+  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_K) {          // nn.Linear forward, implicit convolution forward
+    if (kind == ASIS_EPI_NONE) return launch_pair_variant<0, 0, ASIS_EPI_NONE>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_GELU) return launch_pair_variant<0, 0, ASIS_EPI_GELU>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_SCALE_RESIDUAL) return launch_pair_variant<0, 0, ASIS_EPI_SCALE_RESIDUAL>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_GELU_GRAD) return launch_pair_variant<0, 0, ASIS_EPI_GELU_GRAD>(ta, tb, p, grid, st);
+    return launch_pair_variant<0, 0, -1>(ta, tb, p, grid, st);
+  }
+  if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_MN) {         // input gradients
+    if (kind == ASIS_EPI_NONE) return launch_pair_variant<0, 1, ASIS_EPI_NONE>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_MUL_AUX) return launch_pair_variant<0, 1, ASIS_EPI_MUL_AUX>(ta, tb, p, grid, st);
+    return launch_pair_variant<0, 1, -1>(ta, tb, p, grid, st);
+  }
+  if (a_major == ASIS_MAJOR_MN && b_major == ASIS_MAJOR_MN) {        // weight gradients
+    if (kind == ASIS_EPI_NONE) return launch_pair_variant<1, 1, ASIS_EPI_NONE>(ta, tb, p, grid, st);
+    return launch_pair_variant<1, 1, -1>(ta, tb, p, grid, st);
+  }
+  return launch_pair_variant<1, 0, -1>(ta, tb, p, grid, st);
 }
 
 // ASIS_GEMM_PAIR=0 falls back to the 1-CTA MMA kernel with B multicast (kept for comparison / bisecting)
