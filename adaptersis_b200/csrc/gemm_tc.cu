@@ -322,7 +322,8 @@ __device__ __forceinline__ void epi3_colvec(const GemmTcParams &p, int col, floa
 }
 
 // one transposed 32 x 32 chunk read back as lane -> (row it*4 + lane/8, 4 columns): fused math, coalesced stores
-template <int KIND, bool CBF16>
+// SAUX (SCALE_RESIDUAL only): the branch output is saved as well -- a compile-time flag, each variant in its own kernel
+template <int KIND, bool CBF16, bool SAUX>
 __device__ __forceinline__ void epi3_chunk(const EpiLane &L, uint32_t rd0, uint32_t rd1, const float4 &b4, const float4 &g4,
                                            const uint4 (&cur)[8]) {
 #pragma unroll
@@ -331,9 +332,8 @@ __device__ __forceinline__ void epi3_chunk(const EpiLane &L, uint32_t rd0, uint3
       const float4 t = lds128(((it & 1) ? rd1 : rd0) + it * 512);
       float w[4] = {t.x, t.y, t.z, t.w};
       if (EpiHasBias<KIND>::value) { w[0] += b4.x; w[1] += b4.y; w[2] += b4.z; w[3] += b4.w; }
-      if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
-        if (L.aux) *reinterpret_cast<uint2 *>(L.aux + (size_t)((uint32_t)it * L.astep)) = pack_bf16x4(w);
-      }
+      if (KIND == ASIS_EPI_SCALE_RESIDUAL && SAUX)
+        *reinterpret_cast<uint2 *>(L.aux + (size_t)((uint32_t)it * L.astep)) = pack_bf16x4(w);
       if (KIND == ASIS_EPI_GELU) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) w[i] = gelu_fast(w[i]);
@@ -368,7 +368,7 @@ __device__ __forceinline__ void epi3_chunk(const EpiLane &L, uint32_t rd0, uint3
 // the epilogue of one 32-row x 128-column slab (entirely inside N) owned by one warp; `stage_u32`: its 4 KB buffer
 // `nch`: how many of the slab's four 32-column chunks lie inside N (a narrow GEMM -- N = 64 convolutions -- uses 2 or 0)
 // FULL: all four chunks, known at compile time (the hot instantiation: every loop bound and `last` are constants)
-template <int KIND, bool CBF16, bool FULL>
+template <int KIND, bool CBF16, bool FULL, bool SAUX = false>
 __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr, uint32_t stage_u32, int row0, int col_base,
                                           int lane, uint64_t *tfull, uint32_t tfull_phase, int tr_idx, int nch_rt) {
   const int nch = FULL ? 4 : nch_rt;
@@ -388,7 +388,7 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
     L.astep = (uint32_t)(4 * e.ldaux) * 2u;
     L.in2 = nullptr;
     L.istep = 0;
-    if ((KIND == ASIS_EPI_SCALE_RESIDUAL || KIND == ASIS_EPI_GELU_GRAD) && e.aux)      // (GELU + saved pre-activation: generic path)
+    if (((KIND == ASIS_EPI_SCALE_RESIDUAL && SAUX) || KIND == ASIS_EPI_GELU_GRAD) && e.aux)      // (GELU + saved pre-activation: generic path)
       L.aux = reinterpret_cast<char *>(e.aux) + ((size_t)(row0 + r) * e.ldaux + col) * 2;
     if (KIND == ASIS_EPI_SCALE_RESIDUAL) {
       L.in2 = reinterpret_cast<const char *>(e.residual) + eoff * 4;
@@ -447,10 +447,10 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
         L.in2 += EpiReads<KIND>::value ? 32 * I2E : 0;
         epi3_prefetch<KIND>(L, pre);
       }
-      epi3_chunk<KIND, CBF16>(L, rdA0, rdA1, b4, g4, cur);
+      epi3_chunk<KIND, CBF16, SAUX>(L, rdA0, rdA1, b4, g4, cur);
       __syncwarp();                         // the buffer is rewritten by the next chunk
       L.c += 32 * CE;
-      if (L.aux) L.aux += 32 * 2;
+      if (KIND == ASIS_EPI_GELU_GRAD || SAUX) L.aux += 32 * 2;
       col += 32;
     }
   }
@@ -667,7 +667,9 @@ static_assert(GEMM2_SMEM <= 227 * 1024, "pair kernel: shared memory over the 227
 // for that ONE kind (the switch collapses): the hot (majors, kind) pairs of the step each get their own kernel.  With all
 // fourteen epilogue bodies (7 lean + 7 generic) in one kernel the code was ~23 k SASS lines and the register allocation
 // the union of all of them -- removing one `if (aux)` store from the lean GELU body alone made that call 20 % faster.
-template <int A_MN, int B_MN, int EPI>
+// CDT: output dtype fixed at compile time (0 f32, 1 bf16, -1 run time); AUX: SCALE_RESIDUAL's saved branch output
+// (1 present, 0 absent, -1 run time).
+template <int A_MN, int B_MN, int EPI, int CDT, int AUX>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -842,7 +844,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const bool lean = lean_ok && col_base + 128 <= p.N;
       if (lean) {
         const uint32_t st32 = smem_u32(stage);
-        const bool cb = p.epi.c_dtype == ASIS_BF16;
+        const bool cb = CDT >= 0 ? CDT == 1 : p.epi.c_dtype == ASIS_BF16;
 #define ASIS_EPI3(K)                                                                                                   \
   do {                                                                                                                 \
     if (cb) epi_slab3<K, true, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4);         \
@@ -850,7 +852,12 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } while (0)
         switch (EPI >= 0 ? EPI : p.epi.kind) {
           case ASIS_EPI_GELU: ASIS_EPI3(ASIS_EPI_GELU); break;
-          case ASIS_EPI_SCALE_RESIDUAL: epi_slab3<ASIS_EPI_SCALE_RESIDUAL, false, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4); break;
+          case ASIS_EPI_SCALE_RESIDUAL:
+            if (AUX >= 0 ? AUX == 1 : p.epi.aux != nullptr)
+              epi_slab3<ASIS_EPI_SCALE_RESIDUAL, false, true, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4);
+            else
+              epi_slab3<ASIS_EPI_SCALE_RESIDUAL, false, true, false>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4);
+            break;
           case ASIS_EPI_DGELU: ASIS_EPI3(ASIS_EPI_DGELU); break;
           case ASIS_EPI_ACCUMULATE: epi_slab3<ASIS_EPI_ACCUMULATE, false, true>(p, taddr, st32, row0, col_base, lane, tfull_bar + acc, acc_phase, tr, 4); break;
           case ASIS_EPI_GELU_GRAD: ASIS_EPI3(ASIS_EPI_GELU_GRAD); break;
@@ -987,11 +994,11 @@ static int launch_majors(int a_major, int b_major, const CUtensorMap &ta, const 
   return launch_variant<1, 0, CL>(ta, tb, p, grid, st);
 }
 
-template <int A_MN, int B_MN, int EPI>
+template <int A_MN, int B_MN, int EPI, int CDT, int AUX>
 static int launch_pair_variant(const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ASIS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
+    ASIS_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel<A_MN, B_MN, EPI, CDT, AUX>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM));
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -1006,7 +1013,7 @@ static int launch_pair_variant(const CUtensorMap &ta, const CUtensorMap &tb, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ASIS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN, EPI>, ta, tb, p));
+  ASIS_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_pair_kernel<A_MN, B_MN, EPI, CDT, AUX>, ta, tb, p));
   ASIS_LAUNCHED();
   return ASIS_OK;
 }
@@ -1014,24 +1021,28 @@ static int launch_pair_variant(const CUtensorMap &ta, const CUtensorMap &tb, con
 static int launch_pair(int a_major, int b_major, const CUtensorMap &ta, const CUtensorMap &tb, const GemmTcParams &p,
                        int grid, cudaStream_t st) {
   const int kind = p.epi.kind;
-  // the (majors, epilogue) pairs of the training step: one specialised kernel each
+  const bool bf = p.epi.c_dtype == ASIS_BF16;
+  // the (majors, epilogue, output dtype) combinations of the training step: one specialised kernel each
   if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_K) {          // nn.Linear forward, implicit convolution forward
-    if (kind == ASIS_EPI_NONE) return launch_pair_variant<0, 0, ASIS_EPI_NONE>(ta, tb, p, grid, st);
-    if (kind == ASIS_EPI_GELU) return launch_pair_variant<0, 0, ASIS_EPI_GELU>(ta, tb, p, grid, st);
-    if (kind == ASIS_EPI_SCALE_RESIDUAL) return launch_pair_variant<0, 0, ASIS_EPI_SCALE_RESIDUAL>(ta, tb, p, grid, st);
-    if (kind == ASIS_EPI_GELU_GRAD) return launch_pair_variant<0, 0, ASIS_EPI_GELU_GRAD>(ta, tb, p, grid, st);
-    return launch_pair_variant<0, 0, -1>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_NONE) return bf ? launch_pair_variant<0, 0, ASIS_EPI_NONE, 1, -1>(ta, tb, p, grid, st)
+                                         : launch_pair_variant<0, 0, ASIS_EPI_NONE, 0, -1>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_GELU && bf) return launch_pair_variant<0, 0, ASIS_EPI_GELU, 1, -1>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_SCALE_RESIDUAL && !bf)
+      return p.epi.aux ? launch_pair_variant<0, 0, ASIS_EPI_SCALE_RESIDUAL, 0, 1>(ta, tb, p, grid, st)
+                       : launch_pair_variant<0, 0, ASIS_EPI_SCALE_RESIDUAL, 0, 0>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_GELU_GRAD && bf) return launch_pair_variant<0, 0, ASIS_EPI_GELU_GRAD, 1, -1>(ta, tb, p, grid, st);
+    return launch_pair_variant<0, 0, -1, -1, -1>(ta, tb, p, grid, st);
   }
   if (a_major == ASIS_MAJOR_K && b_major == ASIS_MAJOR_MN) {         // input gradients
-    if (kind == ASIS_EPI_NONE) return launch_pair_variant<0, 1, ASIS_EPI_NONE>(ta, tb, p, grid, st);
-    if (kind == ASIS_EPI_MUL_AUX) return launch_pair_variant<0, 1, ASIS_EPI_MUL_AUX>(ta, tb, p, grid, st);
-    return launch_pair_variant<0, 1, -1>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_NONE && bf) return launch_pair_variant<0, 1, ASIS_EPI_NONE, 1, -1>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_MUL_AUX && bf) return launch_pair_variant<0, 1, ASIS_EPI_MUL_AUX, 1, -1>(ta, tb, p, grid, st);
+    return launch_pair_variant<0, 1, -1, -1, -1>(ta, tb, p, grid, st);
   }
   if (a_major == ASIS_MAJOR_MN && b_major == ASIS_MAJOR_MN) {        // weight gradients
-    if (kind == ASIS_EPI_NONE) return launch_pair_variant<1, 1, ASIS_EPI_NONE>(ta, tb, p, grid, st);
-    return launch_pair_variant<1, 1, -1>(ta, tb, p, grid, st);
+    if (kind == ASIS_EPI_NONE && !bf) return launch_pair_variant<1, 1, ASIS_EPI_NONE, 0, -1>(ta, tb, p, grid, st);
+    return launch_pair_variant<1, 1, -1, -1, -1>(ta, tb, p, grid, st);
   }
-  return launch_pair_variant<1, 0, -1>(ta, tb, p, grid, st);
+  return launch_pair_variant<1, 0, -1, -1, -1>(ta, tb, p, grid, st);
 }
 
 // ASIS_GEMM_PAIR=0 falls back to the 1-CTA MMA kernel with B multicast (kept for comparison / bisecting)
