@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu --set full captures of the step's top kernels (one GPU), summarised ON THE BOX: the .ncu-rep files of a full set are
 # 10-30 MB each and gpurun brings back at most 64 MiB, so only the markdown summaries and the stall hot spots travel.
-#   usage: tools/profile_round.sh <tag>      ->  gpurun_out/<tag>_ncu_*.md, gpurun_out/<tag>_hot_*.txt
+#   usage: tools/profile_round.sh <tag> ["capture names"]      ->  gpurun_out/<tag>_ncu_*.md, gpurun_out/<tag>_hot_*.txt
 set -u
 tag=${1:-r2}
 out=gpurun_out
@@ -16,9 +16,15 @@ cap() {   # name, kernel regex, skip, count, one_kernel argument
   echo "ok $1"
 }
 cd "$(dirname "$0")/.."
-cap gemm_gelu_grad gemm_tc_pair 2 1 gemm_gelu_grad
-cap gemm_proj gemm_tc_pair 2 1 gemm_proj
-cap attn attn_ 3 4 attn_bwd
-cap conv gemm_tc_pair 3 3 conv
-cap msda msda_ 5 5 msda
+which=${2:-"gemm_gelu_grad gemm_proj attn conv msda"}
+for w in $which; do
+  case $w in
+    gemm_gelu_grad) cap gemm_gelu_grad gemm_tc_pair 2 1 gemm_gelu_grad ;;
+    gemm_proj) cap gemm_proj gemm_tc_pair 2 1 gemm_proj ;;
+    attn) cap attn attn_ 3 4 attn_bwd ;;
+    attn_fwd) cap attn_fwd attn_fwd 2 1 attn ;;
+    conv) cap conv gemm_tc_pair 3 3 conv ;;
+    msda) cap msda msda_ 5 5 msda ;;
+  esac
+done
 ls -la $out | grep $tag
