@@ -412,6 +412,23 @@ __device__ __forceinline__ void epi_slab3(const GemmTcParams &p, uint32_t taddr,
   if (nch > 0) {
     epi3_colvec<KIND>(p, col, b4n, g4n);                  // chunk 0's columns
     epi3_prefetch<KIND>(L, pre);                          // in flight while the MMAs of this tile finish
+    // chunks 1..3 of the second operand (residual / saved derivative): pulled into L2 now, while this warp only waits
+    // for the MMAs -- their register loads are issued one chunk (~300 clk) ahead, far less than a DRAM round trip, and
+    // with K = 1024 the epilogue, not the MMA loop, sets the tile period.  One lane per 128-byte line.
+    if (EpiReads<KIND>::value && KIND != ASIS_EPI_ACCUMULATE) {
+      constexpr uint32_t I2Ep = (KIND == ASIS_EPI_DGELU || KIND == ASIS_EPI_MUL_AUX) ? 2 : 4;
+      if (I2Ep == 4 || (cg & 1) == 0) {                   // f32: 8 lanes = one 128 B line per chunk; bf16: 64 B per chunk
+#pragma unroll
+        for (int c = 1; c < 4; ++c) {
+          if (I2Ep == 4 && cg != 0) break;
+          if (I2Ep == 2 && (cg != 0 || (c & 1) == 0)) continue;       // bf16: chunks 2c, 2c+1 share a line: prefetch once
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            if (it < L.nit)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(L.in2 + (size_t)((uint32_t)it * L.istep) + c * 32 * I2Ep));
+        }
+      }
+    }
   }
   if (tr_idx >= 0) GEMM_TRACE(3, tr_idx);
   mbar_wait(tfull, tfull_phase);
