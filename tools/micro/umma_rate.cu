@@ -11,8 +11,10 @@
 using namespace asis;
 using namespace asis::tc;
 
-template <int N, bool TS, bool B_MN>
-__global__ void __launch_bounds__(128, 1) k(long long *clk, int iters) {
+// LOAD > 0: warps 2.. keep reading (and, LOAD == 2, also writing) tensor memory the way the softmax warps of the attention
+// backward do, while warp 1 issues the MMA stream
+template <int N, bool TS, bool B_MN, int LOAD = 0>
+__global__ void __launch_bounds__(LOAD ? 576 : 128, 1) k(long long *clk, int iters) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
@@ -52,6 +54,25 @@ __global__ void __launch_bounds__(128, 1) k(long long *clk, int iters) {
       clk[1] = t2 - t0;      // until the last one has completed
     }
   }
+  if (LOAD && warp >= 2) {
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t col = ((warp - 2) >> 2) * 32 % 256;        // score-buffer columns [0, 256): not the MMA's accumulator
+    float v[32];
+    uint32_t pk[16];
+    float acc = 0.f;
+    for (int it = 0; it < iters * 2; ++it) {
+      tmem_ld32(tmem + lane_addr + col, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc += v[i];
+      if (LOAD == 2) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = __float_as_uint(acc) + i;
+        tmem_st16u(tmem + lane_addr + col, pk);
+        tmem_st_wait();
+      }
+    }
+    if (acc == 123.456f) clk[2] = 1;
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -60,14 +81,14 @@ __global__ void __launch_bounds__(128, 1) k(long long *clk, int iters) {
   }
 }
 
-template <int N, bool TS, bool B_MN>
+template <int N, bool TS, bool B_MN, int LOAD = 0>
 void run(const char *name) {
   long long *clk, h[2];
-  cudaMalloc(&clk, 16);
+  cudaMalloc(&clk, 32);
   const int iters = 2000, smem = 96 * 1024;
-  cudaFuncSetAttribute(k<N, TS, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  k<N, TS, B_MN><<<148, 128, smem>>>(clk, 10);
-  k<N, TS, B_MN><<<148, 128, smem>>>(clk, iters);
+  cudaFuncSetAttribute(k<N, TS, B_MN, LOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k<N, TS, B_MN, LOAD><<<148, LOAD ? 576 : 128, smem>>>(clk, 10);
+  k<N, TS, B_MN, LOAD><<<148, LOAD ? 576 : 128, smem>>>(clk, iters);
   cudaError_t e = cudaDeviceSynchronize();
   cudaMemcpy(h, clk, 16, cudaMemcpyDeviceToHost);
   const double n = 4.0 * iters;
@@ -83,5 +104,8 @@ int main() {
   run<64, true, false>("M128 N64  K16  TS  B K-major");
   run<64, true, true>("M128 N64  K16  TS  B MN-major");
   run<128, true, false>("M128 N128 K16  TS  B K-major");
+  run<64, true, false, 1>("M128 N64 TS + 16 warps tcgen05.ld");
+  run<64, true, false, 2>("M128 N64 TS + 16 warps ld + st");
+  run<128, true, false, 2>("M128 N128 TS + 16 warps ld + st");
   return 0;
 }
