@@ -234,7 +234,8 @@ def run_reference(args, rank):
 
 
 def config_dict(args, per_gpu_batch, where):
-    return {"workload": f"config[2]: {args.arch.replace('_', '-')}/14 + adapter (n_last_blocks 4) train step, imsize "
+    cfg = {"vit_large": "config[2]", "vit_base": "config[1]"}.get(args.arch, "(not a BASELINE config)")
+    return {"workload": f"{cfg}: {args.arch.replace('_', '-')}/14 + adapter (n_last_blocks 4) train step, imsize "
                         f"{args.imsize}, batch {per_gpu_batch}/GPU",
             "arch": args.arch, "imsize": args.imsize, "tokens": (args.imsize // 14) ** 2 + 1,
             "global_batch": per_gpu_batch * max(1, args.gpus if where != "cpu" else 1), "parallelism": f"dp{args.gpus}",
