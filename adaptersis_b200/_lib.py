@@ -49,6 +49,7 @@ SIGNATURES = {
     "asis_attention_backward": (_I, [_I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _Z, _P]),
     "asis_patchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _L, _P]),
     "asis_frames_to_batch": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "asis_sgd_step": (_I, [_I, _P, _P, _P, _P, _F, _F, _F, _P]),
     "asis_upsample2x_bilinear_forward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "asis_upsample2x_bilinear_backward": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "asis_upsample2x_bilinear_forward_padded": (_I, [_P, _P] + [_I] * 7 + [_P]),

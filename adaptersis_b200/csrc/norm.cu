@@ -421,6 +421,61 @@ static int ln_nv(int C) {
   return 0;
 }
 
+// ---- SGD with momentum and weight decay over a LIST of tensors (train.py:178-189: torch.optim.SGD(momentum=0.99,
+// weight_decay=3e-5)): g' = g + wd p;  buf = momentum buf + g';  p -= lr buf  -- up to kSgdMax tensors per launch, the
+// pointer table travels in the kernel parameters (no device-side table: the launch is CUDA-graph capturable as is).
+constexpr int kSgdMax = 48;
+constexpr int kSgdChunk = 8192;          // elements per block
+struct SgdTable {
+  float *p[kSgdMax];
+  const float *g[kSgdMax];
+  float *m[kSgdMax];
+  int first_block[kSgdMax + 1];          // blocks [first_block[i], first_block[i+1]) work on tensor i
+  long long n[kSgdMax];
+  int count;
+};
+__global__ void __launch_bounds__(256) sgd_kernel(const __grid_constant__ SgdTable t, float lr, float momentum, float wd) {
+  int i = 0;
+  while (i + 1 < t.count && (int)blockIdx.x >= t.first_block[i + 1]) ++i;          // (<= 48 entries: a short scan)
+  const long long base = (long long)((int)blockIdx.x - t.first_block[i]) * kSgdChunk;
+  const long long n = t.n[i];
+  float *__restrict__ p = t.p[i];
+  const float *__restrict__ g = t.g[i];
+  float *__restrict__ m = t.m[i];
+  const long long end = base + kSgdChunk < n ? base + kSgdChunk : n;
+  const bool vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m)) & 15) == 0;
+  if (vec) {
+    for (long long e = base + 4 * threadIdx.x; e + 3 < end; e += 4 * 256) {
+      float pv[4], gv[4], mv[4];
+      load4(p + e, pv);
+      load4(g + e, gv);
+      load4(m + e, mv);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gg = gv[k] + wd * pv[k];
+        mv[k] = momentum * mv[k] + gg;
+        pv[k] = pv[k] - lr * mv[k];
+      }
+      store4(m + e, mv);
+      store4(p + e, pv);
+    }
+    const long long tail = base + ((end - base) & ~3ll);
+    for (long long e = tail + threadIdx.x; e < end; e += 256) {
+      const float gg = g[e] + wd * p[e];
+      const float mm = momentum * m[e] + gg;
+      m[e] = mm;
+      p[e] = p[e] - lr * mm;
+    }
+  } else {
+    for (long long e = base + threadIdx.x; e < end; e += 256) {
+      const float gg = g[e] + wd * p[e];
+      const float mm = momentum * m[e] + gg;
+      m[e] = mm;
+      p[e] = p[e] - lr * mm;
+    }
+  }
+}
+
 static int ln_bwd_blocks(int R) {
   const int want = (R + kLn2Rows - 1) / kLn2Rows;
   return want < 444 ? want : 444;  // 3 resident blocks x 148 SMs (persistent)
@@ -596,5 +651,33 @@ extern "C" int asis_cast(const void *a, int a_dtype, void *out, int out_dtype, i
   cudaStream_t st = (cudaStream_t)stream;
   ASIS_DISPATCH_DTYPE(a_dtype, AT, ASIS_DISPATCH_DTYPE(out_dtype, OT, (add_cast_kernel<AT, AT, OT, false><<<blocks, 256, 0, st>>>((const AT *)a, nullptr, (OT *)out, n))));
   ASIS_LAUNCHED();
+  return ASIS_OK;
+}
+
+extern "C" int asis_sgd_step(int n_tensors, void *const *params, const void *const *grads, void *const *bufs, const int64_t *numels,
+                             float lr, float momentum, float weight_decay, void *stream) {
+  ASIS_REQUIRE(n_tensors >= 0 && (n_tensors == 0 || (params && grads && bufs && numels)), "sgd_step: null table");
+  cudaStream_t st = (cudaStream_t)stream;
+  int i = 0;
+  while (i < n_tensors) {
+    SgdTable t{};
+    int blocks = 0, c = 0;
+    for (; i < n_tensors && c < kSgdMax; ++i) {
+      ASIS_REQUIRE(params[i] && grads[i] && bufs[i] && numels[i] >= 0, "sgd_step: bad entry %d", i);
+      if (numels[i] == 0) continue;
+      t.p[c] = (float *)params[i];
+      t.g[c] = (const float *)grads[i];
+      t.m[c] = (float *)bufs[i];
+      t.n[c] = numels[i];
+      t.first_block[c] = blocks;
+      blocks += (int)((numels[i] + kSgdChunk - 1) / kSgdChunk);
+      ++c;
+    }
+    t.first_block[c] = blocks;
+    t.count = c;
+    if (c == 0) break;
+    sgd_kernel<<<blocks, 256, 0, st>>>(t, lr, momentum, weight_decay);
+    ASIS_LAUNCHED();
+  }
   return ASIS_OK;
 }

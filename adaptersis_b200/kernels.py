@@ -325,6 +325,22 @@ def dwconv3x3_backward(dy, pre, x, weight, maps, fuse_gelu):
     return dx, dw, db
 
 
+# ------------------------------------------------------------------------------------------ optimizer
+def sgd_step(params, grads, bufs, lr, momentum, weight_decay):
+    """torch.optim.SGD(momentum, weight_decay) update of a list of contiguous f32 tensors in place (asis_sgd_step)."""
+    import ctypes
+    n = len(params)
+    if n == 0:
+        return
+    for t in (*params, *grads, *bufs):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    P = (ctypes.c_void_p * n)(*[t.data_ptr() for t in params])
+    G = (ctypes.c_void_p * n)(*[t.data_ptr() for t in grads])
+    M = (ctypes.c_void_p * n)(*[t.data_ptr() for t in bufs])
+    N = (ctypes.c_int64 * n)(*[t.numel() for t in params])
+    check(_lib.load().asis_sgd_step(n, P, G, M, N, float(lr), float(momentum), float(weight_decay), stream()))
+
+
 # ------------------------------------------------------------------------------------------ input ingest
 def frames_to_batch(frames_u8, masks_u8=None, img_out=None, target_out=None):
     """frames [B, H, W, 3] uint8 (device) -> img [B, 3, H, W] f32 = frames / 255; masks [B, H, W] uint8 -> target int64

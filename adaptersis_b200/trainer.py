@@ -16,6 +16,33 @@ from .dp import BucketedGradAllReduce
 from .encoder import AdapterEncoder
 
 
+class FusedSGD(torch.optim.SGD):
+    """torch.optim.SGD's constructor, param_groups, state (``momentum_buffer``), state_dict and scheduler interface
+    (train.py:178-189, :191: CosineAnnealingLR steps it); the update itself is asis_sgd_step -- one kernel over 48
+    tensors at a time, pointer tables in the kernel parameters, so the launches sit in the step's CUDA graph."""
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise NotImplementedError("FusedSGD.step: closures are not supported")
+        from . import kernels as K
+        for group in self.param_groups:
+            if group["dampening"] != 0 or group["nesterov"] or group.get("maximize", False):
+                raise NotImplementedError("FusedSGD: dampening / Nesterov / maximize are not implemented (the reference uses none)")
+            ps, gs, ms = [], [], []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if st.get("momentum_buffer") is None:       # zero buffer: the first update then equals PyTorch's (buf = g')
+                    st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                ps.append(p)
+                gs.append(p.grad)
+                ms.append(st["momentum_buffer"])
+            K.sgd_step(ps, gs, ms, group["lr"], group["momentum"], group["weight_decay"])
+        return None
+
+
 def dice_loss_after_softmax(prob, target, n_classes):
     """DC(n).forward on the output of nn.Softmax(1) (train.py:424-428; segloss/dice.py:5-36): the
     reference applies softmax a second time inside the loss; kept as is."""
@@ -46,8 +73,10 @@ class TrainStep(nn.Module):
         params = [p for p in self.parameters() if p.requires_grad]
         # reference: SGD(momentum=0.99, weight_decay=3e-5), train.py:178-189
         on_cuda = torch.device(device).type == "cuda"
-        self.optimizer = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay,
-                                         **({"fused": True} if on_cuda else {"foreach": True}))
+        if on_cuda:
+            self.optimizer = FusedSGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay)
+        else:        # host-side logic tests only
+            self.optimizer = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay, foreach=True)
         self.reducer = BucketedGradAllReduce(params, bucket_bytes=bucket_bytes)
         self.device = torch.device(device)
         self._graph = None            # (CUDAGraph, static input, static target, static loss, our kernel launches per replay)

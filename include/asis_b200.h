@@ -212,6 +212,14 @@ int asis_upsample2x_bilinear_forward_padded(const void *x, void *y, int dtype, i
 int asis_upsample2x_bilinear_backward_padded(const void *gy, void *gx, int dtype, int B, int H, int W,
                                              int C, int pad_in, int pad_out, void *stream);
 
+/* The optimizer update of the step (train.py:178-189: torch.optim.SGD(momentum, weight_decay), dampening 0, no Nesterov)
+ * over a list of f32 tensors:  g' = g + wd p;  buf = momentum buf + g';  p -= lr buf.   params / grads / bufs: HOST arrays
+ * of n_tensors device pointers, numels their element counts; the pointer tables ride in the kernel parameters (48
+ * tensors per launch), so the launches capture into a CUDA graph unchanged.  A zero-initialised buf reproduces
+ * PyTorch's first step (buf = g'). */
+int asis_sgd_step(int n_tensors, void *const *params, const void *const *grads, void *const *bufs,
+                  const int64_t *numels, float lr, float momentum, float weight_decay, void *stream);
+
 /* Input ingest (tools/dataset.py:111-118: np.uint8 HWC image -> torch.from_numpy(img.transpose(2, 0, 1)) / 255.0, mask
  * -> .long()) on the device: frames [B, H, W, 3] u8 -> img [B, 3, H, W] f32 = frames / 255 (IEEE division: bit-identical
  * to the host pipeline), masks [B, H, W] u8 -> target [B, H, W] i64 (both or neither).  A quarter of the host-to-device

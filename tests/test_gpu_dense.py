@@ -167,3 +167,35 @@ def test_frames_to_batch_matches_host_pipeline():
     assert torch.equal(img.cpu(), ref_img) and torch.equal(tgt.cpu(), ref_tgt)
     img2, none = K.frames_to_batch(frames.to(DEV))
     assert none is None and torch.equal(img2.cpu(), ref_img)
+
+
+def test_fused_sgd_matches_torch():
+    # train.py:178-189: SGD(momentum=0.99, weight_decay=3e-5); three steps incl. the first (buffer creation), odd sizes,
+    # a parameter without gradient, 60 tensors (two launches of the 48-entry pointer table)
+    from adaptersis_b200.trainer import FusedSGD
+    g = torch.Generator().manual_seed(11)
+    shapes = [(1024, 1024), (7,), (3, 5, 2), (4096,), (1,), (129, 33)] * 10
+    pa = [torch.randn(s, generator=g).to(DEV).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = FusedSGD(pa, lr=0.01, momentum=0.99, weight_decay=3e-5)
+    ob = torch.optim.SGD(pb, lr=0.01, momentum=0.99, weight_decay=3e-5, foreach=False, fused=False)
+    for step in range(3):
+        for i, (a, b) in enumerate(zip(pa, pb)):
+            if i == 4 and step == 0:
+                a.grad = b.grad = None
+                continue
+            gr = torch.randn(a.shape, generator=g).to(DEV)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        oa.step()
+        ob.step()
+        if step == 0:
+            for grp in oa.param_groups:
+                grp["lr"] = 0.005          # a scheduler changes the learning rate between steps
+            for grp in ob.param_groups:
+                grp["lr"] = 0.005
+    for a, b in zip(pa, pb):
+        assert relerr(a, b) < 1e-6
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert relerr(sa["state"][k]["momentum_buffer"], sb["state"][k]["momentum_buffer"]) < 1e-6

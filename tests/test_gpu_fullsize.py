@@ -314,7 +314,9 @@ def test_weight_cache_follows_parameter_updates():
 
 def test_step_frames_equals_step_on_the_host_pipeline_tensors():
     # uint8 HWC frames ingested on the device give the SAME training step as the float batch the reference's
-    # dataset builds on the host (tools/dataset.py:111-118) -- same loss, same parameters afterwards, bit for bit
+    # dataset builds on the host (tools/dataset.py:111-118): the input tensors are bit-identical (test_gpu_dense.py), so the
+    # loss is bit-equal; the parameters after the update agree to fp32 rounding (the loss's F.interpolate backward is an
+    # ATen kernel with floating-point atomics: two runs of the SAME feed differ in the last bits too)
     g = torch.Generator().manual_seed(31)
     frames = torch.randint(0, 256, (2, 588, 588, 3), generator=g, dtype=torch.uint8)
     masks = torch.randint(0, 2, (2, 588, 588), generator=g, dtype=torch.uint8)
@@ -330,4 +332,4 @@ def test_step_frames_equals_step_on_the_host_pipeline_tensors():
             loss = ts.step_frames(frames.pin_memory(), masks.pin_memory())
         outs.append((loss, ts.seg_decoder.final_out.weight.detach().clone(), ts.encoder.cross_cnn.attn.value_proj.weight.detach().clone()))
     assert outs[0][0] == outs[1][0]
-    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+    assert relerr(outs[0][1], outs[1][1]) < 1e-5 and relerr(outs[0][2], outs[1][2]) < 1e-5
