@@ -702,10 +702,10 @@ attn_fwd8_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p, 
     const int row = quarter * 32 + lane;            // row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t tS = tmem + lane_addr + w * WG_COLS, tP = tS + P_OFF, tO = tS + O_OFF;
-    // Phase shift between the warpgroups.  Every scheduler hosts one warp of each warpgroup; started together they run in
-    // lockstep (timeline: both in the MUFU-bound exponential phase for ~2400 clk, then both in the load / max / wait
-    // phases for ~1000 clk with the MUFU pipe idle: period 3500 clk).  Half a period apart, one warp's exponentials
-    // cover the other's issue-bound phases.  Nothing re-aligns them: S is issued a tile ahead, P V per warpgroup.
+    // Optional initial phase shift between the warpgroups (experiment knob, ASIS_ATTN_STAGGER, default off).  Every
+    // scheduler hosts one warp of each warpgroup; the idea was that, half a period apart, one warp's MUFU-bound
+    // exponential phase covers the other's issue-bound load / max / wait phases.  Measured: no effect at any shift --
+    // a warp's exponential phase takes ~2000 clk whether or not the other warp of its scheduler is in the same phase.
     if (w == 1 && stagger > 0) {
       const long long t0 = clock64();
       while (clock64() - t0 < stagger) { }
@@ -1306,7 +1306,7 @@ int attention_tc_forward(const void *qkv, void *out, float *lse, int B, int T, i
   static int stagger = -1;      // ASIS_ATTN_STAGGER: initial delay of warpgroup 1 in clocks (see the kernel)
   if (stagger < 0) {
     const char *e = getenv("ASIS_ATTN_STAGGER");
-    stagger = e ? atoi(e) : 1600;
+    stagger = e ? atoi(e) : 0;        // measured 0 / 800 / 1600 / 2400 clk: 275.6 / 276.7 / 280.0 / 277.1 us -- no effect, off
   }
   attn_fwd8_kernel<<<grid, ATT_THREADS, F8_SMEM, st>>>(tq, p, num_items, npair, stagger);
   ASIS_LAUNCHED();
