@@ -80,6 +80,47 @@ def test_host_side_validation_and_workspace_sizes():
     assert rc == -1 and b"n_levels" in lib.asis_last_error()
 
 
+def test_host_side_validation_round2_entry_points():
+    """The entry points added in round 2 (convolutional stages, optimizer, ingest): every call below fails its argument
+    check before any CUDA call, or only computes a size."""
+    import ctypes
+    from adaptersis_b200 import _lib
+    lib = _lib.load()
+    fake = ctypes.c_void_p(256)
+    # implicit 3x3 convolution: channels in 64s, op in {0, 1, 2}, f32 weight gradient
+    rc = lib.asis_conv3x3s1_gemm(0, fake, fake, fake, 1, None, 2, 8, 8, 48, 64, None)
+    assert rc == -1 and b"multiples of 64" in lib.asis_last_error()
+    rc = lib.asis_conv3x3s1_gemm(3, fake, fake, fake, 1, None, 2, 8, 8, 64, 64, None)
+    assert rc == -1 and b"op must be" in lib.asis_last_error()
+    rc = lib.asis_conv3x3s1_gemm(2, fake, fake, fake, 1, None, 2, 8, 8, 64, 64, None)
+    assert rc == -1 and b"weight gradient is f32" in lib.asis_last_error()
+    rc = lib.asis_conv3x3s1_gemm(0, None, fake, fake, 1, None, 2, 8, 8, 64, 64, None)
+    assert rc == -1 and b"null pointer" in lib.asis_last_error()
+    # BatchNorm pieces: channel vectors, the one-buffer statistics layout, workspace before launch
+    assert lib.asis_chan_stats_workspace_bytes(12, 294, 294, 64) >= 2 * 64 * 4
+    s1 = ctypes.c_void_p(1024)
+    rc = lib.asis_chan_stats(0, fake, None, 1, 2, 8, 8, 12, 0, 0, fake, None, None, None, None, 0, s1, ctypes.c_void_p(1024 + 48), fake, 1 << 20, None)
+    assert rc == -1 and b"multiple of 8" in lib.asis_last_error()
+    rc = lib.asis_chan_stats(0, fake, None, 1, 2, 8, 8, 16, 0, 0, fake, None, None, None, None, 0, s1, ctypes.c_void_p(4096), fake, 1 << 20, None)
+    assert rc == -1 and b"s2 must follow s1" in lib.asis_last_error()
+    rc = lib.asis_bn_apply(0, fake, None, 1, fake, 0, 2, 8, 8, 16, 0, 0, 0, fake, fake, fake, None, None, None, 1, None)
+    assert rc == -1 and b"bf16 -> f32" in lib.asis_last_error()
+    # segmentation head: 1..4 classes; workspace = low-resolution taps + weight-gradient partials
+    assert lib.asis_seg_head_workspace_bytes(12, 336, 336, 64, 2) >= 12 * 336 * 336 * 18 * 4
+    rc = lib.asis_seg_head_forward(fake, 1, fake, None, fake, 2, 8, 8, 64, 5, fake, 1 << 30, None)
+    assert rc == -1 and b"1..4 classes" in lib.asis_last_error()
+    rc = lib.asis_seg_head_forward(fake, 1, fake, None, fake, 2, 8, 8, 64, 2, fake, 16, None)
+    assert rc != 0 and b"workspace" in lib.asis_last_error()
+    # optimizer and ingest
+    rc = lib.asis_sgd_step(3, None, None, None, None, 0.01, 0.99, 3e-5, None)
+    assert rc == -1 and b"null table" in lib.asis_last_error()
+    assert lib.asis_sgd_step(0, None, None, None, None, 0.01, 0.99, 3e-5, None) == 0            # nothing to do
+    rc = lib.asis_frames_to_batch(fake, fake, fake, None, 2, 8, 8, None)
+    assert rc == -1 and b"go together" in lib.asis_last_error()
+    rc = lib.asis_frames_to_batch(None, fake, None, None, 2, 8, 8, None)
+    assert rc == -1 and b"null pointer" in lib.asis_last_error()
+
+
 def test_no_cpu_fallback():
     import adaptersis_b200 as asis
     m = asis.MSDeformAttn(d_model=32, n_levels=1, n_heads=4, n_points=2)
