@@ -4,17 +4,29 @@ running -- the only collective the path has (reference: fo
 DistributedDataParallel wrappers, train.py:84,96,112,116).
 
 Buckets are formed in reverse parameter-registration order (the order backward produces
-gradients); a bucket is reduced as soon as all its gradients have been accumulated
-(post-accumulate-grad hooks).  Works with any torch.distributed backend (gloo on CPU for tests)."""
+gradients).  Two schedules:
+
+  * ``overlap=False`` (default): the buckets are packed and reduced back to back when backward has finished
+    (`finish()`), and every ``p.grad`` is left as a VIEW into its reduced flat bucket (no unpack pass).  The step's hot
+    kernels are persistent one-CTA-per-SM grids (GEMM, attention): an NCCL kernel that runs beside them takes SMs
+    away, the displaced CTAs start only when the collective ends and the static tile schedule makes the whole kernel
+    wait for them (measured at 8 GPUs: GEMMs 53.0 -> 59.6 ms, LayerNorm backward 6.4 -> 7.8 ms, step +10..12 ms),
+    whereas the 1.31 GB of gradients take a few ms over NVLink 5 / NVSwitch when reduced alone.
+  * ``overlap=True`` (``ASIS_DP_OVERLAP=1``): a bucket is reduced on a side stream as soon as all its gradients have
+    been accumulated (post-accumulate-grad hooks), then unpacked -- the classic DDP schedule.
+
+Works with any torch.distributed backend (gloo on CPU for tests)."""
 import contextlib
+import os
 
 import torch
 import torch.distributed as dist
 
 
 class BucketedGradAllReduce:
-    def __init__(self, params, bucket_bytes=64 << 20, process_group=None, average=True):
+    def __init__(self, params, bucket_bytes=64 << 20, process_group=None, average=True, overlap=None):
         self.params = [p for p in params if p.requires_grad]
+        self.overlap = (os.environ.get("ASIS_DP_OVERLAP", "0") == "1") if overlap is None else bool(overlap)
         self.group = process_group
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
@@ -62,7 +74,7 @@ class BucketedGradAllReduce:
                 "be reduced yet under `with reducer.no_sync():`; the last backward (outside it) + finish() reduces "
                 "the accumulated gradients.")
         self._fired.add(id(p))
-        if self._pending[i] == 0:
+        if self._pending[i] == 0 and self.overlap:
             self._launch(i)
 
     @contextlib.contextmanager
@@ -109,11 +121,44 @@ class BucketedGradAllReduce:
                                    async_op=True)
         self._works.append((bucket, flat, work, avg_in_op))
 
+    def _finish_deferred(self):
+        """All buckets packed, then reduced back to back (the collectives queue on NCCL's stream while the current
+        stream has nothing else to run), gradients left as views into the reduced buffers."""
+        jobs = []
+        for i, bucket in enumerate(self.buckets):
+            live = [p for p in bucket if p.grad is not None]     # same set on every rank: the graph is the same
+            if not live:
+                continue
+            sizes = [p.numel() for p in live]
+            if len(live) == len(bucket):
+                if self._flat[i] is None:
+                    self._flat[i] = torch.empty(sum(sizes), dtype=torch.float32, device=live[0].device)
+                flat = self._flat[i]
+            else:
+                flat = torch.empty(sum(sizes), dtype=torch.float32, device=live[0].device)
+            chunks = list(flat.split(sizes))
+            torch._foreach_copy_(chunks, [p.grad.reshape(-1) for p in live])
+            jobs.append((live, flat, chunks))
+        works = []
+        for live, flat, _ in jobs:
+            avg_in_op = self.average and flat.device.type == "cuda" and dist.get_backend(self.group) == "nccl"
+            works.append((dist.all_reduce(flat, op=dist.ReduceOp.AVG if avg_in_op else dist.ReduceOp.SUM,
+                                          group=self.group, async_op=True), avg_in_op))
+        for (live, flat, chunks), (work, averaged) in zip(jobs, works):
+            work.wait()
+            if self.average and not averaged:
+                flat.div_(self.world)
+            for p, c in zip(live, chunks):
+                p.grad = c.view_as(p)
+        self.reset()
+
     def finish(self):
         """Wait for all buckets, write the reduced (averaged) gradients back."""
         if self.world == 1:
             self.reset()
             return
+        if not self.overlap:
+            return self._finish_deferred()
         for i, left in enumerate(self._pending):
             if left != 0:
                 self._launch(i, partial=True)

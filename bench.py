@@ -242,7 +242,8 @@ def config_dict(args, per_gpu_batch, where):
             "backward": "full (backbone dgrad+wgrad, adapters, SPM, decoder); taps pass forward-only as in the reference",
             "optimizer": "SGD(momentum 0.99, wd 3e-5) on all parameters",
             "launch": "whole step replayed as one CUDA graph" if getattr(args, "graph_used", False) else "eager launches",
-            "cache": "per-step working set (>15 GB of activations) >> 126 MB L2; no explicit flush needed"}
+            "cache": "per-step working set (>15 GB of activations) >> 126 MB L2; no explicit flush needed",
+            **({"gradient_exchange": getattr(args, "dp_schedule", "")} if where != "cpu" and args.gpus > 1 else {})}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -271,6 +272,9 @@ def run_ours(args, rank, world, local_rank):
     # (measured at N = 2: 139.2 vs 141.1 ms; ASIS_GRAPH_DP=0 turns it off)
     use_graph = not args.no_graph and (world == 1 or os.environ.get("ASIS_GRAPH_DP", "1") != "0")
     args.graph_used = use_graph
+    args.dp_schedule = "NCCL all-reduce (AVG, fp32, 64 MB buckets) " + \
+        ("overlapped with backward on a side stream" if ts.reducer.overlap else
+         "after backward, back to back; gradients stay views into the reduced buckets")
     if use_graph:
         ts.capture(*dev_batches[0])
         for i in range(2):                                   # warm replays

@@ -1,5 +1,6 @@
-"""World-size-2 gloo test of the data-parallel gradient path (CPU): bucketed, hook-driven
-all-reduce must equal the mean of the per-rank gradients, with several buckets in flight."""
+"""World-size-2 gloo test of the data-parallel gradient path (CPU): the bucketed all-reduce must equal the mean
+of the per-rank gradients, with several buckets in flight -- in both schedules (reduced after backward with the
+gradients left as views into the buckets: the default; hook-driven and overlapped with backward)."""
 import os
 import socket
 
@@ -21,12 +22,24 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        for overlap in (False, True):
+            _check_schedule(rank, world, overlap)
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def _check_schedule(rank, world, overlap):
+    if True:
         from adaptersis_b200.dp import BucketedGradAllReduce
         torch.manual_seed(0)
         net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.GELU(), torch.nn.Linear(16, 16), torch.nn.Linear(16, 4))
         unused = torch.nn.Linear(3, 3)              # never takes part in the step (like cls_token / pos_embed here)
-        red = BucketedGradAllReduce(list(net.parameters()) + list(unused.parameters()), bucket_bytes=600)
-        assert len(red.buckets) >= 3
+        red = BucketedGradAllReduce(list(net.parameters()) + list(unused.parameters()), bucket_bytes=600, overlap=overlap)
+        assert len(red.buckets) >= 3 and red.overlap == overlap
         for step in range(2):
             g = torch.Generator().manual_seed(100 + step)
             data = torch.randn(world, 5, 8, generator=g)
@@ -67,12 +80,9 @@ def _worker(rank, world, port, q):
         except RuntimeError as e:
             assert "no_sync" in str(e)
         red.finish()
-        q.put((rank, "ok"))
-    except Exception as e:  # pragma: no cover
-        import traceback
-        q.put((rank, traceback.format_exc()))
-    finally:
-        dist.destroy_process_group()
+        if not overlap:     # the default schedule leaves every gradient as a view into its reduced bucket (no unpack pass)
+            assert all(p.grad._base is not None and p.grad._base.dim() == 1 for p in net.parameters())
+        red.remove()
 
 
 def test_bucketed_allreduce_world2():

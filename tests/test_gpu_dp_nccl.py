@@ -1,6 +1,6 @@
 """SURVEY.md section 8(e) parity check, on NCCL: the gradients a 2-GPU data-parallel step produces (per-rank
-shards, bucketed all-reduce AVG overlapped with backward, SyncBN statistics exchanged in the spatial prior
-module) equal the gradients ONE GPU produces on the same global batch.
+shards, bucketed all-reduce AVG -- after backward, the default, or overlapped with it --, SyncBN statistics exchanged
+in the spatial prior module) equal the gradients ONE GPU produces on the same global batch.
 
 The decoder's plain BatchNorm2d uses per-GPU batch statistics under DP by construction (as in the reference:
 backbones/decoders.py uses nn.BatchNorm2d under DDP), which is a semantic difference of DP itself, not of the
@@ -63,7 +63,8 @@ def _grads(ts, img, tgt):
     return {k: p.grad.detach().float().cpu() for k, p in ts.named_parameters() if p.grad is not None}, float(loss)
 
 
-def _worker(rank, world, port, precision, per_rank, q):
+def _worker(rank, world, port, precision, per_rank, overlap, q):
+    os.environ["ASIS_DP_OVERLAP"] = overlap
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dev = torch.device("cuda", rank)
@@ -71,7 +72,7 @@ def _worker(rank, world, port, precision, per_rank, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         ts = _make(precision, dev)
-        assert ts.reducer.world == world and len(ts.reducer.buckets) > 2
+        assert ts.reducer.world == world and len(ts.reducer.buckets) > 2 and ts.reducer.overlap == (overlap == "1")
         img, tgt = _batch(world * per_rank, 99)
         sl = slice(rank * per_rank, (rank + 1) * per_rank)
         g, loss = _grads(ts, img[sl].to(dev), tgt[sl].to(dev))
@@ -83,15 +84,15 @@ def _worker(rank, world, port, precision, per_rank, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
-def test_two_gpu_gradients_equal_one_gpu(precision, tol):
+@pytest.mark.parametrize("precision,tol,overlap", [("fp32", 1e-3, "0"), ("bf16", 2e-2, "0"), ("fp32", 1e-3, "1")])
+def test_two_gpu_gradients_equal_one_gpu(precision, tol, overlap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     world, per_rank = 2, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, precision, per_rank, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, precision, per_rank, overlap, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
@@ -130,7 +131,7 @@ def test_two_gpu_gradients_equal_one_gpu(precision, tol):
     print(f"[dp nccl {precision}] {len(g1)} gradients, worst 2-GPU vs 1-GPU error {worst[0]:.2e} ({worst[1]})")
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
-        with open(os.path.join(out, f"dp_nccl_parity_{precision}.txt"), "w") as f:
+        with open(os.path.join(out, f"dp_nccl_parity_{precision}{'_overlap' if overlap == '1' else ''}.txt"), "w") as f:
             f.write(f"{len(g1)} gradients; worst error {worst[0]:.3e} at {worst[1]} (spatial prior module: {worst_spm[0]:.3e} at "
                     f"{worst_spm[1]}); loss 1-GPU {loss1:.7f} 2-GPU mean {loss2:.7f}\n")
     assert worst[0] < tol, worst
