@@ -24,9 +24,12 @@ import torch.distributed as dist
 
 
 class BucketedGradAllReduce:
-    def __init__(self, params, bucket_bytes=64 << 20, process_group=None, average=True, overlap=None):
+    def __init__(self, params, bucket_bytes=None, process_group=None, average=True, overlap=None):
         self.params = [p for p in params if p.requires_grad]
         self.overlap = (os.environ.get("ASIS_DP_OVERLAP", "0") == "1") if overlap is None else bool(overlap)
+        if bucket_bytes is None:
+            bucket_bytes = (64 << 20) if self.overlap else (256 << 20)
+        self.bucket_bytes = bucket_bytes
         self.group = process_group
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1

@@ -56,7 +56,7 @@ def dice_loss_after_softmax(prob, target, n_classes):
 class TrainStep(nn.Module):
     def __init__(self, arch="vit_large", num_classes=2, adapter_heads=8, inplanes=64, lr=0.01, momentum=0.99,
                  weight_decay=3e-5, train_backbone=True, dec_features=None, device="cuda", precision="bf16",
-                 bucket_bytes=64 << 20):
+                 bucket_bytes=None):
         super().__init__()
         self.precision = precision
         self.encoder = AdapterEncoder(arch=arch, adapter_heads=adapter_heads, inplanes=inplanes,
@@ -77,6 +77,8 @@ class TrainStep(nn.Module):
             self.optimizer = FusedSGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay)
         else:        # host-side logic tests only
             self.optimizer = torch.optim.SGD(params, lr=lr, momentum=momentum, weight_decay=weight_decay, foreach=True)
+        # bucket size: 64 MB when the buckets are reduced while backward still runs (granularity of the overlap), 256 MB
+        # when they are reduced back to back afterwards (the default schedule, dp.py: fewer, larger collectives)
         self.reducer = BucketedGradAllReduce(params, bucket_bytes=bucket_bytes)
         self.device = torch.device(device)
         self._graph = None            # (CUDAGraph, static input, static target, static loss, our kernel launches per replay)

@@ -272,7 +272,7 @@ def run_ours(args, rank, world, local_rank):
     # (measured at N = 2: 139.2 vs 141.1 ms; ASIS_GRAPH_DP=0 turns it off)
     use_graph = not args.no_graph and (world == 1 or os.environ.get("ASIS_GRAPH_DP", "1") != "0")
     args.graph_used = use_graph
-    args.dp_schedule = "NCCL all-reduce (AVG, fp32, 64 MB buckets) " + \
+    args.dp_schedule = f"NCCL all-reduce (AVG, fp32, {ts.reducer.bucket_bytes >> 20} MB buckets) " + \
         ("overlapped with backward on a side stream" if ts.reducer.overlap else
          "after backward, back to back; gradients stay views into the reduced buckets")
     if use_graph:
