@@ -128,15 +128,20 @@ class CACNN(nn.Module):
             self.ffn_norm = norm_layer(dim)
             self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
 
-    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index, H, W):
+    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index, H, W, return_feat=False):
+        """``return_feat`` (not in the reference's signature): also return ``feat`` as the tensor the caller should
+        carry on with -- the same values, attached to this module's feat_norm node so that its backward adds the
+        gradients of the later uses inside the LayerNorm backward kernel (Fn.layer_norm_fork)."""
         qn, fn = self.query_norm, self.feat_norm
-        query = self.attn(Fn.layer_norm(query, qn.weight, qn.bias, qn.eps), reference_points,
-                          Fn.layer_norm(feat, fn.weight, fn.bias, fn.eps), spatial_shapes, level_start_index, None,
+        q_ln, query = Fn.layer_norm_fork(query, qn.weight, qn.bias, qn.eps)
+        f_ln, feat = Fn.layer_norm_fork(feat, fn.weight, fn.bias, fn.eps)
+        query = self.attn(q_ln, reference_points, f_ln, spatial_shapes, level_start_index, None,
                           gamma=None, residual=query)
         if self.with_cffn:
             n = self.ffn_norm
-            query = self.ffn(Fn.layer_norm(query, n.weight, n.bias, n.eps), H, W, residual=query)
-        return query
+            q_ln, query = Fn.layer_norm_fork(query, n.weight, n.bias, n.eps)
+            query = self.ffn(q_ln, H, W, residual=query)
+        return (query, feat) if return_feat else query
 
 
 class CAViT(nn.Module):
@@ -158,8 +163,11 @@ class CAViT(nn.Module):
                                  ratio=deform_ratio)
         self.gamma = nn.Parameter(init_values * torch.ones((dim)), requires_grad=True)
 
-    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index):
+    def forward(self, query, reference_points, feat, spatial_shapes, level_start_index, return_feat=False):
+        """``return_feat``: as in CACNN.forward."""
         qn, fn = self.query_norm, self.feat_norm
-        return self.attn(Fn.layer_norm(query, qn.weight, qn.bias, qn.eps), reference_points,
-                         Fn.layer_norm(feat, fn.weight, fn.bias, fn.eps), spatial_shapes, level_start_index, None,
-                         gamma=self.gamma, residual=query)
+        q_ln, query = Fn.layer_norm_fork(query, qn.weight, qn.bias, qn.eps)
+        f_ln, feat = Fn.layer_norm_fork(feat, fn.weight, fn.bias, fn.eps)
+        out = self.attn(q_ln, reference_points, f_ln, spatial_shapes, level_start_index, None,
+                        gamma=self.gamma, residual=query)
+        return (out, feat) if return_feat else out

@@ -55,9 +55,12 @@ class AdapterEncoder(nn.Module):
             if stage > 0:
                 with guard():
                     x = model.blocks[depth - 4 + stage](x)
-            x = self.cross_vit(query=x, reference_points=d1[0], feat=c, spatial_shapes=d1[1], level_start_index=d1[2])
-            c = self.cross_cnn(query=c, reference_points=d2[0], feat=x, spatial_shapes=d2[1], level_start_index=d2[2],
-                               H=H_c, W=W_c)
+            # (return_feat: the value-side tensor comes back attached to the module's feat_norm node, so the gradients
+            #  of its later uses are added inside that LayerNorm's backward kernel instead of by separate ATen passes)
+            x, c = self.cross_vit(query=x, reference_points=d1[0], feat=c, spatial_shapes=d1[1], level_start_index=d1[2],
+                                  return_feat=True)
+            c, x = self.cross_cnn(query=c, reference_points=d2[0], feat=x, spatial_shapes=d2[1], level_start_index=d2[2],
+                                  H=H_c, W=W_c, return_feat=True)
             x = x + taps[stage]
         gh, gw = H // self.patch_size, W // self.patch_size
         C = x.shape[-1]
