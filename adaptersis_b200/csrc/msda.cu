@@ -160,8 +160,21 @@ __device__ __forceinline__ void make_point(PointFwd &pt, const LevelInfo &lv, in
   pt.w[3] = (yb && xr) ? f.fx * f.fy * a : 0.f;
 }
 
+// tuning knobs (A/B builds: tools/msda_variants.sh): minimum resident blocks per SM the register allocation is held to, and
+// sampling points per loop iteration (4 corner loads each)
+// Measured (tools/msda_variants.sh, profiles/r2y_msda_variants.jsonl; outputs bit-identical in every variant): holding the
+// forward to 6 blocks per SM (40 registers instead of 43) is 5-14 % faster on the two real shapes; 7 blocks (32 registers,
+// 16 bytes of spills) gains another 4-6 % with bf16 values and loses 5-8 % with f32 ones, hence the dtype-dependent bound.
+#ifndef ASIS_MSDA_FWD_MINB
+#define ASIS_MSDA_FWD_MINB (sizeof(VT) == 2 ? 7 : 6)
+#endif
+#ifndef ASIS_MSDA_FWD_UNROLL
+#define ASIS_MSDA_FWD_UNROLL 2
+#endif
+#define ASIS_MSDA_PRAGMA(x) _Pragma(#x)
+#define ASIS_MSDA_UNROLL(n) ASIS_MSDA_PRAGMA(unroll n)
 template <typename VT, int CPL, int GP>
-__global__ void __launch_bounds__(256) msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ ss,
+__global__ void __launch_bounds__(256, ASIS_MSDA_FWD_MINB) msda_fwd_kernel(const VT *__restrict__ value, const int64_t *__restrict__ ss,
                                                        const int64_t *__restrict__ lsi,
                                                        const float *__restrict__ loc, const float *__restrict__ aw,
                                                        VT *__restrict__ out, int S, int M, int D, int Lq, int L,
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const VT *__restrict__ va
   float acc[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
-#pragma unroll 2
+  ASIS_MSDA_UNROLL(ASIS_MSDA_FWD_UNROLL)
   for (int lp = 0; lp < LP; ++lp) {
     const uint4 o = *reinterpret_cast<const uint4 *>(mine[lp].off);
     const float4 w = *reinterpret_cast<const float4 *>(mine[lp].w);
@@ -238,8 +251,11 @@ struct __align__(16) PointBwd {
   float fx, fy, aw_w, aw_h;   // fractions; attention weight * level width / height (d pixel / d loc)
 };
 
+#ifndef ASIS_MSDA_LOCAW_MINB
+#define ASIS_MSDA_LOCAW_MINB 1      // (measured: 5 / 6 blocks per SM spill 24-132 bytes and are 2-20 % slower)
+#endif
 template <typename VT, int CPL, int GP, bool FULL>   // FULL: D == 16 * GP, every lane vector is live
-__global__ void __launch_bounds__(256) msda_bwd_locaw_kernel(const VT *__restrict__ value, const int64_t *__restrict__ ss,
+__global__ void __launch_bounds__(256, ASIS_MSDA_LOCAW_MINB) msda_bwd_locaw_kernel(const VT *__restrict__ value, const int64_t *__restrict__ ss,
                                                              const int64_t *__restrict__ lsi,
                                                              const float *__restrict__ loc,
                                                              const float *__restrict__ aw,
@@ -562,11 +578,47 @@ __global__ void __launch_bounds__(32) msda_bwd_fill_kernel(const int64_t *__rest
 // stored order and accumulates weight * grad_out[query] over its CPL channels; every grad_value
 // element is written exactly once.
 // ---------------------------------------------------------------------------------------------
+#ifndef ASIS_MSDA_GATHER_U
+#define ASIS_MSDA_GATHER_U 4        // grad_out rows in flight per lane
+#endif
+#ifndef ASIS_MSDA_GATHER_WIDE
+#define ASIS_MSDA_GATHER_WIDE 0     // > 0: long entry lists first run in unmasked steps of this many rows
+#endif
+// UU entries starting at e: entry loads are uniform over the group (one broadcast transaction each); entries past
+// the end are clamped to the last one and masked, so all UU row loads are unconditional.  The entries are accumulated
+// in their stored order whatever UU is: the result does not depend on the step width.
+template <typename GT, int CPL, int UU>
+__device__ __forceinline__ void gather_rows(const int2 *__restrict__ entries, const char *gb, int e, int end, float (&acc)[CPL]) {
+  typedef typename VecIO<CPL, GT>::Raw Raw;
+  int2 t[UU];
+  Raw r[UU];
+#pragma unroll
+  for (int u = 0; u < UU; ++u) t[u] = __ldg(entries + min(e + u, end - 1));
+#pragma unroll
+  for (int u = 0; u < UU; ++u) r[u] = load_raw_v<CPL>(reinterpret_cast<const GT *>(gb + (unsigned)t[u].x));
+#pragma unroll
+  for (int u = 0; u < UU; ++u) {
+    float v[CPL];
+    VecIO<CPL, GT>::unpack(r[u], v);
+    const float w = (e + u < end) ? __int_as_float(t[u].y) : 0.f;
+    if (e + u < end) {
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) acc[i] = fmaf(w, v[i], acc[i]);
+    }
+  }
+}
+
+// (measured: 6 blocks per SM -- 40 registers instead of 50 / 72, 8-28 bytes of spills -- backward 7-16 % faster; 8 rows in flight
+//  per lane, with or without an unmasked wide loop for long lists, 5-17 % slower: occupancy, not loads in flight, is what
+//  this kernel lacks)
+#ifndef ASIS_MSDA_GATHER_MINB
+#define ASIS_MSDA_GATHER_MINB 6
+#endif
 template <typename GT, int CPL, int GP>
-__global__ void __launch_bounds__(256) msda_bwd_gather_kernel(const GT *__restrict__ gout, const int *__restrict__ pixptr,
+__global__ void __launch_bounds__(256, ASIS_MSDA_GATHER_MINB) msda_bwd_gather_kernel(const GT *__restrict__ gout, const int *__restrict__ pixptr,
                                                               const int2 *__restrict__ entries,
                                                               GT *__restrict__ gvalue, int S, int M, int D, int Lq) {
-  constexpr int U = 4;                        // grad_out rows in flight per lane
+  constexpr int U = ASIS_MSDA_GATHER_U;
   const int G = D / CPL;
   const int g = threadIdx.x % GP;
   const int s = blockIdx.x * (blockDim.x / GP) + threadIdx.x / GP;
@@ -578,30 +630,13 @@ __global__ void __launch_bounds__(256) msda_bwd_gather_kernel(const GT *__restri
   const int end = __ldg(pp + 1);
   const size_t MD = (size_t)M * D;
   const char *gb = reinterpret_cast<const char *>(gout + (size_t)n * Lq * MD + (size_t)m * D + CPL * g);
-  typedef typename VecIO<CPL, GT>::Raw Raw;
   float acc[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
-  for (; e < end; e += U) {
-    // entry loads are uniform over the group (one broadcast transaction each); entries past the
-    // end are clamped to the last one and masked, so all U row loads are unconditional
-    int2 t[U];
-    Raw r[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) t[u] = __ldg(entries + min(e + u, end - 1));
-#pragma unroll
-    for (int u = 0; u < U; ++u) r[u] = load_raw_v<CPL>(reinterpret_cast<const GT *>(gb + (unsigned)t[u].x));
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      float v[CPL];
-      VecIO<CPL, GT>::unpack(r[u], v);
-      const float w = (e + u < end) ? __int_as_float(t[u].y) : 0.f;
-      if (e + u < end) {
-#pragma unroll
-        for (int i = 0; i < CPL; ++i) acc[i] = fmaf(w, v[i], acc[i]);
-      }
-    }
-  }
+#if ASIS_MSDA_GATHER_WIDE > 0
+  for (; e + ASIS_MSDA_GATHER_WIDE <= end; e += ASIS_MSDA_GATHER_WIDE) gather_rows<GT, CPL, ASIS_MSDA_GATHER_WIDE>(entries, gb, e, end, acc);
+#endif
+  for (; e < end; e += U) gather_rows<GT, CPL, U>(entries, gb, e, end, acc);
   if (lane_on) VecIO<CPL, GT>::store(gvalue + ((size_t)n * S + s) * MD + (size_t)m * D + CPL * g, acc);
 }
 
