@@ -162,10 +162,21 @@ __global__ void __launch_bounds__(kLnWarps * 32, 2) ln_bwd_kernel(const DT *__re
 // (row data stays in registers between the row reduction and the dx pass), and the loads of all
 // kLn2Rows rows are in flight together.  Row sums: warp shuffles, then one shared-memory exchange per
 // iteration (double buffered: one __syncthreads per kLn2Rows rows).
-constexpr int kLn2Rows = 4;
+// Tuning knobs (A/B builds, tools/ln_variants.sh, profiles/r2y_ln_variants.md): rows per block iteration and resident
+// blocks per SM (= grid / 148).  4 rows x 3 blocks (80 registers, 28-40 bytes of spills) was the first setting: 78.9 us
+// for [21168 x 1024] with the fused residual gradient; 2 rows x 4 blocks (59 registers, no spills): 68.6 us = 4.4 TB/s,
+// [83388 x 1024] 253 -> 218 us = 5.5 TB/s; 2 x 5 the same, 2 x 6 / 4 x 4 spill 100+ bytes and are slower, 1 x 8 no gain.
+#ifndef ASIS_LN_BWD_ROWS
+#define ASIS_LN_BWD_ROWS 2
+#endif
+#ifndef ASIS_LN_BWD_MINB
+#define ASIS_LN_BWD_MINB 4
+#endif
+constexpr int kLn2Rows = ASIS_LN_BWD_ROWS;
+constexpr int kLn2Blocks = ASIS_LN_BWD_MINB * 148;
 
 template <typename DT, typename XT>
-__global__ void __launch_bounds__(256, 3) ln_bwd2_kernel(const DT *__restrict__ dy, const XT *__restrict__ x,
+__global__ void __launch_bounds__(256, ASIS_LN_BWD_MINB) ln_bwd2_kernel(const DT *__restrict__ dy, const XT *__restrict__ x,
                                                       const float *__restrict__ gamma, const float *__restrict__ mean,
                                                       const float *__restrict__ rstd, const float *__restrict__ dres,
                                                       float *__restrict__ dx, float *__restrict__ partial, int R, int C) {
@@ -248,7 +259,7 @@ __global__ void __launch_bounds__(256, 3) ln_bwd2_kernel(const DT *__restrict__ 
 // (columns [n, 2n) go to out2 when it is given: dgamma and dbeta of LayerNorm in one launch)
 // block = 32 columns x PL part-lanes: part-lane y sums parts y, y+PL, ... (coalesced 128-byte rows, four loads in
 // flight), the PL part sums are combined through shared memory in a fixed order.  PL = 32 for long part lists (the
-// 444 block partials of the LayerNorm backward: with 8 lanes each thread walked 55 parts, ~14 dependent load rounds
+// 444-592 block partials of the LayerNorm backward: with 8 lanes each thread walked 55 parts, ~14 dependent load rounds
 // = 9.6 us for 3.6 MB; 113 launches per step), 8 otherwise.
 template <int PL>
 __global__ void __launch_bounds__(32 * PL) reduce_partials_kernel(const float *__restrict__ partial, int nparts, int stride,
@@ -488,7 +499,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(const __grid_constant__ SgdTab
 
 static int ln_bwd_blocks(int R) {
   const int want = (R + kLn2Rows - 1) / kLn2Rows;
-  return want < 444 ? want : 444;  // 3 resident blocks x 148 SMs (persistent)
+  return want < kLn2Blocks ? want : kLn2Blocks;  // resident blocks x 148 SMs (persistent)
 }
 
 }  // namespace asis
