@@ -43,45 +43,62 @@ __device__ __forceinline__ int find_map(const Maps &mp, int tok) {
   return i;
 }
 
-// one thread per (b, token, 4 channels)
+// one thread per (b, token, 4 channels), kDwIter such items per thread.
+// The nine taps of all channels sit transposed in shared memory ([9][C], filled with coalesced loads): read from the
+// [C][9] parameter directly, a warp's tap load touches 32 different 128-byte lines (stride 36 bytes x 4 channels), 36 such
+// loads per thread -- the first version spent its time there (210 us per [12, 6949, 256] bf16 call, 14x the copy
+// roofline).  The nine neighbour loads are unconditional (clamped coordinates, the tap zeroed outside the map), so they
+// are all in flight together instead of one per resolved branch.
+constexpr int kDwIter = 4;
 template <typename T>
 __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const T *__restrict__ x, const float *__restrict__ weight,
                                                          const float *__restrict__ bias, T *__restrict__ pre,
                                                          T *__restrict__ y, int B, int C, int ntok, Maps mp,
                                                          int fuse_gelu) {
+  extern __shared__ __align__(16) float dw_taps[];     // [9][C]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) dw_taps[(i % 9) * C + i / 9] = __ldg(weight + i);
+  __syncthreads();
   const int cv = C / 4;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)B * ntok * cv) return;
-  const int c = (int)(i % cv) * 4;
-  const int tok = (int)((i / cv) % ntok);
-  const int b = (int)(i / ((int64_t)cv * ntok));
-  const int mi = find_map(mp, tok);
-  const int W = mp.w[mi], H = mp.h[mi], t0 = mp.start[mi];
-  const int py = (tok - t0) / W, px = (tok - t0) % W;
-  float acc[4];
-  load4(bias + c, acc);
-  const T *xb = x + ((int64_t)b * ntok + t0) * C + c;
+  const int64_t total = (int64_t)B * ntok * cv;
+  for (int it = 0; it < kDwIter; ++it) {
+    const int64_t i = ((int64_t)blockIdx.x * kDwIter + it) * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % cv) * 4;
+    const int tok = (int)((i / cv) % ntok);
+    const int b = (int)(i / ((int64_t)cv * ntok));
+    const int mi = find_map(mp, tok);
+    const int W = mp.w[mi], H = mp.h[mi], t0 = mp.start[mi];
+    const int py = (tok - t0) / W, px = (tok - t0) % W;
+    float acc[4];
+    load4(bias + c, acc);
+    const T *xb = x + ((int64_t)b * ntok + t0) * C + c;
+    float v[9][4];
+    bool ok[9];
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int yy = py + dy - 1;
-    if (yy < 0 || yy >= H) continue;
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int xx = px + dx - 1;
-      if (xx < 0 || xx >= W) continue;
-      float v[4];
-      load4(xb + (int64_t)(yy * W + xx) * C, v);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[k] += v[k] * __ldg(weight + (c + k) * 9 + dy * 3 + dx);
+    for (int j = 0; j < 9; ++j) {
+      const int yy = py + j / 3 - 1, xx = px + j % 3 - 1;
+      ok[j] = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const int yc = min(max(yy, 0), H - 1), xc = min(max(xx, 0), W - 1);
+      load4(xb + (int64_t)(yc * W + xc) * C, v[j]);
     }
-  }
-  const int64_t o = ((int64_t)b * ntok + tok) * C + c;
-  if (fuse_gelu) {
-    if (pre) store4(pre + o, acc);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) acc[k] = gelu_erf(acc[k]);
+    for (int j = 0; j < 9; ++j) {      // same order and the same fused multiply-adds as a loop that skips the outside taps
+      const float4 w4 = *reinterpret_cast<const float4 *>(dw_taps + j * C + c);
+      if (ok[j]) {
+        acc[0] += v[j][0] * w4.x;
+        acc[1] += v[j][1] * w4.y;
+        acc[2] += v[j][2] * w4.z;
+        acc[3] += v[j][3] * w4.w;
+      }
+    }
+    const int64_t o = ((int64_t)b * ntok + tok) * C + c;
+    if (fuse_gelu) {
+      if (pre) store4(pre + o, acc);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = gelu_erf(acc[k]);
+    }
+    store4(y + o, acc);
   }
-  store4(y + o, acc);
 }
 
 // g = dy * GELU'(pre), once per element: the 3x3 backward below reads the gradient at 9 neighbours, and
@@ -100,12 +117,15 @@ __global__ void __launch_bounds__(256) dwconv_gelu_grad_kernel(const T *__restri
 }
 
 // backward: block = 32 channel-lanes (128 channels) x 8 token-lanes; grid (C/128, token blocks).
-// dx per element; per-block partial dweight/dbias -> workspace[block_y][10][C]
+// dx per element; per-block partial dweight/dbias -> workspace[block_y][10][C].  `g` is the gradient w.r.t. the
+// convolution output (the host multiplies by GELU' first when the activation was fused).  The 18 neighbour loads of a
+// token (x and g at the nine clamped positions) are unconditional and issued together; positions outside the map are
+// skipped in the arithmetic only (the first version loaded under the bounds branches, one load in flight at a time:
+// 318 us per [12, 6949, 256] bf16 call).
 template <typename T>
-__global__ void __launch_bounds__(256) dwconv_bwd_kernel(const T *__restrict__ dy_, const T *__restrict__ pre,
-                                                         const T *__restrict__ x, const float *__restrict__ weight,
-                                                         T *__restrict__ dx_, float *__restrict__ partial, int B, int C,
-                                                         int ntok, Maps mp, int fuse_gelu) {
+__global__ void __launch_bounds__(256) dwconv_bwd_kernel(const T *__restrict__ g_, const T *__restrict__ x,
+                                                         const float *__restrict__ weight, T *__restrict__ dx_,
+                                                         float *__restrict__ partial, int B, int C, int ntok, Maps mp) {
   __shared__ float red[8][132];
   const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + lane * 4;
@@ -129,45 +149,32 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const T *__restrict__ d
     const int W = mp.w[mi], H = mp.h[mi], t0 = mp.start[mi];
     const int py = (tok - t0) / W, px = (tok - t0) % W;
     const int64_t base = ((int64_t)b * ntok + t0) * C + c;
-    // gradient w.r.t. the conv output at this token
     float g[4];
-    load4(dy_ + r * C + c, g);
-    if (fuse_gelu) {
-      float h[4];
-      load4(pre + r * C + c, h);
+    load4(g_ + r * C + c, g);
+    // position j = (py + j/3 - 1, px + j%3 - 1): the input neighbour of tap j, and the output pixel that used this
+    // token with tap 8 - j
+    float xv[9][4], gv[9][4];
+    bool ok[9];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) g[k] *= dgelu_erf(h[k]);
+    for (int j = 0; j < 9; ++j) {
+      const int yy = py + j / 3 - 1, xx = px + j % 3 - 1;
+      ok[j] = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const int64_t off = base + (int64_t)(min(max(yy, 0), H - 1) * W + min(max(xx, 0), W - 1)) * C;
+      load4(x + off, xv[j]);
+      load4(g_ + off, gv[j]);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) dw[9][k] += g[k];
     float dxv[4] = {0, 0, 0, 0};
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
+    for (int j = 0; j < 9; ++j) {      // (same order of accumulation as the branchy version: tap j, then input tap j)
+      if (ok[j]) {
 #pragma unroll
-      for (int dxo = 0; dxo < 3; ++dxo) {
-        // weight gradient: input neighbour (py+dy-1, px+dxo-1) times g
-        const int yy = py + dy - 1, xx = px + dxo - 1;
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-          float v[4];
-          load4(x + base + (int64_t)(yy * W + xx) * C, v);
+        for (int k = 0; k < 4; ++k) dw[j][k] += g[k] * xv[j][k];
+      }
+      if (ok[8 - j]) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) dw[dy * 3 + dxo][k] += g[k] * v[k];
-        }
-        // input gradient: output neighbour (py-dy+1, px-dxo+1) used this token with tap (dy, dxo)
-        const int oy = py - dy + 1, ox = px - dxo + 1;
-        if (oy >= 0 && oy < H && ox >= 0 && ox < W) {
-          const int64_t orow = (int64_t)b * ntok + t0 + oy * W + ox;
-          float go[4];
-          load4(dy_ + orow * C + c, go);
-          if (fuse_gelu) {
-            float h[4];
-            load4(pre + orow * C + c, h);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) go[k] *= dgelu_erf(h[k]);
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dxv[k] += go[k] * wv[dy * 3 + dxo][k];
-        }
+        for (int k = 0; k < 4; ++k) dxv[k] += gv[8 - j][k] * wv[j][k];
       }
     }
     store4(dx_ + r * C + c, dxv);
@@ -219,9 +226,11 @@ static int make_maps(Maps &mp, int n_maps, const int *hs, const int *ws) {
   return ASIS_OK;
 }
 
-static int dwconv_row_blocks(int64_t rows) {
+// token blocks of the backward: one wave of 2 resident blocks (128 registers) on each of the 148 SMs over all channel blocks
+static int dwconv_row_blocks(int64_t rows, int C) {
   int64_t rb = (rows + 63) / 64;
-  if (rb > 256) rb = 256;
+  const int cap = std::max(1, 296 / ((C + 127) / 128));
+  if (rb > cap) rb = cap;
   if (rb < 1) rb = 1;
   return (int)rb;
 }
@@ -415,15 +424,17 @@ extern "C" int asis_dwconv3x3_forward(const void *x, int dtype, const float *wei
   if (int rc = make_maps(mp, n_maps, hs_host, ws_host)) return rc;
   const int ntok = mp.start[kMaxMaps];
   const int64_t total = (int64_t)B * ntok * (C / 4);
-  const unsigned blocks = (unsigned)((total + 255) / 256);
+  ASIS_REQUIRE(C <= 1280, "dwconv_forward: C=%d > 1280 (the taps of all channels are staged in 36 C bytes of shared memory)", C);
+  const unsigned blocks = (unsigned)((total + 256 * kDwIter - 1) / (256 * kDwIter));
+  const size_t smem = (size_t)9 * C * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
-  ASIS_DISPATCH_DTYPE(dtype, T, (dwconv_fwd_kernel<T><<<blocks, 256, 0, st>>>((const T *)x, weight, bias, (T *)pre, (T *)y, B, C, ntok, mp, fuse_gelu)));
+  ASIS_DISPATCH_DTYPE(dtype, T, (dwconv_fwd_kernel<T><<<blocks, 256, smem, st>>>((const T *)x, weight, bias, (T *)pre, (T *)y, B, C, ntok, mp, fuse_gelu)));
   ASIS_LAUNCHED();
   return ASIS_OK;
 }
 
 static size_t dwconv_partial_bytes(int B, int C, int n_tok) {
-  return align_up((size_t)dwconv_row_blocks((int64_t)B * n_tok) * 10 * C * sizeof(float), 256);
+  return align_up((size_t)dwconv_row_blocks((int64_t)B * n_tok, C) * 10 * C * sizeof(float), 256);
 }
 
 // column partials + one [B, n_tok, C] buffer for dy * GELU'(pre) (sized for f32)
@@ -444,7 +455,7 @@ extern "C" int asis_dwconv3x3_backward(const void *dy, const void *pre, const vo
   const int ntok = mp.start[kMaxMaps];
   const size_t need = asis_dwconv3x3_backward_workspace_bytes(B, C, ntok);
   if (workspace_bytes < need) ASIS_FAIL(ASIS_ERR_WORKSPACE, "dwconv_backward: workspace %zu < %zu bytes", workspace_bytes, need);
-  const int rb = dwconv_row_blocks((int64_t)B * ntok);
+  const int rb = dwconv_row_blocks((int64_t)B * ntok, C);
   dim3 grid((C + 127) / 128, rb);
   cudaStream_t st = (cudaStream_t)stream;
   float *partial = (float *)workspace;
@@ -454,9 +465,8 @@ extern "C" int asis_dwconv3x3_backward(const void *dy, const void *pre, const vo
     ASIS_DISPATCH_DTYPE(dtype, T, (dwconv_gelu_grad_kernel<T><<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>((const T *)dy, (const T *)pre, (T *)gbuf, n4)));
     ASIS_LAUNCHED();
     dy = gbuf;
-    fuse_gelu = 0;
   }
-  ASIS_DISPATCH_DTYPE(dtype, T, (dwconv_bwd_kernel<T><<<grid, 256, 0, st>>>((const T *)dy, (const T *)pre, (const T *)x, weight, (T *)dx, partial, B, C, ntok, mp, fuse_gelu)));
+  ASIS_DISPATCH_DTYPE(dtype, T, (dwconv_bwd_kernel<T><<<grid, 256, 0, st>>>((const T *)dy, (const T *)x, weight, (T *)dx, partial, B, C, ntok, mp)));
   ASIS_LAUNCHED();
   dwconv_reduce_kernel<<<(10 * C + 255) / 256, 256, 0, st>>>(partial, rb, C, dweight, dbias, accumulate);
   ASIS_LAUNCHED();
