@@ -121,6 +121,39 @@ def test_host_side_validation_round2_entry_points():
     assert rc == -1 and b"null pointer" in lib.asis_last_error()
 
 
+def test_host_side_validation_last_build_entry_points():
+    """Host logic touched by the last build of round 2: the depth-wise convolution stages its taps in shared memory
+    (channel limit reported, not silently exceeded), its backward workspace follows the one-wave grid, and the
+    LayerNorm backward workspace follows the 4-blocks-per-SM grid."""
+    import ctypes
+    from adaptersis_b200 import _lib
+    lib = _lib.load()
+    fake = ctypes.c_void_p(256)
+    hs = (ctypes.c_int * 2)(7, 4)
+    ws = (ctypes.c_int * 2)(5, 3)
+    rc = lib.asis_dwconv3x3_forward(fake, 1, fake, fake, None, fake, 2, 1284, 2, hs, ws, 1, None)
+    assert rc == -1 and b"1280" in lib.asis_last_error()
+    rc = lib.asis_dwconv3x3_forward(fake, 1, fake, fake, None, fake, 2, 66, 2, hs, ws, 1, None)
+    assert rc == -1 and b"multiple of 4" in lib.asis_last_error()
+    rc = lib.asis_dwconv3x3_forward(fake, 1, fake, fake, None, fake, 2, 64, 0, hs, ws, 1, None)
+    assert rc == -1 and b"maps required" in lib.asis_last_error()
+    # backward: partials of at most 296 blocks over all channel blocks (one wave of two blocks per SM) + the GELU' buffer
+    for C, ntok in ((256, 6949), (64, 47), (1024, 6949)):
+        need = lib.asis_dwconv3x3_backward_workspace_bytes(12, C, ntok)
+        rows = 12 * ntok
+        rb = min((rows + 63) // 64, max(1, 296 // ((C + 127) // 128)))
+        assert need == (rb * 10 * C * 4 + 255) // 256 * 256 + 12 * ntok * C * 4, (C, ntok, need)
+    rc = lib.asis_dwconv3x3_backward(fake, fake, fake, 1, fake, fake, fake, fake, 0, 12, 256, 2, hs, ws, 1, fake, 16, None)
+    assert rc != 0 and b"workspace" in lib.asis_last_error()
+    # LayerNorm backward: 2 rows per block iteration, at most 4 x 148 persistent blocks, two partial rows of C floats per block
+    assert lib.asis_layernorm_backward_workspace_bytes(21168, 1024) == 592 * 2 * 1024 * 4
+    assert lib.asis_layernorm_backward_workspace_bytes(100, 1024) == 50 * 2 * 1024 * 4
+    rc = lib.asis_layernorm_backward(fake, 1, fake, 0, fake, fake, fake, None, fake, None, None, 0, 64, 1024, fake, 16, None)
+    assert rc != 0 and b"workspace" in lib.asis_last_error()
+    rc = lib.asis_layernorm_backward(fake, 1, fake, 0, fake, fake, fake, None, fake, None, None, 0, 64, 2048, fake, 1 << 20, None)
+    assert rc != 0 and b"1024" in lib.asis_last_error()
+
+
 def test_no_cpu_fallback():
     import adaptersis_b200 as asis
     m = asis.MSDeformAttn(d_model=32, n_levels=1, n_heads=4, n_points=2)
